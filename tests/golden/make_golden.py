@@ -1,0 +1,216 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own modules on seeded inputs.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Each fixture stores the inputs and what the reference classes returned (outputs and autograd
+gradients).  The fixtures are committed; the GPU box replays them without the reference.
+Reference entry points exercised (paths relative to /root/reference):
+  * avssl/module/weighted_sum.py            WeightedSumLayer.forward                      (S1)
+  * avssl/model/kw_branches.py:158-197      GeneralBranch.get_keyword_cosine_score,
+                                            GeneralBranch.vq_audio_features (identity projection)  (V1, V4)
+  * avssl/module/speechclip_c_modules/my_vector_quantizer.py  SimpleVectorQuantizer.forward   (V3)
+  * avssl/module/losses.py:129-245          MaskedContrastiveLoss                          (S3)
+  * avssl/model/kwClip.py:999-1040          KWClip_GeneralTransformer.compute_loss         (C0)
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import _ref_import as ref  # noqa: E402
+
+SEED = 7122  # the reference's default seed, avssl/util/args.py:28
+
+
+def _gen(seed_offset: int) -> torch.Generator:
+    g = torch.Generator()
+    g.manual_seed(SEED + seed_offset)
+    return g
+
+
+def _np(t):
+    if torch.is_tensor(t):
+        return t.detach().cpu().numpy()
+    return np.asarray(t)
+
+
+def save(name: str, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **{k: _np(v) for k, v in arrays.items()})
+    print(f"wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+# ----------------------------------------------------------------------------------------------
+def golden_wsum():
+    ws = ref.load_leaf("avssl/module/weighted_sum.py", "ref_weighted_sum")
+    cases = [
+        # name, L, B, T, D, normalize, zero_weights
+        ("wsum_base_plain", 13, 2, 7, 768, False, False),
+        ("wsum_base_zero_w", 13, 2, 5, 768, False, True),
+        ("wsum_large_norm", 25, 2, 5, 1024, True, False),
+        ("wsum_small_norm", 4, 3, 9, 192, True, False),
+    ]
+    for i, (name, L, B, T, D, norm, zero_w) in enumerate(cases):
+        g = _gen(100 + i)
+        # HuBERT hands over (T,B,D)-storage tensors viewed as (B,T,D): speech_encoder_plus.py:596-599
+        storage = [torch.randn(T, B, D, generator=g) * (1.0 + 0.3 * l) + 0.1 * l for l in range(L)]
+        layers = [s.transpose(0, 1).requires_grad_(True) for s in storage]
+        layer = ws.WeightedSumLayer(n_weights=L, normalize_features=norm)
+        if not zero_w:
+            with torch.no_grad():
+                layer.weights.copy_(torch.randn(L, generator=g) * 0.5)
+        y = layer(layers)
+        gy = torch.randn(B, T, D, generator=g)
+        grads = torch.autograd.grad(y, [layer.weights] + layers, grad_outputs=gy)
+        save(name, layers_tbd=torch.stack(storage), weights=layer.weights, normalize=np.array(norm),
+             y=y, grad_y=gy, grad_weights=grads[0], grad_layers=torch.stack([x for x in grads[1:]]))
+
+
+# ----------------------------------------------------------------------------------------------
+def _fake_branch(kb, vq_mod, table: torch.Tensor, temp_spec: str, training: bool):
+    """A GeneralBranch whose projection is the identity, so that vq_audio_features (kw_branches.py:181-197)
+    runs V1 + V3 + V4 of the reference on the given keyword vectors."""
+    branch = kb.GeneralBranch.__new__(kb.GeneralBranch)
+    torch.nn.Module.__init__(branch)
+    branch.text_dim = table.shape[1]
+    emb = torch.nn.Embedding(table.shape[0], table.shape[1])
+    with torch.no_grad():
+        emb.weight.copy_(table)
+    emb.weight.requires_grad_(False)
+    branch.clip = types.SimpleNamespace(model=types.SimpleNamespace(token_embedding=emb))
+    branch.linear_proj = torch.nn.Identity()
+    branch.vector_quantizer = vq_mod.SimpleVectorQuantizer(temp=temp_spec)
+    branch.train(training)
+    return branch
+
+
+def golden_vq():
+    ref.import_avssl()
+    import avssl.model.kw_branches as kb
+    vq_mod = ref.load_leaf("avssl/module/speechclip_c_modules/my_vector_quantizer.py", "ref_vq")
+    cases = [
+        # name, B, K, V, D, temp_spec, training, duplicate rows in the table
+        ("vq_train_fixed", 3, 4, 512, 64, "fixed=0.1", True, False),
+        ("vq_eval_fixed", 3, 4, 512, 64, "fixed=0.1", False, False),
+        ("vq_train_learnable", 2, 8, 1024, 128, "learnable=0.07", True, False),
+        ("vq_train_ties", 2, 3, 260, 64, "fixed=0.1", True, True),
+    ]
+    for i, (name, B, K, V, D, temp_spec, training, dup) in enumerate(cases):
+        g = _gen(200 + i)
+        table = torch.randn(V, D, generator=g) * 0.02 + 0.003 * torch.randn(1, D, generator=g)
+        if dup:
+            # exact duplicates -> exact ties: "first max wins" must hold (my_vector_quantizer.py:82)
+            table[17] = table[200]
+            table[5] = table[200]
+        # keywords mimic the batch-norm output initialised to table mean/std (kw_branches.py:99-100)
+        kw = torch.randn(B, K, D, generator=g) * table.std(0) + table.mean(0)
+        if dup:
+            kw[0, 0] = table[200] * 3.0
+            kw[1, 2] = table[2] * 2.0  # best raw match is a masked column (2): must not be selected
+        kw.requires_grad_(True)
+        branch = _fake_branch(kb, vq_mod, table, temp_spec, training)
+        cos = branch.get_keyword_cosine_score(kw.detach())
+        vq_results, kw_out = branch.vq_audio_features(kw)
+        arrays = dict(keywords_in=kw, table=table, training=np.array(training), temp_spec=np.array(temp_spec),
+                      cos=cos, keywords_out=kw_out, subword_prob=vq_results["subword_prob"],
+                      targets=vq_results["targets"], code_perplexity=vq_results["code_perplexity"],
+                      prob_perplexity=vq_results["prob_perplexity"], ent_per_t=vq_results["ent_per_t"],
+                      temp=np.array(vq_results["temp"]), diversity_loss=vq_results["diversity_loss"],
+                      num_vars=np.array(vq_results["num_vars"]))
+        if training:
+            g_out = torch.randn(B, K, D, generator=g)
+            params = [kw]
+            if temp_spec.startswith("learnable"):
+                params.append(branch.vector_quantizer.curr_temp)
+            grads = torch.autograd.grad(kw_out, params, grad_outputs=g_out)
+            arrays.update(grad_keywords_out=g_out, grad_keywords_in=grads[0])
+            if len(grads) > 1:
+                arrays.update(grad_temp=grads[1])
+        save(name, **arrays)
+
+
+# ----------------------------------------------------------------------------------------------
+def golden_nce():
+    losses = ref.load_leaf("avssl/module/losses.py", "ref_losses")
+    cases = [
+        # name, N, D, ctor kwargs, ids kind
+        ("nce_n8_trainable", 8, 64, dict(temperature=0.07, temperature_trainable=True), "unique"),
+        ("nce_n48_dupids", 48, 64, dict(temperature=0.07, temperature_trainable=True), "dup"),
+        ("nce_n48_fixed_margin", 48, 128, dict(temperature=0.1, temperature_trainable=False, margin=0.2), "dup"),
+        ("nce_n40_dcl", 40, 64, dict(temperature=0.07, temperature_trainable=True, dcl=True), "dup"),
+        ("nce_n40_a2b_only", 40, 64, dict(temperature=0.07, temperature_trainable=True, b2a=False), "dup"),
+        ("nce_n40_b2a_noindex", 40, 64, dict(temperature=0.07, temperature_trainable=True, a2b=False), "none"),
+        ("nce_n300_big", 300, 64, dict(temperature=0.07, temperature_trainable=True), "dup"),
+    ]
+    for i, (name, N, D, kw, ids_kind) in enumerate(cases):
+        g = _gen(300 + i)
+        a = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=-1).requires_grad_(True)
+        b = torch.nn.functional.normalize(torch.randn(N, D, generator=g) + 0.5 * a.detach(), dim=-1).requires_grad_(True)
+        if ids_kind == "unique":
+            ids = torch.arange(N)
+        elif ids_kind == "dup":
+            ids = torch.randint(0, max(N // 5, 1), (N,), generator=g)  # Flickr: 5 captions per image
+        else:
+            ids = None
+        if N > losses.MAX_EYE:
+            losses.MAX_EYE = N  # reference limit losses.py:126 (IndexError for N > 256)
+        crit = losses.MaskedContrastiveLoss(**kw)
+        loss = crit(a, b, ids)
+        params = [a, b] + ([crit.temperature] if kw.get("temperature_trainable") else [])
+        grads = torch.autograd.grad(loss, params)
+        arrays = dict(feat_a=a, feat_b=b, ids=ids if ids is not None else np.array([-1]),
+                      has_ids=np.array(ids is not None), loss=loss, grad_a=grads[0], grad_b=grads[1],
+                      temperature=np.array(kw["temperature"]), trainable=np.array(kw.get("temperature_trainable", False)),
+                      margin=np.array(kw.get("margin", 0.0)), dcl=np.array(kw.get("dcl", False)),
+                      a2b=np.array(kw.get("a2b", True)), b2a=np.array(kw.get("b2a", True)),
+                      current_temperature=np.array(crit.current_temperature))
+        if len(grads) > 2:
+            arrays["grad_temperature"] = grads[2]
+        save(name, **arrays)
+
+
+# ----------------------------------------------------------------------------------------------
+def golden_hybrid_loss():
+    ref.import_avssl()
+    import avssl.model.kwClip as kc
+    losses = ref.load_leaf("avssl/module/losses.py", "ref_losses2")
+    g = _gen(400)
+    N, D = 32, 64
+    img = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=-1)
+    ca = torch.nn.functional.normalize(torch.randn(N, D, generator=g) + img, dim=-1).requires_grad_(True)
+    pa = torch.nn.functional.normalize(torch.randn(N, D, generator=g) + 2 * img, dim=-1).requires_grad_(True)
+    ids = torch.randint(0, 8, (N,), generator=g)
+    qo = torch.rand(N, generator=g) * 10
+    ql = torch.randint(4, 12, (N,), generator=g).float()
+    fake = types.SimpleNamespace()
+    fake.config = types.SimpleNamespace(model_settings=types.SimpleNamespace(
+        cascaded_objective_weight=1.5, parallel_objective_weight=0.5))
+    fake.criterion = losses.MaskedContrastiveLoss(temperature=0.07, temperature_trainable=True)
+    fake.quantity_loss_criteria = torch.nn.L1Loss()
+    fake.quantity_loss_weight = 0.25
+    out = kc.KWClip_GeneralTransformer.compute_loss(
+        fake, {"id": ids, "image_feat": img, "cascaded_audio_feat": ca, "parallel_audio_feat": pa,
+               "cif_quantity_out": qo, "cif_target_len": ql})
+    grads = torch.autograd.grad(out["loss"], [ca, pa, fake.criterion.temperature])
+    save("hybrid_loss", image_feat=img, cascaded_audio_feat=ca, parallel_audio_feat=pa, ids=ids,
+         cif_quantity_out=qo, cif_target_len=ql, cascaded_weight=np.array(1.5), parallel_weight=np.array(0.5),
+         quantity_loss_weight=np.array(0.25), temperature=np.array(0.07),
+         loss=out["loss"], c_cl_loss=out["c_cl_loss"], p_cl_loss=out["p_cl_loss"], quantity_loss=out["quantity_loss"],
+         grad_cascaded=grads[0], grad_parallel=grads[1], grad_temperature=grads[2])
+
+
+if __name__ == "__main__":
+    assert ref.reference_available(), "needs /root/reference"
+    torch.set_num_threads(max(os.cpu_count() or 1, 1))
+    golden_wsum()
+    golden_vq()
+    golden_nce()
+    golden_hybrid_loss()
