@@ -1,0 +1,167 @@
+/*
+ * scp_b200.h -- C ABI of libscp_b200.so: the SpeechCLIP+ data-parallel training hot path on B200 (sm_100a).
+ *
+ * Drop-in boundary.  The reference (ShampooWang/SpeechCLIP_plus) is pure Python: its "plugin API" for this path
+ * is getattr-by-name on Python modules (avssl/model/kwClip.py:84, avssl/model/kw_branches.py:75-91) plus the
+ * WeightedSumLayer constructor (avssl/module/speech_encoder_plus.py:218-220, :472-476).  It has no FFI of its
+ * own; the entry points below are what a ctypes binding for the three hot-path classes binds, one group per
+ * reference class.  The Python mirror of the reference interface lives in speechclip_plus_b200/ and calls
+ * these through ctypes (see INTEGRATION.md for the reference-side stub).
+ *
+ * Conventions
+ *   - every function returns 0 (SCP_OK) or a negative SCP_ERR_* code; scp_last_error_string() explains it.
+ *   - never throws, never allocates device memory, never synchronises the device or the stream:
+ *     scratch space is caller-provided (query the size with the matching *_workspace_bytes function).
+ *   - all data pointers are DEVICE pointers valid on the stream's device unless marked "host".
+ *   - sizes are int64_t element counts; strides are in elements; the last dimension is contiguous.
+ *   - kernels are launched on `stream` (a cudaStream_t / CUstream); re-entrant, no global mutable state
+ *     except the lazily resolved driver entry point for tensor-map encoding.
+ *   - there is no CPU fallback: on a device that is not sm_100 the functions return SCP_ERR_ARCH.
+ */
+#ifndef SCP_B200_H_
+#define SCP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* scp_stream_t; /* == cudaStream_t */
+
+enum {
+  SCP_OK = 0,
+  SCP_ERR_INVALID = -1,     /* bad argument (null pointer, non-positive size, misaligned pointer) */
+  SCP_ERR_UNSUPPORTED = -2, /* shape / dtype combination this build has no kernel for */
+  SCP_ERR_WORKSPACE = -3,   /* workspace too small */
+  SCP_ERR_CUDA = -4,        /* a CUDA runtime / driver call failed (launch error, tensor-map encode ...) */
+  SCP_ERR_ARCH = -5         /* device is not compute capability 10.x */
+};
+
+enum { SCP_F32 = 0, SCP_F16 = 1, SCP_BF16 = 2 };
+
+#define SCP_MAX_LAYERS 32
+#define SCP_MAX_MASKED 8
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+int scp_version(void);                         /* MAJOR*10000 + MINOR*100 + PATCH */
+const char* scp_last_error_string(int code);   /* static string for `code`; detail of the last failure on this thread */
+int scp_num_launches(void);                    /* kernels launched by this library in this process (bench accounting) */
+
+/* ---- S1: upstream-feature fusion -- replaces WeightedSumLayer.forward (avssl/module/weighted_sum.py:26-45) -- */
+/* y[b,t,:] = sum_l softmax(weights)_l * LN?(x_l[b,t,:]).  layer_ptrs: HOST array of L device pointers; every layer
+ * is addressed as x_l[b*stride_b + t*stride_t + d] (the reference hands over (T,B,D) storage viewed as (B,T,D):
+ * avssl/module/speech_encoder_plus.py:596-599).  y is (B,T,D) contiguous.  layer_norm != 0 applies the non-affine
+ * LayerNorm of weighted_sum.py:41-42 to each layer before the sum. */
+int scp_wsum_fwd(const void* const* layer_ptrs, int L, int64_t B, int64_t T, int64_t D,
+                 int64_t stride_b, int64_t stride_t, int dtype_in,
+                 const float* weights, int layer_norm, float eps,
+                 void* y, int dtype_out, scp_stream_t stream);
+
+size_t scp_wsum_bwd_workspace_bytes(int L, int64_t B, int64_t T, int64_t D);
+
+/* Backward of the above.  d_weights[l] = d(loss)/d(weights_l) (softmax backward included).  g_layers: nullable HOST
+ * array of L device pointers to (B,T,D)-contiguous fp32 buffers receiving d(loss)/d(x_l) (only needed when the
+ * upstream encoder is trainable: avssl/module/speech_encoder_plus.py:416-446). */
+int scp_wsum_bwd(const void* const* layer_ptrs, int L, int64_t B, int64_t T, int64_t D,
+                 int64_t stride_b, int64_t stride_t, int dtype_in,
+                 const float* weights, int layer_norm, float eps,
+                 const void* g_y, int dtype_g, float* d_weights, void* const* g_layers,
+                 void* workspace, size_t workspace_bytes, scp_stream_t stream);
+
+/* ---- S2: keyword vector quantiser -- replaces GeneralBranch.get_keyword_cosine_score + SimpleVectorQuantizer.forward
+ *      + the lookup matmul (avssl/model/kw_branches.py:158-197, avssl/module/speechclip_c_modules/my_vector_quantizer.py:64-165) -- */
+
+/* One-time (per table version) preparation of the frozen CLIP token table E (V,D) fp32 row-major:
+ *   table_hat  (Vp,D)  f16 : rows normalised to unit L2 norm (eps 1e-8), zero rows for v >= V, Vp = round_up(V,256)
+ *   table_hat_t(D,Vp)  f16 : its transpose (K-major operand of the backward GEMM)
+ *   table_norm (Vp,)   f32 : max(||e_v||, 1e-8)
+ *   table_mean (D+1,)  f32 : mean_v e_v (centring vector of the backward pass); element [D] = max_v ||e_v||          */
+int64_t scp_vq_padded_vocab(int64_t V);
+int scp_vq_prepare_table(const float* table, int64_t V, int64_t D,
+                         void* table_hat, void* table_hat_t, float* table_norm, float* table_mean,
+                         scp_stream_t stream);
+
+size_t scp_vq_fwd_workspace_bytes(int64_t M, int64_t V, int64_t D);
+
+/* Forward.  kw (M,D) fp32 = keyword vectors in CLIP space, M = B*K rows ordered (b,k).
+ *   idx        (M,)  int64 : arg-max code per row, first maximum wins, masked columns excluded
+ *                            (bit-exact w.r.t. an exact evaluation of the cosine; see DESIGN.md "exact arg-max")
+ *   keywords   (M,D) f32   : E[idx]  (value of subword_prob @ E, kw_branches.py:195)
+ *   row_stats  (M,4) f32   : {lse at temperature 1, lse at temperature tau, entropy at temperature 1, 1/max(||kw||,1e-8)}
+ *   code_hist  (Vp,) f32   : histogram of idx (counts)
+ *   avg_probs  (Vp,) f32   : mean_m softmax(cos[m,:]) at temperature 1  (my_vector_quantizer.py:102); nullable -> skipped
+ *   metrics    (3+K,) f32  : {code_perplexity, prob_perplexity, diversity_loss, ent_per_t[0..K)}
+ *   kw_hat     (Mp,D) f16  : normalised keywords kept for the backward pass, Mp = round_up(M,128)
+ * masked_cols: HOST array of n_masked (<= SCP_MAX_MASKED) column ids that receive -inf (prob_msk). */
+int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int64_t D,
+               const void* table_hat, const float* table_norm, const float* table,
+               const int32_t* masked_cols, int n_masked, const float* tau,
+               int64_t* idx, float* keywords, float* row_stats, float* code_hist, float* avg_probs,
+               float* metrics, void* kw_hat,
+               void* workspace, size_t workspace_bytes, scp_stream_t stream);
+
+size_t scp_vq_bwd_workspace_bytes(int64_t M, int64_t V, int64_t D);
+
+/* Backward of the straight-through estimator (training mode):
+ *   g_p = g_keywords E^T ; g_c = p_tau (g_p - <p_tau,g_p>) / tau ; g_khat = g_c Ehat ;
+ *   g_kw = (g_khat - <g_khat,khat> khat) / ||kw||          
+ * g_tau (nullable, (1,) f32) receives d(loss)/d(tau) for a learnable temperature (finite closed form). */
+int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, int64_t V, int64_t D,
+               const void* kw_hat, const void* table_hat, const void* table_hat_t,
+               const float* table_norm, const float* table_mean, const float* row_stats,
+               const int32_t* masked_cols, int n_masked, const float* tau,
+               float* g_kw, float* g_tau,
+               void* workspace, size_t workspace_bytes, scp_stream_t stream);
+
+/* Dense-input form of SimpleVectorQuantizer.forward (my_vector_quantizer.py:64-165) for callers that already hold the
+ * (M,V) score matrix x (fp32, row pitch ldx).  Masks x IN PLACE like the reference (:78-79).  subword_prob (nullable,
+ * (M,V) f32 contiguous) receives the forward VALUE of `hard + p - p.detach()` / `hard`, i.e. the one-hot.  Outputs as in
+ * scp_vq_fwd (row_stats[.,3] unused; code_hist / avg_probs have V entries). */
+size_t scp_vq_dense_workspace_bytes(int64_t M, int64_t V);
+int scp_vq_dense_fwd(float* x, int64_t M, int64_t K, int64_t V, int64_t ldx,
+                     const int32_t* masked_cols, int n_masked, const float* tau, int training,
+                     int64_t* idx, float* row_stats, float* code_hist, float* avg_probs, float* metrics,
+                     float* subword_prob, void* workspace, size_t workspace_bytes, scp_stream_t stream);
+/* g_x (M,V contiguous) = p_tau * (g_p - <p_tau, g_p>) / tau for the dense form (g_p = d loss / d subword_prob, pitch ldg);
+ * g_tau nullable. */
+int scp_vq_dense_bwd(const float* x_masked, const float* g_p, int64_t M, int64_t V, int64_t ldx, int64_t ldg,
+                     const float* row_stats, const float* tau, float* g_x, float* g_tau, scp_stream_t stream);
+
+/* ---- N0 + G0: L2-normalise the loss features and pack them into the all-gather send buffer
+ *      (avssl/model/kwClip.py:857, :905-907, :913-915; gather point kwClip.py:149-169) -------------------- */
+/* packed layout per rank: n_feats blocks of (n,D) f32 followed by n int64 ids.  feats: HOST array of device ptrs.
+ * inv_norms (n_feats,n) f32 receives 1/||f|| for the backward of the normalisation. */
+size_t scp_pack_bytes(int n_feats, int64_t n, int64_t D);
+int scp_l2norm_pack(const void* const* feats, int n_feats, int64_t n, int64_t D, int dtype_in,
+                    const int64_t* ids, void* packed_out, float* inv_norms, scp_stream_t stream);
+/* backward of f/||f||: g_f = (g_n - <g_n,fhat> fhat) * inv_norm, all (n,D) f32 */
+int scp_l2norm_bwd(const float* g_n, const float* f_hat, const float* inv_norm, int64_t n, int64_t D,
+                   float* g_f, scp_stream_t stream);
+
+/* ---- S3: masked in-batch InfoNCE -- replaces MaskedContrastiveLoss.forward (avssl/module/losses.py:185-245) ---- */
+size_t scp_nce_workspace_bytes(int64_t N, int64_t D);
+
+/* A, Bm (N,D) f32, ids (N,) int64 or NULL.  logit scale = exp(*log_scale) when log_scale != NULL, else fixed_scale
+ * (losses.py:219-222).  Rows/columns [row_begin,row_end) are this rank's shard: the loss is over all N rows (every rank
+ * computes the same value), gradients are produced for the local rows only.
+ *   loss    (1,) f32, lse_row (N,) f32 = log sum_j mask*exp(S_ij), lse_col (N,) f32 = log sum_i mask*exp(S_ij) */
+int scp_nce_fwd(const float* A, const float* Bm, const int64_t* ids, int64_t N, int64_t D,
+                const float* log_scale, float fixed_scale, float margin, int dcl, int a2b, int b2a,
+                float* loss, float* lse_row, float* lse_col,
+                void* workspace, size_t workspace_bytes, scp_stream_t stream);
+
+/* dA, dB: (row_end-row_begin, D) f32 gradients of g_loss*loss w.r.t. A[row_begin:row_end], Bm[row_begin:row_end]
+ * (dB nullable).  d_log_scale (nullable, (1,)): gradient w.r.t. the log-scale parameter, full sum over the N x N
+ * matrix (identical on every rank). */
+int scp_nce_bwd(const float* A, const float* Bm, const int64_t* ids, int64_t N, int64_t D,
+                const float* log_scale, float fixed_scale, float margin, int dcl, int a2b, int b2a,
+                const float* lse_row, const float* lse_col, const float* g_loss,
+                int64_t row_begin, int64_t row_end, float* dA, float* dB, float* d_log_scale,
+                void* workspace, size_t workspace_bytes, scp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCP_B200_H_ */

@@ -1,0 +1,100 @@
+// Library bookkeeping: error strings, launch counter, device-architecture gate.
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+
+#include "scp_tc.cuh"
+
+namespace scp {
+
+static thread_local char g_detail[512] = "";
+static std::atomic<int> g_launches{0};
+
+void set_error_detail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_detail, sizeof(g_detail), fmt, ap);
+  va_end(ap);
+}
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_detail, sizeof(g_detail), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int check_device_arch() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(SCP_ERR_CUDA, "cudaGetDevice failed");
+  static thread_local int cached_dev = -1;
+  static thread_local int cached_rc = SCP_OK;
+  if (dev == cached_dev) return cached_rc;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+    return fail(SCP_ERR_CUDA, "cudaDeviceGetAttribute failed");
+  cached_dev = dev;
+  cached_rc = major == 10 ? SCP_OK : fail(SCP_ERR_ARCH, "device %d has compute capability %d.x; sm_100a required", dev, major);
+  return cached_rc;
+}
+
+// ---- TMA tensor maps ------------------------------------------------------------------------------------------
+namespace tc {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+int make_tmap_f16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return fail(SCP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16 != 0 || box_rows < 1 || box_rows > 256)
+    return fail(SCP_ERR_INVALID, "tensor map: base/pitch must be 16-byte aligned, box rows in [1,256]");
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)box_rows};
+  const cuuint32_t estride[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SCP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return SCP_OK;
+}
+}  // namespace tc
+
+}  // namespace scp
+
+extern "C" int scp_version(void) { return 0 * 10000 + 1 * 100 + 0; }
+
+extern "C" int scp_num_launches(void) { return scp::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" const char* scp_last_error_string(int code) {
+  static thread_local char buf[640];
+  const char* base = "unknown error";
+  switch (code) {
+    case SCP_OK: base = "ok"; break;
+    case SCP_ERR_INVALID: base = "invalid argument"; break;
+    case SCP_ERR_UNSUPPORTED: base = "unsupported shape or dtype"; break;
+    case SCP_ERR_WORKSPACE: base = "workspace too small"; break;
+    case SCP_ERR_CUDA: base = "CUDA error"; break;
+    case SCP_ERR_ARCH: base = "wrong GPU architecture (needs sm_100a)"; break;
+  }
+  if (code != SCP_OK && scp::g_detail[0])
+    snprintf(buf, sizeof(buf), "%s: %s", base, scp::g_detail);
+  else
+    snprintf(buf, sizeof(buf), "%s", base);
+  return buf;
+}

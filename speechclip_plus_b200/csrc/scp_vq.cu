@@ -1,0 +1,1036 @@
+// S2 -- keyword vector quantiser (cosine vs CLIP token table, arg-max / softmax / straight-through, fwd + bwd).
+// Replaces GeneralBranch.get_keyword_cosine_score + SimpleVectorQuantizer.forward + the lookup matmul of the
+// reference (avssl/model/kw_branches.py:158-197, avssl/module/speechclip_c_modules/my_vector_quantizer.py:64-165).
+//
+// Forward pipeline (the (M,V) logit matrix is never written to memory):
+//   vq_prep_kw          kw fp32 -> unit rows in fp16 (A operand) + 1/||kw||
+//   sweep 1 (tcgen05)   S = khat * Ehat^T tile by tile; per row: running softmax statistics at temperature 1 and tau,
+//                       and the maximum of every 32-column chunk (fp16-product precision)
+//   vq_select           per row: chunks whose maximum is within the fp16 error bound of the row maximum are re-scored
+//                       EXACTLY (fp64 accumulation over the fp32 table) -> arg-max is bit-exact w.r.t. an exact cosine,
+//                       first index wins ties; combines the split statistics; gathers keywords = E[idx]; code histogram
+//   sweep 2 (tcgen05)   transposed product Ehat * khat^T so that the column sums  avg_probs[v] = mean_m softmax(x)[m,v]
+//                       (which need the row normaliser from sweep 1) are thread-serial
+//   vq_metrics          code_perplexity, prob_perplexity, diversity_loss, ent_per_t
+// Backward pipeline:
+//   vq_bwd_prep         g_keywords -> unit rows fp16 + scale + centring constant
+//   sweep 3 (tcgen05)   two accumulators sharing Ehat tiles: S1 = khat Ehat^T, S2 = ghat Ehat^T;
+//                       P = softmax_tau row, Q = P * (T - s0); writes fp16 P~, Q~ and the row sums
+//   gemm_out (tcgen05)  U = Q~ * Ehat, W = P~ * Ehat  (K = V, split-K)
+//   vq_bwd_finalize     g_khat = (U - s W)/tau, projection through the normalisation, optional d/dtau
+#include <cfloat>
+
+#include "scp_stream_gemm.cuh"
+
+namespace scp {
+
+using tc::GemmMaps;
+using tc::Sched;
+using tc::WorkInfo;
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kNegBig = -1.0e30f;          // stands in for -inf (keeps 0 * x finite)
+constexpr float kRescueMargin = 2.2e-3f;     // 2 x (2^-10 fp16 product bound) + slack, see DESIGN.md
+constexpr float kPScale = 16384.0f;          // P~ = P * 2^14 keeps softmax rows in the fp16 normal range
+constexpr int kVqBN = 256;                   // sweep 1 column tile
+constexpr int kVqPad = 256;                  // vocabulary padding
+
+struct MaskedCols {
+  int n;
+  int col[SCP_MAX_MASKED];
+};
+__device__ __forceinline__ bool is_masked(const MaskedCols& mc, int c) {
+  bool m = false;
+#pragma unroll
+  for (int i = 0; i < SCP_MAX_MASKED; ++i) m |= (i < mc.n && mc.col[i] == c);
+  return m;
+}
+__device__ __forceinline__ bool chunk_has_mask(const MaskedCols& mc, int col0) {
+  bool m = false;
+#pragma unroll
+  for (int i = 0; i < SCP_MAX_MASKED; ++i) m |= (i < mc.n && (mc.col[i] >> 5) == (col0 >> 5));
+  return m;
+}
+
+// =====================================================================================================================
+// preparation kernels
+// =====================================================================================================================
+// warp <-> table row: unit-normalise into fp16, record the norm.  rows >= V are zero padding.
+__global__ void vq_table_normalize_kernel(const float* __restrict__ table, int64_t V, int64_t Vp, int D,
+                                          __half* __restrict__ hat, float* __restrict__ norm,
+                                          unsigned int* __restrict__ norm_max_bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (v >= Vp) return;
+  __half* dst = hat + v * D;
+  if (v >= V) {
+    for (int d = lane; d < D; d += 32) dst[d] = __float2half(0.f);
+    if (lane == 0) norm[v] = 1.f;
+    return;
+  }
+  const float* src = table + v * D;
+  float ss = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float x = src[d];
+    ss = fmaf(x, x, ss);
+  }
+  ss = warp_sum(ss);
+  const float n = fmaxf(sqrtf(ss), 1e-8f);  // F.cosine_similarity eps
+  const float inv = 1.0f / n;
+  for (int d = lane; d < D; d += 32) dst[d] = __float2half_rn(src[d] * inv);
+  if (lane == 0) {
+    norm[v] = n;
+    atomicMax(norm_max_bits, __float_as_uint(n));  // positive floats order like their bit patterns
+  }
+}
+
+// (R, C) fp16 -> (C, ldo) fp16 transpose through a padded smem tile
+__global__ void transpose_f16_kernel(const __half* __restrict__ in, int64_t R, int C, __half* __restrict__ out,
+                                     int64_t ldo) {
+  __shared__ __half tile[32][34];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i;
+    const int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? in[r * C + c] : __float2half(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const int64_t r = r0 + threadIdx.x;
+    if (c < C && r < ldo) out[(int64_t)c * ldo + r] = tile[threadIdx.x][i];
+  }
+}
+
+// column means of the fp32 table: grid (ceil(D/32), row_splits), atomics into a zeroed buffer
+__global__ void vq_table_mean_kernel(const float* __restrict__ table, int64_t V, int D, float* __restrict__ mean) {
+  const int d = blockIdx.x * 32 + threadIdx.x;
+  if (d >= D) return;
+  float s = 0.f;
+  for (int64_t v = (int64_t)blockIdx.y * blockDim.y + threadIdx.y; v < V; v += (int64_t)gridDim.y * blockDim.y)
+    s += table[v * D + d];
+  atomicAdd(&mean[d], s / (float)V);
+}
+
+// warp <-> keyword row: unit-normalise into fp16 (zero rows for m >= M), 1/max(||kw||,1e-8) -> row_stats[m][3]
+__global__ void vq_prep_kw_kernel(const float* __restrict__ kw, int64_t M, int64_t Mp, int D,
+                                  __half* __restrict__ kw_hat, float* __restrict__ row_stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= Mp) return;
+  __half* dst = kw_hat + m * D;
+  if (m >= M) {
+    for (int d = lane; d < D; d += 32) dst[d] = __float2half(0.f);
+    return;
+  }
+  const float* src = kw + m * D;
+  float ss = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float x = src[d];
+    ss = fmaf(x, x, ss);
+  }
+  ss = warp_sum(ss);
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-8f);
+  for (int d = lane; d < D; d += 32) dst[d] = __float2half_rn(src[d] * inv);
+  if (lane == 0) row_stats[m * 4 + 3] = inv;
+}
+
+// =====================================================================================================================
+// sweep 1: per-row statistics of S = khat * Ehat^T
+// =====================================================================================================================
+struct Sweep1Epi {
+  struct Params {
+    float* chunk_max;   // (Mp, n_chunks)
+    float* partials;    // (Mp, n_groups, 4): sum e^c, sum c e^c, running max, sum e^{(c-max)/tau}
+    const float* tau;   // device scalar
+    int n_chunks;
+    int n_groups;
+    int V;
+    MaskedCols mc;
+  };
+  static constexpr int kSmemBytes = 0;
+  const Params& p;
+  int64_t row;
+  int group;
+  float k_tau;  // log2(e)/tau
+  float sum_e1, sum_ce1, run_max, sum_et;
+
+  __device__ __forceinline__ Sweep1Epi(const Params& p_, const WorkInfo& w, int row_in_tile, uint8_t*)
+      : p(p_), row((int64_t)w.m_tile * tc::kTileM + row_in_tile), group(w.n_group) {
+    k_tau = kLog2e / __ldg(p.tau);
+    sum_e1 = 0.f; sum_ce1 = 0.f; run_max = kNegBig; sum_et = 0.f;
+  }
+  __device__ __forceinline__ void tile_begin(int) {}
+  __device__ __forceinline__ void tile_end(int) {}
+  __device__ __forceinline__ void chunk(int col0, float (&v)[1][32]) {
+    float(&c)[32] = v[0];
+    if (col0 + 32 > p.V || chunk_has_mask(p.mc, col0)) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i >= p.V || is_masked(p.mc, col0 + i)) c[i] = kNegBig;
+    }
+    float cmax = c[0];
+#pragma unroll
+    for (int i = 1; i < 32; ++i) cmax = fmaxf(cmax, c[i]);
+    p.chunk_max[row * p.n_chunks + (col0 >> 5)] = cmax;
+    if (cmax > run_max) {  // rescale the temperature-tau sum to the new running maximum
+      sum_et *= exp2f((run_max - cmax) * k_tau);
+      run_max = cmax;
+    }
+    const float shift = run_max * k_tau;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float e1 = exp2f(c[i] * kLog2e);  // |c| <= 1: no shift needed at temperature 1
+      sum_e1 += e1;
+      sum_ce1 = fmaf(c[i], e1, sum_ce1);
+      sum_et += exp2f(fmaf(c[i], k_tau, -shift));
+    }
+  }
+  __device__ __forceinline__ void finish() {
+    float4 o = make_float4(sum_e1, sum_ce1, run_max, sum_et);
+    *reinterpret_cast<float4*>(p.partials + (row * p.n_groups + group) * 4) = o;
+  }
+};
+
+// =====================================================================================================================
+// exact arg-max + statistics combine + keyword gather      (block of 128 threads <-> row)
+// =====================================================================================================================
+struct Best {
+  double val;
+  int idx;
+};
+__device__ __forceinline__ Best better(const Best& a, const Best& b) {
+  // larger value wins; equal values: smaller index (torch.max returns the first maximum)
+  if (b.idx < 0) return a;
+  if (a.idx < 0) return b;
+  if (b.val > a.val || (b.val == a.val && b.idx < a.idx)) return b;
+  return a;
+}
+
+__global__ void __launch_bounds__(128)
+vq_select_kernel(const float* __restrict__ kw, const float* __restrict__ table, int64_t M, int V, int D,
+                 const float* __restrict__ chunk_max, int n_chunks, const float* __restrict__ partials, int n_groups,
+                 const float* __restrict__ tau_ptr, MaskedCols mc, int64_t* __restrict__ idx_out,
+                 float* __restrict__ keywords, float* __restrict__ row_stats, float* __restrict__ code_hist) {
+  extern __shared__ double s_kw[];  // D doubles
+  __shared__ float s_red[4];
+  __shared__ Best s_best[4];
+  const int64_t m = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int d = tid; d < D; d += 128) s_kw[d] = (double)kw[m * D + d];
+  // approximate row maximum
+  const float* cm = chunk_max + m * n_chunks;
+  float mx = kNegBig;
+  for (int c = tid; c < n_chunks; c += 128) mx = fmaxf(mx, cm[c]);
+  mx = warp_max(mx);
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+  const float thr = mx - kRescueMargin;
+  // exact re-scoring of every candidate chunk: lane <-> column
+  Best best{0.0, -1};
+  for (int c0 = warp * 32; c0 < n_chunks; c0 += 128) {
+    const int c = c0 + lane;
+    const bool cand = c < n_chunks && cm[c] >= thr;
+    unsigned ballot = __ballot_sync(0xffffffffu, cand);
+    while (ballot) {
+      const int b = __ffs(ballot) - 1;
+      ballot &= ballot - 1;
+      const int v = (c0 + b) * 32 + lane;
+      if (v < V && !is_masked(mc, v)) {
+        const float4* e = reinterpret_cast<const float4*>(table + (int64_t)v * D);
+        double dot = 0.0, nn = 0.0;
+        for (int d4 = 0; d4 < D / 4; ++d4) {
+          const float4 x = __ldg(e + d4);
+          const double x0 = x.x, x1 = x.y, x2 = x.z, x3 = x.w;
+          dot = fma(s_kw[4 * d4 + 0], x0, dot); nn = fma(x0, x0, nn);
+          dot = fma(s_kw[4 * d4 + 1], x1, dot); nn = fma(x1, x1, nn);
+          dot = fma(s_kw[4 * d4 + 2], x2, dot); nn = fma(x2, x2, nn);
+          dot = fma(s_kw[4 * d4 + 3], x3, dot); nn = fma(x3, x3, nn);
+        }
+        const double score = dot / fmax(sqrt(nn), 1e-8);  // common factor 1/||kw|| does not change the order
+        best = better(best, Best{score, v});
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Best other;
+    other.val = __shfl_xor_sync(0xffffffffu, best.val, o);
+    other.idx = __shfl_xor_sync(0xffffffffu, best.idx, o);
+    best = better(best, other);
+  }
+  if (lane == 0) s_best[warp] = best;
+  __syncthreads();
+  best = better(better(s_best[0], s_best[1]), better(s_best[2], s_best[3]));
+  int k = best.idx;
+  if (k < 0) {  // no finite candidate (all columns masked): first unmasked column, like argmax over equal values
+    k = 0;
+    while (k < V - 1 && is_masked(mc, k)) ++k;
+  }
+  if (tid == 0) {
+    idx_out[m] = k;
+    atomicAdd(&code_hist[k], 1.0f);
+    // combine the per-group statistics
+    const float tau = *tau_ptr;
+    const float4* pp = reinterpret_cast<const float4*>(partials + m * n_groups * 4);
+    float z1 = 0.f, c1 = 0.f, gmax = kNegBig;
+    for (int g = 0; g < n_groups; ++g) {
+      const float4 q = pp[g];
+      z1 += q.x; c1 += q.y; gmax = fmaxf(gmax, q.z);
+    }
+    float zt = 0.f;
+    for (int g = 0; g < n_groups; ++g) {
+      const float4 q = pp[g];
+      zt += q.w * expf((q.z - gmax) / tau);
+    }
+    const float lse1 = logf(z1);
+    int n_valid = V;
+    for (int i = 0; i < mc.n; ++i) n_valid -= (mc.col[i] >= 0 && mc.col[i] < V);
+    // -sum p log(p + 1e-9) = H - n_valid*1e-9 + O(1e-8): at temperature 1 every p >= 1/(V e^2) >> 1e-9
+    const float ent = lse1 - c1 / z1 - (float)n_valid * 1e-9f;
+    float* rs = row_stats + m * 4;
+    rs[0] = lse1;
+    rs[1] = gmax / tau + logf(zt);
+    rs[2] = ent;
+  }
+  // keywords = E[k]   (value of subword_prob @ E, kw_branches.py:195)
+  const float4* src = reinterpret_cast<const float4*>(table + (int64_t)k * D);
+  float4* dst = reinterpret_cast<float4*>(keywords + m * D);
+  for (int d4 = tid; d4 < D / 4; d4 += 128) dst[d4] = __ldg(src + d4);
+}
+
+// =====================================================================================================================
+// sweep 2: avg_probs[v] = (1/M) sum_m exp(c[m,v] - lse1[m])       X = Ehat (rows v), Y = khat (rows m)
+// =====================================================================================================================
+__global__ void vq_lse_to_log2_kernel(const float* __restrict__ row_stats, int64_t M, int64_t Mp2,
+                                      float* __restrict__ lse1_l2) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < Mp2) lse1_l2[m] = m < M ? row_stats[m * 4] * kLog2e : 1.0e30f;  // padding columns contribute exp2(-1e30) = 0
+}
+
+struct Sweep2Epi {
+  struct Params {
+    const float* lse1_l2;  // (Mp2,) lse at temperature 1 times log2(e); +1e30 for padding
+    float* avg_probs;      // (Vp,)
+    float inv_m;
+    int V;
+    MaskedCols mc;
+  };
+  static constexpr int kSmemBytes = 0;
+  const Params& p;
+  int v;
+  float acc;
+  __device__ __forceinline__ Sweep2Epi(const Params& p_, const WorkInfo& w, int row_in_tile, uint8_t*)
+      : p(p_), v(w.m_tile * tc::kTileM + row_in_tile), acc(0.f) {}
+  __device__ __forceinline__ void tile_begin(int) {}
+  __device__ __forceinline__ void tile_end(int) {}
+  __device__ __forceinline__ void chunk(int col0, float (&c)[1][32]) {
+    const float4* l4 = reinterpret_cast<const float4*>(p.lse1_l2 + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 l = __ldg(l4 + i);
+      acc += exp2f(fmaf(c[0][4 * i + 0], kLog2e, -l.x));
+      acc += exp2f(fmaf(c[0][4 * i + 1], kLog2e, -l.y));
+      acc += exp2f(fmaf(c[0][4 * i + 2], kLog2e, -l.z));
+      acc += exp2f(fmaf(c[0][4 * i + 3], kLog2e, -l.w));
+    }
+  }
+  __device__ __forceinline__ void finish() {
+    p.avg_probs[v] = (v < p.V && !is_masked(p.mc, v)) ? acc * p.inv_m : 0.f;
+  }
+};
+
+// =====================================================================================================================
+// metrics: code_perplexity, prob_perplexity, diversity_loss, ent_per_t      (one block)
+// =====================================================================================================================
+__device__ __forceinline__ float block_sum_1024(float v, float* s_red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  float t = (int)threadIdx.x < (int)(blockDim.x >> 5) ? s_red[threadIdx.x] : 0.f;
+  if (warp == 0) {
+    t = warp_sum(t);
+    if (lane == 0) s_red[0] = t;
+  }
+  __syncthreads();
+  return s_red[0];
+}
+
+__global__ void __launch_bounds__(1024)
+vq_metrics_kernel(const float* __restrict__ code_hist, const float* __restrict__ avg_probs,
+                  const float* __restrict__ row_stats, int64_t M, int K, int V, float* __restrict__ metrics) {
+  __shared__ float s_red[32];
+  const float inv_m = 1.0f / (float)M;
+  float hc = 0.f, hp = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float h = code_hist[v] * inv_m;  // my_vector_quantizer.py:94-99
+    hc += h * logf(h + 1e-7f);
+    if (avg_probs) {
+      const float a = avg_probs[v];  // :119-121
+      hp += a * logf(a + 1e-7f);
+    }
+  }
+  hc = block_sum_1024(hc, s_red);
+  hp = block_sum_1024(hp, s_red);
+  if (threadIdx.x == 0) {
+    metrics[0] = expf(-hc);
+    const float pp = avg_probs ? expf(-hp) : nanf("");
+    metrics[1] = pp;
+    metrics[2] = ((float)V - pp) / (float)V;  // diversity_loss, :155-158
+  }
+  // ent_per_t[i] = mean_b entropy[b*K + i]     (:104-116)
+  const int64_t Bsz = M / K;
+  for (int i = threadIdx.x >> 5; i < K; i += (blockDim.x >> 5)) {
+    float s = 0.f;
+    for (int64_t b = threadIdx.x & 31; b < Bsz; b += 32) s += row_stats[(b * K + i) * 4 + 2];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) metrics[3 + i] = s / (float)Bsz;
+  }
+}
+
+// =====================================================================================================================
+// backward
+// =====================================================================================================================
+// warp <-> row: ghat = g/||g|| (fp16), gscale = ||g||, s0 = <ghat, mean(E)> / norm_ref
+__global__ void vq_bwd_prep_kernel(const float* __restrict__ g, int64_t M, int64_t Mp, int D,
+                                   const float* __restrict__ table_mean /* (D+1): [D] = norm_ref */,
+                                   __half* __restrict__ g_hat, float* __restrict__ g_aux /* (Mp,2): scale, s0 */) {
+  const int lane = threadIdx.x & 31;
+  const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= Mp) return;
+  __half* dst = g_hat + m * D;
+  if (m >= M) {
+    for (int d = lane; d < D; d += 32) dst[d] = __float2half(0.f);
+    if (lane == 0) { g_aux[m * 2] = 0.f; g_aux[m * 2 + 1] = 0.f; }
+    return;
+  }
+  const float* src = g + m * D;
+  float ss = 0.f, dm = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float x = src[d];
+    ss = fmaf(x, x, ss);
+    dm = fmaf(x, table_mean[d], dm);
+  }
+  ss = warp_sum(ss);
+  dm = warp_sum(dm);
+  const float n = sqrtf(ss);
+  const float inv = n > 0.f ? 1.0f / n : 0.f;
+  for (int d = lane; d < D; d += 32) dst[d] = __float2half_rn(src[d] * inv);
+  if (lane == 0) {
+    g_aux[m * 2] = n;
+    g_aux[m * 2 + 1] = dm * inv / table_mean[D];
+  }
+}
+
+struct Sweep3Epi {
+  struct Params {
+    const float* row_stats;   // (M,4): [1] = lse at tau
+    const float* g_aux;       // (Mp,2): scale, s0
+    const float* table_norm;  // (Vp,)
+    const float* table_mean;  // [D] = norm_ref
+    const float* tau;
+    __half* pq;               // (2*Mp, Vp): rows [0,Mp) = Q~, rows [Mp,2Mp) = P~
+    float* partials;          // (Mp, n_groups, 4): sum Q, sum P, sum Q c, sum P c
+    int64_t M, Mp, Vp;
+    int n_groups, V, D;
+    MaskedCols mc;
+  };
+  static constexpr int kSmemBytes = 0;
+  const Params& p;
+  int64_t row;
+  int group;
+  float k_tau, lse_l2, s0, inv_norm_ref;
+  float sq, sp, sqc, spc;
+  __device__ __forceinline__ Sweep3Epi(const Params& p_, const WorkInfo& w, int row_in_tile, uint8_t*)
+      : p(p_), row((int64_t)w.m_tile * tc::kTileM + row_in_tile), group(w.n_group) {
+    k_tau = kLog2e / __ldg(p.tau);
+    const bool valid = row < p.M;
+    lse_l2 = valid ? p.row_stats[row * 4 + 1] * kLog2e : 1.0e30f;  // padding rows: P = 0
+    s0 = p.g_aux[row * 2 + 1];
+    inv_norm_ref = 1.0f / p.table_mean[p.D];
+    sq = sp = sqc = spc = 0.f;
+  }
+  __device__ __forceinline__ void tile_begin(int) {}
+  __device__ __forceinline__ void tile_end(int) {}
+  __device__ __forceinline__ void chunk(int col0, float (&v)[2][32]) {
+    float(&c)[32] = v[0];
+    float(&t)[32] = v[1];
+    if (col0 + 32 > p.V || chunk_has_mask(p.mc, col0)) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i >= p.V || is_masked(p.mc, col0 + i)) c[i] = kNegBig;
+    }
+    const float4* n4 = reinterpret_cast<const float4*>(p.table_norm + col0);
+    uint32_t pk_q[16], pk_p[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 nv = __ldg(n4 + i);
+      const float nn[4] = {nv.x, nv.y, nv.z, nv.w};
+      float pv[4], qv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float cc = c[4 * i + j];
+        const float pj = exp2f(fmaf(cc, k_tau, -lse_l2));           // softmax_tau
+        const float tj = fmaf(t[4 * i + j] * nn[j], inv_norm_ref, -s0);  // (g . e_v)/(|g| norm_ref) - s0
+        const float qj = pj * tj;
+        sp += pj;
+        sq += qj;
+        const float cf = cc > -2.f ? cc : 0.f;
+        spc = fmaf(pj, cf, spc);
+        sqc = fmaf(qj, cf, sqc);
+        pv[j] = pj * kPScale;
+        qv[j] = qj * kPScale;
+      }
+      __half2 h;
+      h = __floats2half2_rn(qv[0], qv[1]); pk_q[2 * i] = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2half2_rn(qv[2], qv[3]); pk_q[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2half2_rn(pv[0], pv[1]); pk_p[2 * i] = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2half2_rn(pv[2], pv[3]); pk_p[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    uint4* dq = reinterpret_cast<uint4*>(p.pq + row * p.Vp + col0);
+    uint4* dp = reinterpret_cast<uint4*>(p.pq + (p.Mp + row) * p.Vp + col0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      dq[i] = make_uint4(pk_q[4 * i], pk_q[4 * i + 1], pk_q[4 * i + 2], pk_q[4 * i + 3]);
+      dp[i] = make_uint4(pk_p[4 * i], pk_p[4 * i + 1], pk_p[4 * i + 2], pk_p[4 * i + 3]);
+    }
+  }
+  __device__ __forceinline__ void finish() {
+    *reinterpret_cast<float4*>(p.partials + (row * p.n_groups + group) * 4) = make_float4(sq, sp, sqc, spc);
+  }
+};
+
+// plain accumulator store: out[k_split][x][row][col]  (fp32)
+template <int NX>
+struct StoreEpi {
+  struct Params {
+    float* out;
+    int64_t rows;  // rows per x-slab (Mp)
+    int ld;        // columns (D)
+  };
+  static constexpr int kSmemBytes = 0;
+  const Params& p;
+  int64_t row;
+  int ks;
+  __device__ __forceinline__ StoreEpi(const Params& p_, const WorkInfo& w, int row_in_tile, uint8_t*)
+      : p(p_), row((int64_t)w.m_tile * tc::kTileM + row_in_tile), ks(w.k_split) {}
+  __device__ __forceinline__ void tile_begin(int) {}
+  __device__ __forceinline__ void tile_end(int) {}
+  __device__ __forceinline__ void chunk(int col0, float (&v)[NX][32]) {
+#pragma unroll
+    for (int x = 0; x < NX; ++x) {
+      float4* dst = reinterpret_cast<float4*>(p.out + (((int64_t)ks * NX + x) * p.rows + row) * p.ld + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[x][4 * i], v[x][4 * i + 1], v[x][4 * i + 2], v[x][4 * i + 3]);
+    }
+  }
+  __device__ __forceinline__ void finish() {}
+};
+
+// warp <-> row: g_khat = (U - s W) * scale / tau ; g_kw = (g_khat - <g_khat,khat> khat) / ||kw||
+__global__ void vq_bwd_finalize_kernel(const float* __restrict__ uw /* (k_splits, 2, Mp, D) */, int k_splits,
+                                       int64_t M, int64_t Mp, int D, const float* __restrict__ partials, int n_groups,
+                                       const float* __restrict__ g_aux, const float* __restrict__ kw,
+                                       const float* __restrict__ row_stats, const float* __restrict__ table_mean,
+                                       const float* __restrict__ tau_ptr, float* __restrict__ g_kw,
+                                       float* __restrict__ g_tau) {
+  const int lane = threadIdx.x & 31;
+  const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const float tau = *tau_ptr;
+  float sq = 0.f, sp = 0.f, sqc = 0.f, spc = 0.f;
+  for (int g = 0; g < n_groups; ++g) {
+    const float4 q = *reinterpret_cast<const float4*>(partials + (m * n_groups + g) * 4);
+    sq += q.x; sp += q.y; sqc += q.z; spc += q.w;
+  }
+  const float s_adj = sp > 0.f ? sq / sp : 0.f;
+  const float scale = g_aux[m * 2] * table_mean[D] / (kPScale * tau);
+  const float inv_norm = row_stats[m * 4 + 3];
+  float proj = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    float u = 0.f, w = 0.f;
+    for (int ks = 0; ks < k_splits; ++ks) {
+      u += uw[(((int64_t)ks * 2 + 0) * Mp + m) * D + d];
+      w += uw[(((int64_t)ks * 2 + 1) * Mp + m) * D + d];
+    }
+    const float gk = (u - s_adj * w) * scale;
+    proj = fmaf(gk, kw[m * D + d] * inv_norm, proj);
+  }
+  proj = warp_sum(proj);
+  for (int d = lane; d < D; d += 32) {
+    float u = 0.f, w = 0.f;
+    for (int ks = 0; ks < k_splits; ++ks) {
+      u += uw[(((int64_t)ks * 2 + 0) * Mp + m) * D + d];
+      w += uw[(((int64_t)ks * 2 + 1) * Mp + m) * D + d];
+    }
+    const float gk = (u - s_adj * w) * scale;
+    const float kh = kw[m * D + d] * inv_norm;
+    g_kw[m * D + d] = (gk - proj * kh) * inv_norm;
+  }
+  if (g_tau && lane == 0) {
+    // d/dtau = -(1/tau^2) sum_v P (T - s) c      (T in true units = T' * |g| * norm_ref)
+    const float contrib = -(g_aux[m * 2] * table_mean[D]) * (sqc - s_adj * spc) / (tau * tau);
+    atomicAdd(g_tau, contrib);
+  }
+}
+
+
+// =====================================================================================================================
+// dense-input form of SimpleVectorQuantizer.forward (my_vector_quantizer.py:64-165): the caller already holds the (M,V)
+// score matrix.  HBM/L2-bound helper kernels; not on the fused hot path.
+// =====================================================================================================================
+__device__ __forceinline__ float block_max_256(float v, float* s_red) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = s_red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) t = fmaxf(t, s_red[i]);
+  return t;
+}
+__device__ __forceinline__ float block_sum_256(float v, float* s_red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += s_red[i];
+  return t;
+}
+
+// block (256 threads) <-> row.  Masks x in place (:78-79), arg-max with first-index ties (:82), softmax statistics.
+__global__ void __launch_bounds__(256)
+vq_dense_row_kernel(float* __restrict__ x, int64_t M, int V, int64_t ldx, MaskedCols mc, const float* __restrict__ tau_ptr,
+                    int training, int64_t* __restrict__ idx_out, float* __restrict__ row_stats,
+                    float* __restrict__ code_hist, float* __restrict__ subword_prob) {
+  __shared__ float s_red[8];
+  __shared__ int s_idx[8];
+  const int64_t m = blockIdx.x;
+  float* row = x + m * ldx;
+  const int tid = threadIdx.x;
+  if (tid < mc.n && mc.col[tid] >= 0 && mc.col[tid] < V) row[mc.col[tid]] = -INFINITY;
+  __syncthreads();
+  // pass A: maximum and its first index
+  float mx = -INFINITY;
+  int mi = 0x7fffffff;
+  for (int v = tid; v < V; v += 256) {
+    const float c = row[v];
+    if (c > mx) { mx = c; mi = v; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    if (om > mx || (om == mx && oi < mi)) { mx = om; mi = oi; }
+  }
+  if ((tid & 31) == 0) { s_red[tid >> 5] = mx; s_idx[tid >> 5] = mi; }
+  __syncthreads();
+  mx = s_red[0]; mi = s_idx[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i)
+    if (s_red[i] > mx || (s_red[i] == mx && s_idx[i] < mi)) { mx = s_red[i]; mi = s_idx[i]; }
+  if (mi == 0x7fffffff) mi = 0;  // all -inf / NaN row: torch returns index 0
+  const float tau = *tau_ptr;
+  // pass B: normalisers at temperature 1 and tau
+  float z1 = 0.f, zt = 0.f;
+  for (int v = tid; v < V; v += 256) {
+    const float c = row[v];
+    z1 += expf(c - mx);
+    zt += expf((c - mx) / tau);
+  }
+  z1 = block_sum_256(z1, s_red);
+  zt = block_sum_256(zt, s_red);
+  const float lse1 = mx + logf(z1);
+  // pass C: entropy exactly as the reference (:111) and the value of subword_prob (:130-139)
+  float ent = 0.f;
+  for (int v = tid; v < V; v += 256) {
+    const float p = expf(row[v] - lse1);
+    ent -= p * logf(p + 1e-9f);
+    if (subword_prob) subword_prob[m * (int64_t)V + v] = v == mi ? 1.f : 0.f;
+  }
+  ent = block_sum_256(ent, s_red);
+  if (tid == 0) {
+    idx_out[m] = mi;
+    atomicAdd(&code_hist[mi], 1.0f);
+    float* rs = row_stats + m * 4;
+    rs[0] = lse1;
+    rs[1] = mx / tau + logf(zt);
+    rs[2] = ent;
+    rs[3] = 0.f;
+  }
+  (void)training;
+}
+
+// thread <-> column: avg_probs[v] = mean_m exp(x[m,v] - lse1[m])   (deterministic column sums)
+__global__ void vq_dense_colsum_kernel(const float* __restrict__ x, int64_t M, int V, int64_t ldx,
+                                       const float* __restrict__ row_stats, float* __restrict__ avg_probs) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  float s = 0.f;
+  for (int64_t m = 0; m < M; ++m) s += expf(x[m * ldx + v] - row_stats[m * 4]);
+  avg_probs[v] = s / (float)M;
+}
+
+// block <-> row: g_x = p_tau (g_p - <p_tau, g_p>) / tau ; g_tau partial
+__global__ void __launch_bounds__(256)
+vq_dense_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g_p, int V, int64_t ldx, int64_t ldg,
+                    const float* __restrict__ row_stats, const float* __restrict__ tau_ptr, float* __restrict__ g_x,
+                    float* __restrict__ g_tau) {
+  __shared__ float s_red[8];
+  const int64_t m = blockIdx.x;
+  const float tau = *tau_ptr;
+  const float lse_t = row_stats[m * 4 + 1];
+  const float* row = x + m * ldx;
+  const float* gp = g_p + m * ldg;
+  float s = 0.f;
+  for (int v = threadIdx.x; v < V; v += 256) s += expf(row[v] / tau - lse_t) * gp[v];
+  s = block_sum_256(s, s_red);
+  float gt = 0.f;
+  for (int v = threadIdx.x; v < V; v += 256) {
+    const float c = row[v];
+    const float g = expf(c / tau - lse_t) * (gp[v] - s) / tau;
+    g_x[m * (int64_t)V + v] = g;
+    if (c > -INFINITY) gt -= g * c / tau;
+  }
+  if (g_tau) {
+    gt = block_sum_256(gt, s_red);
+    if (threadIdx.x == 0) atomicAdd(g_tau, gt);
+  }
+}
+
+// =====================================================================================================================
+// host side
+// =====================================================================================================================
+static MaskedCols make_masked(const int32_t* cols, int n) {
+  MaskedCols mc{};
+  mc.n = n;
+  for (int i = 0; i < SCP_MAX_MASKED; ++i) mc.col[i] = i < n ? cols[i] : -1;
+  return mc;
+}
+
+struct VqFwdWs {
+  float* chunk_max;
+  float* partials;
+  float* lse1_l2;
+  size_t total;
+  int n_chunks, n_groups;
+};
+static int vq_sweep1_groups(int64_t Mp, int64_t Vp) {
+  const int m_tiles = (int)(Mp / tc::kTileM);
+  const int n_tiles = (int)(Vp / kVqBN);
+  int g = kNumSMs / m_tiles;
+  if (g < 1) g = 1;
+  if (g > n_tiles) g = n_tiles;
+  return g;
+}
+static VqFwdWs vq_fwd_ws(void* base, int64_t M, int64_t V) {
+  const int64_t Mp = round_up(M, tc::kTileM), Vp = scp_vq_padded_vocab(V);
+  VqFwdWs w{};
+  w.n_chunks = (int)(Vp / 32);
+  w.n_groups = vq_sweep1_groups(Mp, Vp);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? static_cast<uint8_t*>(base) + off : nullptr;
+    off += (bytes + 255) & ~size_t(255);
+    return p;
+  };
+  w.chunk_max = static_cast<float*>(take((size_t)Mp * w.n_chunks * 4));
+  w.partials = static_cast<float*>(take((size_t)Mp * w.n_groups * 16));
+  w.lse1_l2 = static_cast<float*>(take((size_t)round_up(M, 256) * 4));
+  w.total = off;
+  return w;
+}
+
+struct VqBwdWs {
+  __half* g_hat;
+  float* g_aux;
+  __half* pq;
+  float* partials;
+  float* uw;
+  size_t total;
+  int n_groups, k_splits, bn_out;
+};
+static int vq_out_bn(int64_t D) { return D % 256 == 0 ? 256 : (D % 128 == 0 ? 128 : 64); }
+static VqBwdWs vq_bwd_ws(void* base, int64_t M, int64_t V, int64_t D) {
+  const int64_t Mp = round_up(M, tc::kTileM), Vp = scp_vq_padded_vocab(V);
+  VqBwdWs w{};
+  const int m_tiles = (int)(Mp / tc::kTileM);
+  const int n_tiles3 = (int)(Vp / 128);
+  w.n_groups = std::max(1, std::min(n_tiles3, kNumSMs / m_tiles));
+  w.bn_out = vq_out_bn(D);
+  const int out_items = m_tiles * (int)(D / w.bn_out);
+  const int k_chunks = (int)(Vp / tc::kChunkK);
+  w.k_splits = std::max(1, std::min(k_chunks, kNumSMs / out_items));
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? static_cast<uint8_t*>(base) + off : nullptr;
+    off += (bytes + 255) & ~size_t(255);
+    return p;
+  };
+  w.g_hat = static_cast<__half*>(take((size_t)Mp * D * 2));
+  w.g_aux = static_cast<float*>(take((size_t)Mp * 2 * 4));
+  w.pq = static_cast<__half*>(take((size_t)2 * Mp * Vp * 2));
+  w.partials = static_cast<float*>(take((size_t)Mp * w.n_groups * 16));
+  w.uw = static_cast<float*>(take((size_t)w.k_splits * 2 * Mp * D * 4));
+  w.total = off;
+  return w;
+}
+
+static int check_vq_shape(int64_t M, int64_t V, int64_t D) {
+  SCP_CHECK_ARG(M > 0 && V > 0 && D > 0, "vq: non-positive shape");
+  if (D % 64 != 0 || D > 4096) return fail(SCP_ERR_UNSUPPORTED, "vq: D must be a multiple of 64 (<= 4096), got %lld", (long long)D);
+  if (V < 2) return fail(SCP_ERR_UNSUPPORTED, "vq: V must be >= 2");
+  return SCP_OK;
+}
+
+}  // namespace scp
+
+using namespace scp;
+
+extern "C" int64_t scp_vq_padded_vocab(int64_t V) { return round_up(V, kVqPad); }
+
+extern "C" int scp_vq_prepare_table(const float* table, int64_t V, int64_t D, void* table_hat, void* table_hat_t,
+                                    float* table_norm, float* table_mean, scp_stream_t stream) {
+  int rc = check_device_arch();
+  if (rc) return rc;
+  rc = check_vq_shape(1, V, D);
+  if (rc) return rc;
+  SCP_CHECK_ARG(table && table_hat && table_hat_t && table_norm && table_mean, "vq_prepare_table: null pointer");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t Vp = scp_vq_padded_vocab(V);
+  // table_mean has D+1 entries: [D] temporarily holds the bit pattern of the maximum norm
+  if (cudaMemsetAsync(table_mean, 0, (size_t)(D + 1) * 4, s) != cudaSuccess) return fail(SCP_ERR_CUDA, "memset");
+  vq_table_normalize_kernel<<<(unsigned)ceil_div(Vp, 8), 256, 0, s>>>(
+      table, V, Vp, (int)D, reinterpret_cast<__half*>(table_hat), table_norm,
+      reinterpret_cast<unsigned int*>(table_mean + D));
+  SCP_CUDA_LAUNCH_CHECK("vq_table_normalize");
+  dim3 tb(32, 8), tg((unsigned)ceil_div(Vp, 32), (unsigned)ceil_div(D, 32));
+  transpose_f16_kernel<<<tg, tb, 0, s>>>(reinterpret_cast<const __half*>(table_hat), Vp, (int)D,
+                                         reinterpret_cast<__half*>(table_hat_t), Vp);
+  SCP_CUDA_LAUNCH_CHECK("transpose_f16");
+  dim3 mb(32, 8), mg((unsigned)ceil_div(D, 32), 64);
+  vq_table_mean_kernel<<<mg, mb, 0, s>>>(table, V, (int)D, table_mean);
+  SCP_CUDA_LAUNCH_CHECK("vq_table_mean");
+  return SCP_OK;
+}
+
+extern "C" size_t scp_vq_fwd_workspace_bytes(int64_t M, int64_t V, int64_t) { return vq_fwd_ws(nullptr, M, V).total; }
+
+extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int64_t D, const void* table_hat,
+                          const float* table_norm, const float* table, const int32_t* masked_cols, int n_masked,
+                          const float* tau, int64_t* idx, float* keywords, float* row_stats, float* code_hist,
+                          float* avg_probs, float* metrics, void* kw_hat, void* workspace, size_t workspace_bytes,
+                          scp_stream_t stream) {
+  int rc = check_device_arch();
+  if (rc) return rc;
+  rc = check_vq_shape(M, V, D);
+  if (rc) return rc;
+  SCP_CHECK_ARG(kw && table_hat && table_norm && table && tau && idx && keywords && row_stats && code_hist && metrics &&
+                    kw_hat && workspace,
+                "vq_fwd: null pointer");
+  SCP_CHECK_ARG(K > 0 && M % K == 0, "vq_fwd: M=%lld is not a multiple of K=%lld", (long long)M, (long long)K);
+  SCP_CHECK_ARG(n_masked >= 0 && n_masked <= SCP_MAX_MASKED && (n_masked == 0 || masked_cols), "vq_fwd: masked cols");
+  const VqFwdWs ws = vq_fwd_ws(workspace, M, V);
+  if (workspace_bytes < ws.total) return fail(SCP_ERR_WORKSPACE, "vq_fwd: workspace %zu < %zu", workspace_bytes, ws.total);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t Mp = round_up(M, tc::kTileM), Vp = scp_vq_padded_vocab(V);
+  const MaskedCols mc = make_masked(masked_cols, n_masked);
+
+  vq_prep_kw_kernel<<<(unsigned)ceil_div(Mp, 8), 256, 0, s>>>(kw, M, Mp, (int)D, reinterpret_cast<__half*>(kw_hat),
+                                                              row_stats);
+  SCP_CUDA_LAUNCH_CHECK("vq_prep_kw");
+  if (cudaMemsetAsync(code_hist, 0, (size_t)Vp * 4, s) != cudaSuccess) return fail(SCP_ERR_CUDA, "memset code_hist");
+
+  // ---- sweep 1
+  {
+    GemmMaps maps{};
+    if ((rc = tc::make_tmap_f16(&maps.x[0], kw_hat, Mp, D, D, tc::kTileM))) return rc;
+    maps.x[1] = maps.x[0];
+    if ((rc = tc::make_tmap_f16(&maps.y, table_hat, Vp, D, D, kVqBN))) return rc;
+    Sched sc{};
+    sc.m_tiles = (int)(Mp / tc::kTileM);
+    sc.n_tiles = (int)(Vp / kVqBN);
+    sc.n_groups = ws.n_groups;
+    sc.k_chunks = (int)(D / tc::kChunkK);
+    sc.k_splits = 1;
+    sc.m_half = sc.m_tiles;
+    sc.n_upper_off = 0;
+    Sweep1Epi::Params ep{};
+    ep.chunk_max = ws.chunk_max;
+    ep.partials = ws.partials;
+    ep.tau = tau;
+    ep.n_chunks = ws.n_chunks;
+    ep.n_groups = ws.n_groups;
+    ep.V = (int)V;
+    ep.mc = mc;
+    if ((rc = tc::launch_stream_gemm<kVqBN, 1, 4, Sweep1Epi>(maps, sc, ep, s, "vq_sweep1"))) return rc;
+  }
+  // ---- exact arg-max, statistics, gather
+  vq_select_kernel<<<(unsigned)M, 128, (size_t)D * sizeof(double), s>>>(
+      kw, table, M, (int)V, (int)D, ws.chunk_max, ws.n_chunks, ws.partials, ws.n_groups, tau, mc, idx, keywords,
+      row_stats, code_hist);
+  SCP_CUDA_LAUNCH_CHECK("vq_select");
+  // ---- sweep 2 (column sums) -- skipped when the caller does not want prob_perplexity
+  if (avg_probs) {
+    const int64_t Mp2 = round_up(M, 256);
+    vq_lse_to_log2_kernel<<<(unsigned)ceil_div(Mp2, 256), 256, 0, s>>>(row_stats, M, Mp2, ws.lse1_l2);
+    SCP_CUDA_LAUNCH_CHECK("vq_lse_to_log2");
+    GemmMaps maps{};
+    if ((rc = tc::make_tmap_f16(&maps.x[0], table_hat, Vp, D, D, tc::kTileM))) return rc;
+    maps.x[1] = maps.x[0];
+    if ((rc = tc::make_tmap_f16(&maps.y, kw_hat, Mp, D, D, 256))) return rc;
+    Sched sc{};
+    sc.m_tiles = (int)(Vp / tc::kTileM);
+    sc.n_tiles = (int)(Mp2 / 256);
+    sc.n_groups = 1;
+    sc.k_chunks = (int)(D / tc::kChunkK);
+    sc.k_splits = 1;
+    sc.m_half = sc.m_tiles;
+    sc.n_upper_off = 0;
+    Sweep2Epi::Params ep{};
+    ep.lse1_l2 = ws.lse1_l2;
+    ep.avg_probs = avg_probs;
+    ep.inv_m = 1.0f / (float)M;
+    ep.V = (int)V;
+    ep.mc = mc;
+    if ((rc = tc::launch_stream_gemm<256, 1, 4, Sweep2Epi>(maps, sc, ep, s, "vq_sweep2"))) return rc;
+  }
+  vq_metrics_kernel<<<1, 1024, 0, s>>>(code_hist, avg_probs, row_stats, M, (int)K, (int)V, metrics);
+  SCP_CUDA_LAUNCH_CHECK("vq_metrics");
+  return SCP_OK;
+}
+
+extern "C" size_t scp_vq_bwd_workspace_bytes(int64_t M, int64_t V, int64_t D) {
+  return vq_bwd_ws(nullptr, M, V, D).total;
+}
+
+template <int BN>
+static int launch_gemm_out(const GemmMaps& maps, const Sched& sc, const StoreEpi<2>::Params& ep, cudaStream_t s) {
+  constexpr int kStages = BN == 256 ? 3 : 4;
+  return tc::launch_stream_gemm<BN, 2, kStages, StoreEpi<2>>(maps, sc, ep, s, "vq_gemm_out");
+}
+
+extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, int64_t V, int64_t D,
+                          const void* kw_hat, const void* table_hat, const void* table_hat_t,
+                          const float* table_norm, const float* table_mean, const float* row_stats,
+                          const int32_t* masked_cols, int n_masked, const float* tau, float* g_kw, float* g_tau,
+                          void* workspace, size_t workspace_bytes, scp_stream_t stream) {
+  int rc = check_device_arch();
+  if (rc) return rc;
+  rc = check_vq_shape(M, V, D);
+  if (rc) return rc;
+  SCP_CHECK_ARG(g_keywords && kw && kw_hat && table_hat && table_hat_t && table_norm && table_mean && row_stats &&
+                    tau && g_kw && workspace,
+                "vq_bwd: null pointer");
+  SCP_CHECK_ARG(n_masked >= 0 && n_masked <= SCP_MAX_MASKED && (n_masked == 0 || masked_cols), "vq_bwd: masked cols");
+  const VqBwdWs ws = vq_bwd_ws(workspace, M, V, D);
+  if (workspace_bytes < ws.total) return fail(SCP_ERR_WORKSPACE, "vq_bwd: workspace %zu < %zu", workspace_bytes, ws.total);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t Mp = round_up(M, tc::kTileM), Vp = scp_vq_padded_vocab(V);
+  const MaskedCols mc = make_masked(masked_cols, n_masked);
+
+  vq_bwd_prep_kernel<<<(unsigned)ceil_div(Mp, 8), 256, 0, s>>>(g_keywords, M, Mp, (int)D, table_mean, ws.g_hat, ws.g_aux);
+  SCP_CUDA_LAUNCH_CHECK("vq_bwd_prep");
+  // ---- sweep 3: P~, Q~ and row sums
+  {
+    GemmMaps maps{};
+    if ((rc = tc::make_tmap_f16(&maps.x[0], kw_hat, Mp, D, D, tc::kTileM))) return rc;
+    if ((rc = tc::make_tmap_f16(&maps.x[1], ws.g_hat, Mp, D, D, tc::kTileM))) return rc;
+    if ((rc = tc::make_tmap_f16(&maps.y, table_hat, Vp, D, D, 128))) return rc;
+    Sched sc{};
+    sc.m_tiles = (int)(Mp / tc::kTileM);
+    sc.n_tiles = (int)(Vp / 128);
+    sc.n_groups = ws.n_groups;
+    sc.k_chunks = (int)(D / tc::kChunkK);
+    sc.k_splits = 1;
+    sc.m_half = sc.m_tiles;
+    sc.n_upper_off = 0;
+    Sweep3Epi::Params ep{};
+    ep.row_stats = row_stats;
+    ep.g_aux = ws.g_aux;
+    ep.table_norm = table_norm;
+    ep.table_mean = table_mean;
+    ep.tau = tau;
+    ep.pq = ws.pq;
+    ep.partials = ws.partials;
+    ep.M = M; ep.Mp = Mp; ep.Vp = Vp;
+    ep.n_groups = ws.n_groups;
+    ep.V = (int)V;
+    ep.D = (int)D;
+    ep.mc = mc;
+    if ((rc = tc::launch_stream_gemm<128, 2, 4, Sweep3Epi>(maps, sc, ep, s, "vq_sweep3"))) return rc;
+  }
+  // ---- U = Q~ Ehat, W = P~ Ehat   (K = Vp, split-K partials)
+  {
+    GemmMaps maps{};
+    if ((rc = tc::make_tmap_f16(&maps.x[0], ws.pq, Mp, Vp, Vp, tc::kTileM))) return rc;
+    if ((rc = tc::make_tmap_f16(&maps.x[1], ws.pq + Mp * Vp, Mp, Vp, Vp, tc::kTileM))) return rc;
+    if ((rc = tc::make_tmap_f16(&maps.y, table_hat_t, D, Vp, Vp, ws.bn_out))) return rc;
+    Sched sc{};
+    sc.m_tiles = (int)(Mp / tc::kTileM);
+    sc.n_tiles = (int)(D / ws.bn_out);
+    sc.n_groups = sc.n_tiles;
+    sc.k_chunks = (int)(Vp / tc::kChunkK);
+    sc.k_splits = ws.k_splits;
+    sc.m_half = sc.m_tiles;
+    sc.n_upper_off = 0;
+    StoreEpi<2>::Params ep{};
+    ep.out = ws.uw;
+    ep.rows = Mp;
+    ep.ld = (int)D;
+    if (ws.bn_out == 256) rc = launch_gemm_out<256>(maps, sc, ep, s);
+    else if (ws.bn_out == 128) rc = launch_gemm_out<128>(maps, sc, ep, s);
+    else rc = launch_gemm_out<64>(maps, sc, ep, s);
+    if (rc) return rc;
+  }
+  if (g_tau && cudaMemsetAsync(g_tau, 0, 4, s) != cudaSuccess) return fail(SCP_ERR_CUDA, "memset g_tau");
+  vq_bwd_finalize_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, s>>>(ws.uw, ws.k_splits, M, Mp, (int)D, ws.partials,
+                                                                  ws.n_groups, ws.g_aux, kw, row_stats, table_mean,
+                                                                  tau, g_kw, g_tau);
+  SCP_CUDA_LAUNCH_CHECK("vq_bwd_finalize");
+  return SCP_OK;
+}
+
+extern "C" size_t scp_vq_dense_workspace_bytes(int64_t, int64_t) { return 256; }
+
+extern "C" int scp_vq_dense_fwd(float* x, int64_t M, int64_t K, int64_t V, int64_t ldx, const int32_t* masked_cols,
+                                int n_masked, const float* tau, int training, int64_t* idx, float* row_stats,
+                                float* code_hist, float* avg_probs, float* metrics, float* subword_prob, void*, size_t,
+                                scp_stream_t stream) {
+  SCP_CHECK_ARG(x && tau && idx && row_stats && code_hist && metrics, "vq_dense_fwd: null pointer");
+  SCP_CHECK_ARG(M > 0 && V > 1 && K > 0 && M % K == 0 && ldx >= V, "vq_dense_fwd: bad shape");
+  SCP_CHECK_ARG(V < (1ll << 31), "vq_dense_fwd: V too large");
+  SCP_CHECK_ARG(n_masked >= 0 && n_masked <= SCP_MAX_MASKED && (n_masked == 0 || masked_cols), "vq_dense_fwd: masked cols");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const MaskedCols mc = make_masked(masked_cols, n_masked);
+  if (cudaMemsetAsync(code_hist, 0, (size_t)V * 4, s) != cudaSuccess) return fail(SCP_ERR_CUDA, "memset code_hist");
+  vq_dense_row_kernel<<<(unsigned)M, 256, 0, s>>>(x, M, (int)V, ldx, mc, tau, training, idx, row_stats, code_hist,
+                                                  subword_prob);
+  SCP_CUDA_LAUNCH_CHECK("vq_dense_row");
+  if (avg_probs) {
+    vq_dense_colsum_kernel<<<(unsigned)ceil_div(V, 128), 128, 0, s>>>(x, M, (int)V, ldx, row_stats, avg_probs);
+    SCP_CUDA_LAUNCH_CHECK("vq_dense_colsum");
+  }
+  vq_metrics_kernel<<<1, 1024, 0, s>>>(code_hist, avg_probs, row_stats, M, (int)K, (int)V, metrics);
+  SCP_CUDA_LAUNCH_CHECK("vq_metrics");
+  return SCP_OK;
+}
+
+extern "C" int scp_vq_dense_bwd(const float* x_masked, const float* g_p, int64_t M, int64_t V, int64_t ldx, int64_t ldg,
+                                const float* row_stats, const float* tau, float* g_x, float* g_tau,
+                                scp_stream_t stream) {
+  SCP_CHECK_ARG(x_masked && g_p && row_stats && tau && g_x, "vq_dense_bwd: null pointer");
+  SCP_CHECK_ARG(M > 0 && V > 1 && ldx >= V && ldg >= V, "vq_dense_bwd: bad shape");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (g_tau && cudaMemsetAsync(g_tau, 0, 4, s) != cudaSuccess) return fail(SCP_ERR_CUDA, "memset g_tau");
+  vq_dense_bwd_kernel<<<(unsigned)M, 256, 0, s>>>(x_masked, g_p, (int)V, ldx, ldg, row_stats, tau, g_x, g_tau);
+  SCP_CUDA_LAUNCH_CHECK("vq_dense_bwd");
+  return SCP_OK;
+}

@@ -1,0 +1,54 @@
+"""Register the B200 kernels in the reference's own plugin points.
+
+The reference resolves the three hot-path classes by name on Python modules:
+  * ``getattr(losses, config.cl_loss.type)``                      avssl/model/kwClip.py:84
+  * ``getattr(vector_quantizers, vq.type)``                       avssl/model/kw_branches.py:75-91
+  * ``WeightedSumLayer(...)`` imported by name                    avssl/module/speech_encoder_plus.py:24, :218-220, :472-476
+  * the cosine + lookup glue is a method of ``GeneralBranch``     avssl/model/kw_branches.py:158-197
+
+``install()`` must run after ``import avssl`` and before the model is constructed.
+"""
+from __future__ import annotations
+
+import importlib
+import sys
+
+
+def install(avssl_package: str = "avssl", strict: bool = False) -> dict:
+    """Swap the reference classes for the CUDA-backed ones.  Returns {dotted name: replaced?}."""
+    from .module.losses import MaskedContrastiveLoss
+    from .module.vector_quantizers import SimpleVectorQuantizer, fused_vq_audio_features
+    from .module.weighted_sum import WeightedSumLayer
+
+    done = {}
+
+    def patch(mod_name: str, attr: str, value) -> None:
+        key = f"{mod_name}.{attr}"
+        try:
+            mod = sys.modules.get(mod_name) or importlib.import_module(mod_name)
+        except Exception:
+            if strict:
+                raise
+            done[key] = False
+            return
+        setattr(mod, attr, value)
+        done[key] = True
+
+    p = avssl_package
+    patch(f"{p}.module.losses", "MaskedContrastiveLoss", MaskedContrastiveLoss)
+    patch(f"{p}.module", "MaskedContrastiveLoss", MaskedContrastiveLoss)
+    patch(f"{p}.module.weighted_sum", "WeightedSumLayer", WeightedSumLayer)
+    patch(f"{p}.module.speech_encoder_plus", "WeightedSumLayer", WeightedSumLayer)
+    patch(f"{p}.module", "WeightedSumLayer", WeightedSumLayer)
+    patch(f"{p}.module.speechclip_c_modules.my_vector_quantizer", "SimpleVectorQuantizer", SimpleVectorQuantizer)
+    patch(f"{p}.module.speechclip_c_modules.vector_quantizers", "SimpleVectorQuantizer", SimpleVectorQuantizer)
+    # the fused cosine + quantise + lookup replaces the method body on the shared base class of all branches
+    try:
+        kb = sys.modules.get(f"{p}.model.kw_branches") or importlib.import_module(f"{p}.model.kw_branches")
+        kb.GeneralBranch.vq_audio_features = lambda self, audio_feat: fused_vq_audio_features(self, audio_feat)
+        done[f"{p}.model.kw_branches.GeneralBranch.vq_audio_features"] = True
+    except Exception:
+        if strict:
+            raise
+        done[f"{p}.model.kw_branches.GeneralBranch.vq_audio_features"] = False
+    return done

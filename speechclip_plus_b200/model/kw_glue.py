@@ -1,0 +1,167 @@
+"""Host-side glue of the hot path, mirroring the ~40 lines of reference glue around the three modules:
+
+  * the L2 normalisation of image / cascaded-audio / parallel-audio features
+    (avssl/model/kwClip.py:857, :905-907, :913-915),
+  * the gather point of the data-parallel step (``training_step_end``, kwClip.py:149-193): the reference lets
+    ``nn.DataParallel`` copy every replica's ``loss_feats`` to GPU 0; here each process packs its normalised features
+    and ids into one buffer (scp_l2norm_pack) and a single NCCL all-gather over NVLink delivers the global batch to
+    every rank, which then evaluates the global-negatives loss redundantly and back-propagates into its own rows,
+  * ``compute_loss`` (kwClip.py:999-1040).
+
+The collective itself is plain ``torch.distributed`` plumbing (one all-gather of <= 0.8 MB per rank: latency-bound).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .. import _lib
+
+FEAT_KEYS = ("image_feat", "cascaded_audio_feat", "parallel_audio_feat")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# device-agnostic plumbing (exercised on CPU with gloo in tests/test_multiproc_gloo.py)
+# ---------------------------------------------------------------------------------------------------------------
+def shard_rows(n_local: int, rank: int) -> Tuple[int, int]:
+    """Rows of the gathered global batch that belong to ``rank`` (every rank contributes ``n_local`` rows)."""
+    return rank * n_local, (rank + 1) * n_local
+
+
+def pack_nbytes(n_feats: int, n: int, D: int) -> int:
+    return n_feats * n * D * 4 + n * 8
+
+
+def all_gather_packed(packed: torch.Tensor, group=None) -> torch.Tensor:
+    """All-gather one packed uint8 buffer per rank -> (world, nbytes).  Works for NCCL (device) and gloo (host)."""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if world == 1:
+        return packed.reshape(1, -1)
+    out = torch.empty((world, packed.numel()), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(out, packed.reshape(-1), group=group)
+    return out
+
+
+def unpack_gathered(gathered: torch.Tensor, n_feats: int, n: int, D: int) -> Tuple[List[torch.Tensor], torch.Tensor]:
+    """(world, nbytes) uint8 -> ([ (world*n, D) float32 ] * n_feats, (world*n,) int64), rank-major row order."""
+    world = gathered.shape[0]
+    fbytes = n * D * 4
+    feats = []
+    for f in range(n_feats):
+        blk = gathered[:, f * fbytes:(f + 1) * fbytes].contiguous().view(torch.float32)
+        feats.append(blk.reshape(world * n, D))
+    ids = gathered[:, n_feats * fbytes:n_feats * fbytes + n * 8].contiguous().view(torch.int64).reshape(world * n)
+    return feats, ids
+
+
+def ddp_grad_scale(world_size: int) -> float:
+    """Every rank back-propagates the GLOBAL loss into its local rows only.  DDP then averages parameter gradients
+    over ranks; multiplying the loss (or the gradients) by ``world_size`` makes the all-reduced result equal to the
+    reference's single-process gradient of the same global loss."""
+    return float(world_size)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CUDA pieces
+# ---------------------------------------------------------------------------------------------------------------
+class _NormPackGatherFn(torch.autograd.Function):
+    """(ids, feats...) -> (global ids, global normalised feats...); gradients flow to the local feature rows only."""
+
+    @staticmethod
+    def forward(ctx, ids: torch.Tensor, group, *feats: torch.Tensor):
+        lib = _lib.load()
+        f0 = feats[0]
+        _lib.require_cuda(f0, "gather_loss_feats")
+        n, D = f0.shape
+        dev = f0.device
+        srcs = []
+        for f in feats:
+            assert f.shape == (n, D), (f.shape, (n, D))
+            fd = f.detach()
+            if fd.dtype != f0.dtype:
+                fd = fd.to(f0.dtype)
+            srcs.append(fd.contiguous())
+        ids64 = ids.detach().reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
+        nbytes = int(lib.scp_pack_bytes(len(srcs), n, D))
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        inv = torch.empty((len(srcs), n), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = lib.scp_l2norm_pack(_lib.ptr_array(srcs), len(srcs), n, D, _lib.dtype_code(f0.dtype),
+                                     _lib.ptr(ids64), _lib.ptr(packed), _lib.ptr(inv), _lib.stream_ptr(dev))
+        _lib.check(st, "scp_l2norm_pack")
+        gathered = all_gather_packed(packed, group)
+        g_feats, g_ids = unpack_gathered(gathered, len(srcs), n, D)
+        rank = dist.get_rank(group) if gathered.shape[0] > 1 else 0
+        ctx.rows = shard_rows(n, rank)
+        ctx.n_feats = len(srcs)
+        ctx.in_dtypes = [f.dtype for f in feats]
+        ctx.save_for_backward(inv, *[g[ctx.rows[0]:ctx.rows[1]] for g in g_feats])
+        ctx.mark_non_differentiable(g_ids)
+        return (g_ids, *g_feats)
+
+    @staticmethod
+    def backward(ctx, _g_ids, *g_feats):
+        lib = _lib.load()
+        inv, *f_hat = ctx.saved_tensors
+        r0, r1 = ctx.rows
+        grads = []
+        for f in range(ctx.n_feats):
+            g = g_feats[f]
+            if g is None or not ctx.needs_input_grad[2 + f]:
+                grads.append(None)
+                continue
+            g_loc = g[r0:r1].float().contiguous()
+            fh = f_hat[f].contiguous()
+            n, D = fh.shape
+            out = torch.empty_like(fh)
+            with torch.cuda.device(fh.device):
+                st = lib.scp_l2norm_bwd(_lib.ptr(g_loc), _lib.ptr(fh), _lib.ptr(inv[f].contiguous()), n, D,
+                                        _lib.ptr(out), _lib.stream_ptr(fh.device))
+            _lib.check(st, "scp_l2norm_bwd")
+            grads.append(out.to(ctx.in_dtypes[f]))
+        return (None, None, *grads)
+
+
+def gather_loss_feats(loss_feats: Dict[str, torch.Tensor], group=None) -> Tuple[Dict[str, torch.Tensor], Tuple[int, int]]:
+    """Normalise (kwClip.py:857/:905/:913), pack and all-gather the UN-normalised ``image_feat`` /
+    ``cascaded_audio_feat`` / ``parallel_audio_feat`` entries and ``id`` of ``loss_feats``.
+
+    Returns the global ``loss_feats`` dict (same keys) and this rank's ``(row_begin, row_end)``."""
+    keys = [k for k in FEAT_KEYS if loss_feats.get(k) is not None]
+    feats = [loss_feats[k] for k in keys]
+    outs = _NormPackGatherFn.apply(loss_feats["id"], group, *feats)
+    g_ids, g_feats = outs[0], outs[1:]
+    out = dict(loss_feats)
+    out["id"] = g_ids
+    for k, g in zip(keys, g_feats):
+        out[k] = g
+    n = feats[0].shape[0]
+    world = g_ids.shape[0] // n
+    rank = dist.get_rank(group) if world > 1 else 0
+    return out, shard_rows(n, rank)
+
+
+def compute_loss(loss_feats: Dict[str, torch.Tensor], criterion, cascaded_objective_weight: float = 0.0,
+                 parallel_objective_weight: float = 0.0, quantity_loss_weight: float = 0.0,
+                 quantity_loss_criteria=None, local_rows: Optional[Tuple[int, int]] = None) -> Dict[str, torch.Tensor]:
+    """``KWClip_GeneralTransformer.compute_loss`` (kwClip.py:999-1040) with the same keys in and out."""
+    assert isinstance(loss_feats, dict)
+    required_keys = {"id", "image_feat"}
+    assert required_keys.issubset(set(loss_feats.keys())), f"required: {required_keys}, input: {loss_feats.keys()}"
+    losses = {"loss": 0}
+    image_feat = loss_feats["image_feat"].float()
+    ids = loss_feats["id"]
+    for branch, weight in (("cascaded", cascaded_objective_weight), ("parallel", parallel_objective_weight)):
+        if weight > 0.0:
+            key = f"{branch}_audio_feat"
+            assert key in loss_feats, f"{loss_feats.keys()}"
+            kwargs = {} if local_rows is None else {"local_rows": local_rows}
+            losses[f"{branch[0]}_cl_loss"] = criterion(feat_A=loss_feats[key].float(), feat_B=image_feat, index=ids,
+                                                      **kwargs)
+            losses["loss"] = losses["loss"] + weight * losses[f"{branch[0]}_cl_loss"]
+    if ("cif_quantity_out" in loss_feats and "cif_target_len" in loss_feats and quantity_loss_criteria is not None):
+        losses["quantity_loss"] = quantity_loss_criteria(loss_feats["cif_quantity_out"], loss_feats["cif_target_len"])
+        losses["loss"] = losses["loss"] + quantity_loss_weight * losses["quantity_loss"]
+    return losses

@@ -1,0 +1,137 @@
+"""Drop-in for ``avssl.module.losses.MaskedContrastiveLoss`` (reference: avssl/module/losses.py:129-245).
+
+Same constructor kwargs, the same ``temperature`` attribute (0-d log-scale Parameter when trainable, python float
+``1/temperature`` otherwise), the ``current_temperature`` property, the ``eye_mat / neg_eye_mat / eye_mat_fl``
+buffers (kept only so that released checkpoints load; the kernels never read them) and
+``forward(feat_A, feat_B, index=None) -> 0-d Tensor``.  Differences, all deliberate:
+  * no batch-size limit (the reference raises IndexError for N > MAX_EYE = 256, losses.py:126);
+  * log-sum-exp with max-subtraction instead of a raw ``exp`` (losses.py:232): identical value, no overflow;
+  * no host synchronisation inside ``forward`` (the reference's boolean-mask indexing syncs twice per call).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import _lib
+
+MAX_EYE = 256  # losses.py:126 -- only the size of the compatibility buffers
+
+
+class _MaskedNceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat_a, feat_b, log_scale, index, fixed_scale, margin, dcl, a2b, b2a, row_begin, row_end):
+        lib = _lib.load()
+        _lib.require_cuda(feat_a, "MaskedContrastiveLoss")
+        N, D = feat_a.shape
+        dev = feat_a.device
+        a = feat_a.detach()
+        b = feat_b.detach()
+        if a.dtype != torch.float32 or not a.is_contiguous():
+            a = a.float().contiguous()
+        if b.dtype != torch.float32 or not b.is_contiguous():
+            b = b.float().contiguous()
+        ids = None
+        if index is not None:
+            ids = index.detach().reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
+            assert ids.shape[0] == N, (ids.shape, feat_a.shape)  # losses.py:205
+        ls = None
+        if log_scale is not None:
+            ls = log_scale.detach().reshape(1).float().contiguous()
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        lse_row = torch.empty(N, dtype=torch.float32, device=dev)
+        lse_col = torch.empty(N, dtype=torch.float32, device=dev)
+        ws_bytes = lib.scp_nce_workspace_bytes(N, D)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            st = lib.scp_nce_fwd(_lib.ptr(a), _lib.ptr(b), _lib.ptr(ids), N, D, _lib.ptr(ls), float(fixed_scale),
+                                 float(margin), int(dcl), int(a2b), int(b2a), _lib.ptr(loss), _lib.ptr(lse_row),
+                                 _lib.ptr(lse_col), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
+        _lib.check(st, "scp_nce_fwd")
+        ctx.save_for_backward(a, b, ids, ls, lse_row, lse_col)
+        ctx.cfg = (float(fixed_scale), float(margin), int(dcl), int(a2b), int(b2a), int(row_begin), int(row_end))
+        ctx.in_dtypes = (feat_a.dtype, feat_b.dtype)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        lib = _lib.load()
+        a, b, ids, ls, lse_row, lse_col = ctx.saved_tensors
+        fixed_scale, margin, dcl, a2b, b2a, row_begin, row_end = ctx.cfg
+        N, D = a.shape
+        dev = a.device
+        n_local = row_end - row_begin
+        g = g_loss.detach().reshape(1).float().contiguous()
+        need_b = ctx.needs_input_grad[1]
+        need_t = ls is not None and ctx.needs_input_grad[2]
+        dA = torch.empty((n_local, D), dtype=torch.float32, device=dev)
+        dB = torch.empty((n_local, D), dtype=torch.float32, device=dev) if need_b else None
+        dT = torch.empty(1, dtype=torch.float32, device=dev) if need_t else None
+        ws_bytes = lib.scp_nce_workspace_bytes(N, D)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            st = lib.scp_nce_bwd(_lib.ptr(a), _lib.ptr(b), _lib.ptr(ids), N, D, _lib.ptr(ls), fixed_scale, margin,
+                                 dcl, a2b, b2a, _lib.ptr(lse_row), _lib.ptr(lse_col), _lib.ptr(g), row_begin,
+                                 row_end, _lib.ptr(dA), _lib.ptr(dB), _lib.ptr(dT), _lib.ptr(ws), ws_bytes,
+                                 _lib.stream_ptr(dev))
+        _lib.check(st, "scp_nce_bwd")
+
+        def full(local: Optional[torch.Tensor], dtype) -> Optional[torch.Tensor]:
+            if local is None:
+                return None
+            if n_local == N:
+                return local.to(dtype)
+            out = torch.zeros((N, D), dtype=dtype, device=dev)  # rows owned by other ranks get no gradient here
+            out[row_begin:row_end] = local
+            return out
+
+        gA = full(dA, ctx.in_dtypes[0]) if ctx.needs_input_grad[0] else None
+        gB = full(dB, ctx.in_dtypes[1])
+        gT = dT.reshape(()) if dT is not None else None
+        return gA, gB, gT, None, None, None, None, None, None, None, None
+
+
+class MaskedContrastiveLoss(nn.Module):
+    def __init__(self, temperature: float = 0.07, temperature_trainable: bool = False, margin: float = 0.0,
+                 dcl: bool = False, a2b: bool = True, b2a: bool = True):
+        """Masked Contrastive Loss (losses.py:130-168)."""
+        super().__init__()
+        assert a2b or b2a, "Cannot set both `a2b` and `b2a` to False."
+        self.temperature_trainable = temperature_trainable
+        self.margin = margin
+        self.dcl = dcl
+        self.a2b = a2b
+        self.b2a = b2a
+        if temperature_trainable:
+            self.temperature = nn.Parameter(torch.ones([]) * np.log(1 / temperature))
+        else:
+            self.temperature = 1 / temperature
+        eye_mat = torch.eye(MAX_EYE, dtype=torch.bool)
+        self.register_buffer("eye_mat", eye_mat)
+        self.register_buffer("neg_eye_mat", ~eye_mat)
+        self.register_buffer("eye_mat_fl", eye_mat.type(torch.float))
+
+    @property
+    def current_temperature(self) -> float:
+        """losses.py:170-183 (a host read of the learnable scale; only used for logging)."""
+        if self.temperature_trainable:
+            temp = self.temperature.data.cpu().detach().float().exp().item()
+        else:
+            temp = self.temperature
+        return float(temp)
+
+    def forward(self, feat_A: torch.Tensor, feat_B: torch.Tensor, index: torch.LongTensor = None,
+                local_rows: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+        """``local_rows=(begin, end)`` (extension for the one-process-per-GPU layout): the loss is the global one over
+        all rows, gradients are produced only for this rank's rows -- see ``model.kw_glue.gather_loss_feats``."""
+        assert feat_A.shape == feat_B.shape, (feat_A.shape, feat_B.shape)  # losses.py:199
+        N = feat_A.shape[0]
+        begin, end = (0, N) if local_rows is None else local_rows
+        if self.temperature_trainable:
+            return _MaskedNceFn.apply(feat_A, feat_B, self.temperature, index, 0.0, self.margin, self.dcl,
+                                      self.a2b, self.b2a, begin, end)
+        return _MaskedNceFn.apply(feat_A, feat_B, None, index, float(self.temperature), self.margin, self.dcl,
+                                  self.a2b, self.b2a, begin, end)

@@ -1,0 +1,110 @@
+"""Drop-in for ``avssl.module.weighted_sum.WeightedSumLayer`` (reference: avssl/module/weighted_sum.py:10-45).
+
+Same constructor, parameter name (``weights``, zeros-initialised, shape ``(n_weights,)``), ``state_dict`` key and
+``forward(x: List[Tensor]) -> Tensor`` contract; the arithmetic runs in the sm_100a kernels of csrc/scp_wsum.cu
+(one pass over the L layer tensors, no ``torch.stack`` copy, no broadcast temporaries).
+"""
+from __future__ import annotations
+
+import ctypes
+import logging
+from typing import List, Sequence
+
+import torch
+from torch import nn
+
+from .. import _lib
+
+logger = logging.getLogger(__name__)
+
+LN_EPS = 1e-5  # F.layer_norm default, weighted_sum.py:42
+
+
+def _uniform_views(layers: Sequence[torch.Tensor]):
+    """The kernel reads every layer as x[b*sb + t*st + d].  Layers that already share such a layout (the HuBERT
+    wrapper hands over (T,B,D) storage viewed as (B,T,D)) are used in place; anything else is made contiguous."""
+    x0 = layers[0]
+    ne = 4 if x0.dtype == torch.float32 else 8
+    ok = all(
+        l.dim() == 3 and l.shape == x0.shape and l.dtype == x0.dtype and l.device == x0.device and l.stride(2) == 1
+        and l.stride() == x0.stride() and l.stride(0) % ne == 0 and l.stride(1) % ne == 0 and l.data_ptr() % 16 == 0
+        for l in layers)
+    if ok:
+        return list(layers)
+    return [l.contiguous() for l in layers]
+
+
+class _WeightedSumFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weights: torch.Tensor, normalize: bool, *layers: torch.Tensor):
+        lib = _lib.load()
+        x0 = layers[0]
+        _lib.require_cuda(x0, "WeightedSumLayer")
+        lead_shape = x0.shape[:-1]
+        D = x0.shape[-1]
+        if x0.dim() != 3:  # (..., D) -> (1, R, D)
+            layers = tuple(l.reshape(1, -1, D) for l in layers)
+        views = _uniform_views(layers)
+        v0 = views[0]
+        B, T, _ = v0.shape
+        w = weights.detach().float().contiguous()
+        y = torch.empty((B, T, D), dtype=torch.float32, device=v0.device)
+        ptrs = _lib.ptr_array(views)
+        with torch.cuda.device(v0.device):
+            st = lib.scp_wsum_fwd(ptrs, len(views), B, T, D, v0.stride(0), v0.stride(1), _lib.dtype_code(v0.dtype),
+                                  _lib.ptr(w), int(normalize), LN_EPS, _lib.ptr(y), _lib.SCP_F32,
+                                  _lib.stream_ptr(v0.device))
+        _lib.check(st, "scp_wsum_fwd")
+        ctx.normalize = bool(normalize)
+        ctx.save_for_backward(w, *views)
+        ctx.lead_shape = lead_shape
+        ctx.in_shapes = [l.shape for l in layers]
+        return y.reshape(*lead_shape, D)
+
+    @staticmethod
+    def backward(ctx, grad_y: torch.Tensor):
+        lib = _lib.load()
+        w, *views = ctx.saved_tensors
+        v0 = views[0]
+        B, T, D = v0.shape
+        L = len(views)
+        g = grad_y.reshape(B, T, D).float().contiguous()
+        need_layers = any(ctx.needs_input_grad[2:])
+        d_w = torch.empty(L, dtype=torch.float32, device=v0.device)
+        g_layers = None
+        g_ptrs = None
+        if need_layers:
+            g_layers = [torch.empty((B, T, D), dtype=torch.float32, device=v0.device) for _ in range(L)]
+            g_ptrs = _lib.ptr_array(g_layers)
+        ws_bytes = lib.scp_wsum_bwd_workspace_bytes(L, B, T, D)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=v0.device)
+        with torch.cuda.device(v0.device):
+            st = lib.scp_wsum_bwd(_lib.ptr_array(views), L, B, T, D, v0.stride(0), v0.stride(1),
+                                  _lib.dtype_code(v0.dtype), _lib.ptr(w), int(ctx.normalize), LN_EPS,
+                                  _lib.ptr(g), _lib.SCP_F32, _lib.ptr(d_w),
+                                  g_ptrs if g_ptrs is not None else ctypes.cast(None, ctypes.POINTER(ctypes.c_void_p)),
+                                  _lib.ptr(ws), ws_bytes, _lib.stream_ptr(v0.device))
+        _lib.check(st, "scp_wsum_bwd")
+        grads = [None] * L
+        if need_layers:
+            for i in range(L):
+                if ctx.needs_input_grad[2 + i]:
+                    grads[i] = g_layers[i].reshape(ctx.in_shapes[i]).to(views[i].dtype)
+        return (d_w, None, *grads)
+
+
+class WeightedSumLayer(nn.Module):
+    def __init__(self, n_weights: int, normalize_features: bool = False):
+        """Softmax-weighted sum of ``n_weights`` hidden representations (weighted_sum.py:11-24)."""
+        super().__init__()
+        if n_weights > _lib.SCP_MAX_LAYERS:
+            raise _lib.ScpError(f"n_weights={n_weights} > {_lib.SCP_MAX_LAYERS}")
+        self.n_weights = n_weights
+        self.weights = nn.Parameter(torch.zeros((n_weights,), dtype=torch.float))
+        self.normalize_features = normalize_features
+        if self.normalize_features:
+            logger.info("Normalize feature before weighted sum")
+
+    def forward(self, x: List[torch.Tensor]) -> torch.Tensor:
+        assert len(x) == self.n_weights, len(x)  # weighted_sum.py:36
+        return _WeightedSumFn.apply(self.weights, self.normalize_features, *x)
