@@ -1,0 +1,422 @@
+"""bench.py -- train pairs/sec of the SpeechCLIP+ data-parallel hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference algorithm's CPU path (oracle port) on the host cores
+
+Workload (config.workload = "c3_cascaded_plus_base", BASELINE.json configs[2] -- the config the metric is quoted on at
+1/2/4/8 GPUs, and it fits one GPU): per GPU 256 audio-image pairs; one STEP is one pass of the hot path:
+  S1  weighted sum over L=13 HuBERT-base hidden states (256 x 249 x 768 fp32 each, (T,B,D) storage)   fwd + bwd(weights)
+  S2  keyword VQ: M = 256*8 = 2048 keyword rows vs the 49408 x 512 CLIP token table                   fwd + bwd
+  N0/G0  L2-normalise + pack + all-gather of the (256 x 512) audio / image features and ids
+  S3  masked InfoNCE over the gathered global batch N = 256 * n_gpus                                   fwd + bwd
+The frozen HuBERT / CLIP towers and the branch transformer are out of scope: their outputs are
+synthetic tensors of the named shapes (seeded), resident in HBM before the timed region.  Scaling is WEAK: per-GPU
+work is fixed, the loss sees the global batch.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train pairs/sec (hot path: layer weighted-sum + keyword VQ + masked InfoNCE, fwd+bwd)"
+UNIT = "pairs/s"
+WORKLOAD = dict(workload="c3_cascaded_plus_base", per_gpu_batch=256, hubert_layers=13, frames=249, hubert_dim=768,
+                keywords=8, vocab=49408, clip_dim=512, loss="masked InfoNCE, cascaded branch, trainable temperature",
+                vq_temp="fixed=0.1", l2_policy="inputs (2.7 GB/step) exceed the 126 MB L2; no explicit flush")
+SEED = 7122
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], tflops=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    tflops_burst=p["bf16_tflops"], source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, tflops_burst=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+# =====================================================================================================================
+# clocks sampler
+# =====================================================================================================================
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 8:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[1]))
+                smax = max(smax, float(s[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, s[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=smax or None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# =====================================================================================================================
+# CPU arm: the reference algorithm (oracle port) on the host cores
+# =====================================================================================================================
+def cpu_hot_path_step(state):
+    """One pass of the same hot path with the oracle (plain torch CPU ops, structured like the reference, incl. the
+    per-keyword cosine loop of kw_branches.py:167-177)."""
+    import torch
+    from oracle import speechclip_oracle as oracle
+    layers, w, gy, kw, table, img, ids, logt = (state[k] for k in ("layers", "w", "gy", "kw", "table", "img", "ids", "logt"))
+    y = oracle.wsum_forward(layers, w)
+    (dw,) = torch.autograd.grad(y, [w], grad_outputs=gy)
+    vq, kws = oracle.vq_audio_features(kw, table, torch.tensor([0.1]), training=True, faithful_loop=True)
+    feat = oracle.l2_normalise(kws.mean(dim=1))
+    loss = oracle.nce_forward(feat, oracle.l2_normalise(img), ids, logt.exp())
+    g_kw, g_t = torch.autograd.grad(loss, [kw, logt])
+    return float(loss.detach())
+
+
+def make_cpu_state(batch: int):
+    import math
+    import torch
+    g = torch.Generator().manual_seed(SEED)
+    L, T, Da, K, V, D = (WORKLOAD[k] for k in ("hubert_layers", "frames", "hubert_dim", "keywords", "vocab", "clip_dim"))
+    storage = [torch.randn(T, batch, Da, generator=g) for _ in range(L)]
+    return dict(layers=[s.transpose(0, 1) for s in storage], w=(torch.randn(L, generator=g) * 0.5).requires_grad_(True),
+                gy=torch.randn(batch, T, Da, generator=g), table=torch.randn(V, D, generator=g) * 0.02,
+                kw=(torch.randn(batch, K, D, generator=g) * 0.02).requires_grad_(True),
+                img=torch.randn(batch, D, generator=g), ids=torch.arange(batch),
+                logt=torch.tensor(math.log(1 / 0.07), requires_grad=True))
+
+
+def time_cpu(batch: int, steps: int, warmup: int):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    state = make_cpu_state(batch)
+    for _ in range(warmup):
+        cpu_hot_path_step(state)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_hot_path_step(state)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return dict(value=batch / dt, unit=UNIT, cores=cores, kind="port",
+                sample=f"same hot-path step on a {batch}-pair slice of the workload (full 49408x512 table, per-keyword "
+                       f"cosine loop as in the reference), {steps} timed step(s), {dt:.2f} s/step, torch CPU fp32"), dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 2 if args.steps + args.warmup <= 30 else 1  # bounded sample: ~3-6 s of CPU work per step
+    cb, dt = time_cpu(batch, args.steps, max(args.warmup, 1))
+    line = dict(metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference", config=dict(WORKLOAD, cpu_sample_pairs=batch),
+                cpu_baseline=cb, e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# =====================================================================================================================
+# GPU arm
+# =====================================================================================================================
+class HotPath:
+    """Device-resident state + one step of the hot path through the public modules."""
+
+    def __init__(self, dev, rank, world, group=None):
+        import math
+        import torch
+        import speechclip_plus_b200 as scp
+        self.torch, self.scp, self.dev, self.rank, self.world, self.group = torch, scp, dev, rank, world, group
+        w = WORKLOAD
+        self.B, self.L, self.T, self.Da = w["per_gpu_batch"], w["hubert_layers"], w["frames"], w["hubert_dim"]
+        self.K, self.V, self.D = w["keywords"], w["vocab"], w["clip_dim"]
+        g = torch.Generator(device=dev).manual_seed(SEED + rank)
+        B, L, T, Da, K, V, D = self.B, self.L, self.T, self.Da, self.K, self.V, self.D
+        # HuBERT hands over L tensors of (T,B,D) storage viewed as (B,T,D) (speech_encoder_plus.py:596-599)
+        self.storage = [torch.randn(T, B, Da, device=dev, generator=g) for _ in range(L)]
+        self.layers = [s.transpose(0, 1) for s in self.storage]
+        self.grad_y = torch.randn(B, T, Da, device=dev, generator=g)
+        gt = torch.Generator(device=dev).manual_seed(SEED)  # the frozen table is identical on every rank
+        self.table = torch.randn(V, D, device=dev, generator=gt) * 0.02
+        self.kw = (torch.randn(B, K, D, device=dev, generator=g) * 0.02).requires_grad_(True)
+        self.img = torch.randn(B, D, device=dev, generator=g)
+        self.ids = torch.randint(0, 6000, (B,), device=dev, generator=g)  # Flickr8k: 6000 training images x 5 captions
+        self.wsum = scp.WeightedSumLayer(L).to(dev)
+        with torch.no_grad():
+            self.wsum.weights.copy_(torch.linspace(-0.5, 0.5, L))
+        self.vq = scp.SimpleVectorQuantizer(w["vq_temp"]).to(dev).train()
+        self.crit = scp.MaskedContrastiveLoss(temperature=0.07, temperature_trainable=True).to(dev)
+        self.params = [self.wsum.weights, self.crit.temperature, self.kw]
+
+    def step(self):
+        torch, scp = self.torch, self.scp
+        for p in self.params:
+            p.grad = None
+        y = self.wsum(self.layers)                                             # S1 fwd
+        res, kws = self.vq.quantize_keywords(self.kw, self.table)              # V1+V3+V4 fwd
+        feats = {"id": self.ids, "image_feat": self.img, "cascaded_audio_feat": kws.mean(dim=1)}
+        gathered, rows = scp.gather_loss_feats(feats, self.group)              # N0 + G0 (NCCL all-gather when world > 1)
+        out = scp.compute_loss(gathered, self.crit, cascaded_objective_weight=1.0, local_rows=rows)   # S3 fwd
+        loss = out["loss"] * scp.ddp_grad_scale(self.world)
+        torch.autograd.backward([loss, y], [None, self.grad_y])               # S3 bwd, V bwd, S1 bwd
+        return out["loss"].detach(), res
+
+    # ---- host-buffer variant for the end-to-end number ----------------------------------------------------------
+    def make_host_buffers(self):
+        torch = self.torch
+        self.h_storage = [s.cpu().pin_memory() for s in self.storage]
+        self.h_grad_y = self.grad_y.cpu().pin_memory()
+        self.h_kw = self.kw.detach().cpu().pin_memory()
+        self.h_img = self.img.cpu().pin_memory()
+        self.h_ids = self.ids.cpu().pin_memory()
+        self.h_loss = torch.empty((), dtype=torch.float32).pin_memory()
+        self.h_dw = torch.empty(self.L, dtype=torch.float32).pin_memory()
+        self.h_gkw = torch.empty_like(self.h_kw).pin_memory()
+        self.h2d_bytes = (sum(t.numel() * t.element_size() for t in self.h_storage) + self.h_grad_y.numel() * 4 +
+                          self.h_kw.numel() * 4 + self.h_img.numel() * 4 + self.h_ids.numel() * 8)
+        self.d2h_bytes = 4 + self.h_dw.numel() * 4 + self.h_gkw.numel() * 4
+
+    def step_e2e(self):
+        torch = self.torch
+        for d, h in zip(self.storage, self.h_storage):
+            d.copy_(h, non_blocking=True)
+        self.grad_y.copy_(self.h_grad_y, non_blocking=True)
+        with torch.no_grad():
+            self.kw.copy_(self.h_kw, non_blocking=True)
+        self.img.copy_(self.h_img, non_blocking=True)
+        self.ids.copy_(self.h_ids, non_blocking=True)
+        loss, _ = self.step()
+        self.h_loss.copy_(loss, non_blocking=True)
+        self.h_dw.copy_(self.wsum.weights.grad, non_blocking=True)
+        self.h_gkw.copy_(self.kw.grad, non_blocking=True)
+
+
+def time_region(torch, dist_mod, world, fn, steps):
+    """barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks."""
+    if world > 1:
+        dist_mod.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
+        ms = float(t.item())
+        dist_mod.barrier()
+    return ms
+
+
+def kernel_breakdown(hp: "HotPath", iters: int = 10):
+    """Per-API-call device time (CUDA events around the C-ABI calls, after warm-up) and achieved roofline numbers."""
+    import ctypes
+    torch = hp.torch
+    from speechclip_plus_b200 import _lib
+    lib = _lib.load()
+    dev = hp.dev
+    B, L, T, Da, K, V, D = hp.B, hp.L, hp.T, hp.Da, hp.K, hp.V, hp.D
+    M = B * K
+    stream = _lib.stream_ptr(dev)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        for a, b in evs:
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        return statistics.median(a.elapsed_time(b) for a, b in evs) * 1e-3  # seconds
+
+    out = {}
+    # S1 forward / backward
+    w = hp.wsum.weights.detach()
+    y = torch.empty((B, T, Da), device=dev)
+    ptrs = _lib.ptr_array(hp.layers)
+    v0 = hp.layers[0]
+    t = timed(lambda: lib.scp_wsum_fwd(ptrs, L, B, T, Da, v0.stride(0), v0.stride(1), 0, _lib.ptr(w), 0, 1e-5,
+                                       _lib.ptr(y), 0, stream))
+    by = (L + 1) * B * T * Da * 4
+    out["wsum_fwd"] = dict(seconds=t, bound="hbm", algorithmic=by, achieved=by / t / 1e9, unit="GB/s")
+    dw = torch.empty(L, device=dev)
+    ws_b = lib.scp_wsum_bwd_workspace_bytes(L, B, T, Da)
+    ws = torch.empty(ws_b, dtype=torch.uint8, device=dev)
+    null_pp = ctypes.cast(None, ctypes.POINTER(ctypes.c_void_p))
+    t = timed(lambda: lib.scp_wsum_bwd(ptrs, L, B, T, Da, v0.stride(0), v0.stride(1), 0, _lib.ptr(w), 0, 1e-5,
+                                       _lib.ptr(hp.grad_y), 0, _lib.ptr(dw), null_pp, _lib.ptr(ws), ws_b, stream))
+    out["wsum_bwd"] = dict(seconds=t, bound="hbm", algorithmic=by, achieved=by / t / 1e9, unit="GB/s")
+    # S2 forward / backward through the module (includes its small helper kernels)
+    kw = hp.kw.detach().clone().requires_grad_(True)
+    state = {}
+
+    def vq_f():
+        state["res"], state["out"] = hp.vq.quantize_keywords(kw, hp.table)
+    t = timed(vq_f)
+    fl = 2.0 * M * V * D
+    out["vq_fwd"] = dict(seconds=t, bound="tensor", algorithmic=fl, achieved=fl / t / 1e12, unit="TFLOP/s")
+    g = torch.randn(B, K, D, device=dev)
+
+    def vq_fb():
+        vq_f()
+        torch.autograd.grad(state["out"], [kw], grad_outputs=g)
+    t2 = timed(vq_fb) - t
+    fl = 6.0 * M * V * D
+    out["vq_bwd"] = dict(seconds=t2, bound="tensor", algorithmic=fl, achieved=fl / t2 / 1e12, unit="TFLOP/s")
+    # S3 forward + backward
+    N = B
+    a = torch.nn.functional.normalize(torch.randn(N, D, device=dev), dim=-1).requires_grad_(True)
+    b = torch.nn.functional.normalize(torch.randn(N, D, device=dev), dim=-1)
+
+    def nce_fb():
+        loss = hp.crit(a, b, hp.ids)
+        torch.autograd.grad(loss, [a, hp.crit.temperature])
+    t = timed(nce_fb)
+    fl = 2.0 * N * N * D + 4.0 * N * N * D
+    out["nce_fwd_bwd"] = dict(seconds=t, bound="tensor (launch/latency-bound in practice)", algorithmic=fl,
+                              achieved=fl / t / 1e12, unit="TFLOP/s")
+    return out
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
+    import speechclip_plus_b200 as scp
+    from speechclip_plus_b200 import _lib
+    peaks = load_peaks()
+    hp = HotPath(dev, rank, world)
+    B = hp.B
+
+    # ---- parity guard: the first step's loss must match the oracle evaluated on the same features (rank 0, N = 1 GPU rows)
+    for _ in range(args.warmup):
+        hp.step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.num_launches()
+    ms = time_region(torch, dist, world, hp.step, args.steps)
+    launches = (_lib.num_launches() - launches0)
+    clocks = sampler.stop() if rank == 0 else None
+    pairs_per_s = B * world * args.steps / (ms * 1e-3)
+
+    # ---- end to end: host buffers, H2D of every input and D2H of the results inside the timed region
+    hp.make_host_buffers()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        hp.step_e2e()
+    ms_e2e = time_region(torch, dist, world, hp.step_e2e, e2e_steps)
+    e2e = dict(value=B * world * e2e_steps / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=int(hp.h2d_bytes),
+               d2h_bytes_per_step=int(hp.d2h_bytes), steps=e2e_steps, ms_per_step=ms_e2e / e2e_steps)
+
+    line = None
+    if rank == 0:
+        kb = kernel_breakdown(hp)
+        dom = max(kb, key=lambda k: kb[k]["seconds"])
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(dom)
+        d = kb[dom]
+        peak = peaks["hbm_gbs"] if d["bound"] == "hbm" else peaks["tflops_burst"]
+        roofline = dict(kernel=dom, bound=d["bound"], achieved=d["achieved"], peak=peak, unit=d["unit"],
+                        frac=d["achieved"] / peak, traffic=traffic, peak_source=peaks["source"],
+                        ms_per_launch=d["seconds"] * 1e3)
+        kernels = {}
+        for k, v in kb.items():
+            pk = peaks["hbm_gbs"] if v["bound"] == "hbm" else peaks["tflops_burst"]
+            kernels[k] = dict(ms=v["seconds"] * 1e3, achieved=v["achieved"], unit=v["unit"], frac=v["achieved"] / pk,
+                              bound=v["bound"])
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_baseline, _ = time_cpu(2, 2, 1)
+        line = dict(metric=METRIC, value=pairs_per_s, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                    data="synthetic", impl="b200",
+                    config=dict(WORKLOAD, global_batch=B * world, parallelism=f"dp{world}",
+                                numerics="fp32 I/O; VQ tensor-core operands fp16 with fp32 accumulation and exact "
+                                         "fp64 arg-max re-scoring; InfoNCE split-fp16 (hi/lo) operands"),
+                    roofline=roofline, kernels=kernels, cpu_baseline=cpu_baseline, e2e=e2e,
+                    gpu_launches=int(launches), clocks=clocks)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -39,9 +39,9 @@ def all_gather_packed(packed: torch.Tensor, group=None) -> torch.Tensor:
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     if world == 1:
         return packed.reshape(1, -1)
-    out = torch.empty((world, packed.numel()), dtype=packed.dtype, device=packed.device)
-    dist.all_gather_into_tensor(out, packed.reshape(-1), group=group)
-    return out
+    out = torch.empty(world * packed.numel(), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(out, packed.reshape(-1), group=group)  # flat output: accepted by NCCL and gloo
+    return out.reshape(world, -1)
 
 
 def unpack_gathered(gathered: torch.Tensor, n_feats: int, n: int, D: int) -> Tuple[List[torch.Tensor], torch.Tensor]:

@@ -1,0 +1,441 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).
+
+Every test drives the CUDA path through the reference-shaped Python modules, which call the C ABI of
+libscp_b200.so via ctypes, and compares with
+  (1) the committed golden fixtures produced by the REFERENCE's own classes (tests/golden/*.npz),
+  (2) the CPU oracle on seeded inputs (fp64 re-evaluation classifies arg-max ties),
+  (3) size-independent properties at BASELINE.json's full sizes.
+Tolerances (BASELINE.json north_star): VQ code indices bit-exact except exact ties; features / losses / gradients /
+logged metrics within 1e-3 relative error (max |a-b| / max |b|, or ||a-b|| / ||b|| for gradients).
+"""
+import math
+
+import pytest
+import torch
+
+from conftest import golden_names, load_golden, norm_err, rel_err
+from oracle import speechclip_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def scp():
+    import speechclip_plus_b200 as m
+    m.load_library()
+    return m
+
+
+def _temp(spec: str) -> float:
+    return float(spec.split("=")[1])
+
+
+# =====================================================================================================================
+# S1 weighted sum
+# =====================================================================================================================
+@pytest.mark.parametrize("name", golden_names("wsum_"))
+def test_wsum_golden(scp, name):
+    g = load_golden(name)
+    L = g["layers_tbd"].shape[0]
+    layer = scp.WeightedSumLayer(L, normalize_features=g["normalize"]).cuda()
+    with torch.no_grad():
+        layer.weights.copy_(g["weights"])
+    # same memory layout as the reference hands over: (T,B,D) storage viewed as (B,T,D)
+    layers = [t.cuda().transpose(0, 1).requires_grad_(True) for t in g["layers_tbd"]]
+    y = layer(layers)
+    assert y.shape == g["y"].shape and y.dtype == torch.float32
+    assert rel_err(y, g["y"]) < TOL
+    grads = torch.autograd.grad(y, [layer.weights] + layers, grad_outputs=g["grad_y"].cuda())
+    assert rel_err(grads[0], g["grad_weights"]) < TOL
+    assert norm_err(torch.stack(grads[1:]), g["grad_layers"]) < TOL
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("norm", [False, True])
+@pytest.mark.parametrize("shape", [(13, 8, 249, 768), (25, 3, 61, 1024), (5, 2, 7, 64)])
+def test_wsum_vs_oracle(scp, shape, norm, dtype):
+    L, B, T, D = shape
+    gen = torch.Generator().manual_seed(L * 1000 + T)
+    storage = [(torch.randn(T, B, D, generator=gen) * (1 + 0.2 * l) + 0.05 * l).to(dtype) for l in range(L)]
+    w = torch.randn(L, generator=gen) * 0.5
+    gy = torch.randn(B, T, D, generator=gen)
+    layer = scp.WeightedSumLayer(L, norm).cuda()
+    with torch.no_grad():
+        layer.weights.copy_(w)
+    y = layer([s.cuda().transpose(0, 1) for s in storage])
+    (dw,) = torch.autograd.grad(y, [layer.weights], grad_outputs=gy.cuda())
+    ref_layers = [s.double().transpose(0, 1) for s in storage]
+    y_ref = oracle.wsum_forward(ref_layers, w.double(), norm)
+    dw_ref = oracle.wsum_grad_weights(ref_layers, w.double(), gy.double(), norm)
+    assert rel_err(y, y_ref) < TOL
+    assert rel_err(dw, dw_ref) < TOL
+
+
+def test_wsum_contiguous_and_generic_inputs(scp):
+    L, B, T, D = 4, 3, 5, 128
+    gen = torch.Generator().manual_seed(1)
+    xs = [torch.randn(B, T, D, generator=gen) for _ in range(L)]
+    layer = scp.WeightedSumLayer(L).cuda()
+    y = layer([x.cuda() for x in xs])  # plain contiguous (B,T,D)
+    assert rel_err(y, oracle.wsum_forward(xs, torch.zeros(L))) < 1e-5
+    y2 = layer([x.cuda()[:, :, :] if i else x.cuda().clone() for i, x in enumerate(xs)])
+    assert torch.equal(y, y2)
+    with pytest.raises(AssertionError):
+        layer([x.cuda() for x in xs[:-1]])  # weighted_sum.py:36
+    with pytest.raises(scp.ScpError):
+        layer(xs)  # CPU tensors: there is no CPU path
+
+
+def test_wsum_full_size_properties(scp):
+    """BASELINE config 2/3 per-GPU size: L=13, B=256, T=249, D=768 (2.55 GB of layer features)."""
+    L, B, T, D = 13, 256, 249, 768
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    storage = [torch.randn(T, B, D, device="cuda", generator=gen) for _ in range(L)]
+    layers = [s.transpose(0, 1) for s in storage]
+    layer = scp.WeightedSumLayer(L).cuda()
+    # (a) softmax weights sum to one: identical layers -> output equals the layer
+    y = layer([layers[0]] * L)
+    assert rel_err(y[::17, ::5], layers[0][::17, ::5]) < 1e-6
+    # (b) a dominant weight selects its layer
+    with torch.no_grad():
+        layer.weights.zero_()
+        layer.weights[7] = 60.0
+    y = layer(layers)
+    assert rel_err(y[::17, ::5], layers[7][::17, ::5]) < 1e-6
+    # (c) linearity in the layer tensors and the closed-form weight gradient on a strided sample
+    with torch.no_grad():
+        layer.weights.copy_(torch.linspace(-1, 1, L))
+    y = layer(layers)
+    w = torch.softmax(layer.weights.detach(), 0)
+    ref = sum(w[l] * layers[l][::31] for l in range(L))
+    assert rel_err(y[::31], ref) < 1e-5
+    gy = torch.randn(B, T, D, device="cuda", generator=gen)
+    (dw,) = torch.autograd.grad(y, [layer.weights], grad_outputs=gy)
+    d = torch.stack([(gy.double() * layers[l].double()).sum() for l in range(L)])
+    dw_ref = w.double() * (d - (w.double() * d).sum())
+    assert rel_err(dw, dw_ref) < TOL
+
+
+# =====================================================================================================================
+# S2 vector quantiser
+# =====================================================================================================================
+def _make_vq(scp, spec, training):
+    vq = scp.SimpleVectorQuantizer(spec).cuda()
+    vq.train(training)
+    return vq
+
+
+@pytest.mark.parametrize("name", golden_names("vq_"))
+def test_vq_fused_golden(scp, name):
+    g = load_golden(name)
+    vq = _make_vq(scp, g["temp_spec"], g["training"])
+    kw = g["keywords_in"].cuda().requires_grad_(True)
+    res, out = vq.quantize_keywords(kw, g["table"].cuda())
+    # code indices: bit-exact (this includes the fixture with exactly tied duplicate table rows and a masked best match)
+    assert torch.equal(res["targets"].cpu(), g["targets"])
+    assert res["num_vars"] == int(g["num_vars"])
+    assert rel_err(out, g["keywords_out"]) < TOL
+    for key in ("code_perplexity", "prob_perplexity", "ent_per_t", "diversity_loss"):
+        assert rel_err(res[key], g[key]) < TOL, key
+    assert math.isclose(res["temp"], float(g["temp"]), rel_tol=1e-6)
+    if g["training"]:
+        params = [kw] + ([vq.curr_temp] if g["temp_spec"].startswith("learnable") else [])
+        grads = torch.autograd.grad(out, params, grad_outputs=g["grad_keywords_out"].cuda())
+        assert norm_err(grads[0], g["grad_keywords_in"]) < TOL
+        assert rel_err(grads[0], g["grad_keywords_in"]) < 2 * TOL
+        if len(grads) > 1:
+            # the reference hands NaN to a learnable temperature (d(-inf/tau)); we return the finite closed form
+            _, g_tau = oracle.vq_keyword_grad(g["keywords_in"].double(), g["table"].double(),
+                                              torch.tensor(_temp(g["temp_spec"]), dtype=torch.float64),
+                                              g["grad_keywords_out"].double())
+            assert torch.isfinite(grads[1]).all()
+            assert rel_err(grads[1].reshape(()), g_tau) < 5 * TOL
+    else:
+        assert not out.requires_grad  # eval: one-hot lookup, no gradient path
+
+
+@pytest.mark.parametrize("name", golden_names("vq_"))
+def test_vq_dense_golden(scp, name):
+    """The reference signature SimpleVectorQuantizer.forward(x) on the dense cosine scores."""
+    g = load_golden(name)
+    vq = _make_vq(scp, g["temp_spec"], g["training"])
+    x = g["cos"].cuda().clone().requires_grad_(g["training"])
+    xin = x.clone() if g["training"] else x  # a leaf that requires grad cannot be modified in place
+    res = vq(xin)
+    assert torch.equal(res["targets"].cpu(), g["targets"])
+    assert torch.isinf(xin.detach()[..., [0, 2, 3]]).all()  # masked in place like my_vector_quantizer.py:78-79
+    assert rel_err(res["subword_prob"], g["subword_prob"]) < TOL
+    for key in ("code_perplexity", "prob_perplexity", "ent_per_t", "diversity_loss"):
+        assert rel_err(res[key], g[key]) < TOL, key
+    kw_out = res["subword_prob"] @ g["table"].cuda()  # kw_branches.py:195
+    assert rel_err(kw_out, g["keywords_out"]) < TOL
+    if g["training"]:
+        (gx,) = torch.autograd.grad(kw_out, [x], grad_outputs=g["grad_keywords_out"].cuda())
+        # reference gradient w.r.t. the cosine scores via the oracle's autograd
+        xr = g["cos"].clone().requires_grad_(True)
+        vr = oracle.vq_forward(xr, torch.tensor([_temp(g["temp_spec"])]), training=True)
+        (gr,) = torch.autograd.grad(vr["subword_prob"] @ g["table"], [xr], grad_outputs=g["grad_keywords_out"])
+        gr = torch.nan_to_num(gr, nan=0.0)
+        assert norm_err(gx, gr) < TOL
+
+
+def _tie_tolerant_index_check(idx, kw, table, prob_msk=(0, 2, 3)):
+    """Bit-exact except exact ties: a mismatch is tolerated only if the fp64 cosine gap is below fp32 summation noise."""
+    cos = oracle.cosine_scores(kw.double(), table.double())
+    cos[..., list(prob_msk)] = float("-inf")
+    flat = cos.reshape(-1, cos.shape[-1])
+    ref = flat.argmax(-1)
+    idx = idx.reshape(-1).cpu()
+    bad = (idx != ref).nonzero().flatten().tolist()
+    for m in bad:
+        gap = (flat[m, ref[m]] - flat[m, idx[m]]).item()
+        assert gap < 3e-7, f"row {m}: picked {idx[m].item()} instead of {ref[m].item()}, cosine gap {gap:.3e}"
+    return len(bad)
+
+
+@pytest.mark.parametrize("shape", [(32, 8, 8112, 512), (16, 12, 19787, 768), (7, 5, 1000, 64), (1, 1, 300, 64)])
+def test_vq_fused_vs_oracle(scp, shape):
+    B, K, V, D = shape
+    gen = torch.Generator().manual_seed(V + B)
+    table = torch.randn(V, D, generator=gen) * 0.02 + 0.003 * torch.randn(1, D, generator=gen)
+    kw = torch.randn(B, K, D, generator=gen) * table.std(0) + table.mean(0)
+    gout = torch.randn(B, K, D, generator=gen)
+    tau = 0.1
+    vq = _make_vq(scp, f"fixed={tau}", True)
+    kwd = kw.cuda().requires_grad_(True)
+    res, out = vq.quantize_keywords(kwd, table.cuda())
+    n_ties = _tie_tolerant_index_check(res["targets"], kw, table)
+    assert n_ties == 0  # random data has no 3e-7 near-ties; the exact re-scoring must reproduce the fp64 arg-max
+    ref, out_ref = oracle.vq_audio_features(kw.double(), table.double(), torch.tensor([tau], dtype=torch.float64))
+    assert rel_err(out, out_ref) < TOL
+    for key in ("code_perplexity", "prob_perplexity", "ent_per_t", "diversity_loss"):
+        assert rel_err(res[key], ref[key]) < TOL, key
+    assert rel_err(res["avg_probs"], ref["avg_probs"]) < TOL
+    (gk,) = torch.autograd.grad(out, [kwd], grad_outputs=gout.cuda())
+    g_ref, _ = oracle.vq_keyword_grad(kw.double(), table.double(), torch.tensor(tau, dtype=torch.float64), gout.double())
+    assert norm_err(gk, g_ref) < TOL
+
+
+def test_vq_edge_cases(scp):
+    V, D = 520, 64
+    gen = torch.Generator().manual_seed(5)
+    table = torch.randn(V, D, generator=gen) * 0.02
+    table[100] = 0.0  # a zero row: cosine 0 for every keyword (F.cosine_similarity eps clamp)
+    kw = torch.randn(2, 3, D, generator=gen)
+    kw[0, 1] = 0.0     # a zero keyword: all cosines 0 -> first unmasked column wins, like torch.max
+    kw[1, 0] = table[3] * 5   # best raw match masked -> must pick something else
+    kw[1, 2] = table[519] * 2  # last column
+    vq = _make_vq(scp, "fixed=0.1", False)
+    res, out = vq.quantize_keywords(kw.cuda(), table.cuda())
+    ref, out_ref = oracle.vq_audio_features(kw.double(), table.double(), torch.tensor([0.1], dtype=torch.float64),
+                                            training=False)
+    assert torch.equal(res["targets"].cpu(), ref["targets"])
+    assert res["targets"][0, 1, 0].item() == 1 and res["targets"][1, 2, 0].item() == 519
+    assert res["targets"][1, 0, 0].item() not in (0, 2, 3)
+    assert rel_err(out, out_ref) < 1e-6
+    # custom mask list and empty mask
+    res2, _ = vq.quantize_keywords(kw.cuda(), table.cuda(), prob_msk=())
+    ref2, _ = oracle.vq_audio_features(kw.double(), table.double(), torch.tensor([0.1], dtype=torch.float64),
+                                       training=False, prob_msk=())
+    assert torch.equal(res2["targets"].cpu(), ref2["targets"])
+    assert res2["targets"][1, 0, 0].item() == 3
+    with pytest.raises(IndexError):
+        vq.quantize_keywords(kw.cuda(), table.cuda(), prob_msk=(0, 9999))
+
+
+def test_vq_full_size_properties(scp):
+    """BASELINE config 3 at one GPU: M = 256 x 8 = 2048 keyword rows against the full 49408 x 512 CLIP table."""
+    B, K, V, D = 256, 8, 49408, 512
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    table = torch.randn(V, D, device="cuda", generator=gen) * 0.02
+    kw = torch.randn(B, K, D, device="cuda", generator=gen) * 0.02
+    # plant exact answers in a quarter of the rows: kw = scale * table[r]  ->  idx == r (cosine exactly maximal)
+    planted = torch.randint(4, V, (B * K // 4,), device="cuda", generator=gen)
+    rows = torch.arange(0, B * K, 4, device="cuda")
+    kw.view(-1, D)[rows] = table[planted] * 3.0
+    kw.requires_grad_(True)
+    vq = _make_vq(scp, "fixed=0.1", True)
+    res, out = vq.quantize_keywords(kw, table)
+    idx = res["targets"].view(-1)
+    assert torch.equal(idx[rows], planted)
+    assert not bool(((idx == 0) | (idx == 2) | (idx == 3)).any())          # masked codes never win
+    assert torch.equal(out.detach().view(-1, D), table[idx])                # lookup is an exact gather
+    assert abs(res["avg_probs"].sum().item() - 1.0) < 1e-4                  # mean of softmax rows sums to one
+    assert res["code_hist"].sum().item() == B * K
+    assert 1.0 <= res["code_perplexity"].item() <= B * K + 1e-3
+    assert res["prob_perplexity"].item() <= V
+    # rows are independent: a permutation of the rows permutes the codes
+    perm = torch.randperm(B * K, device="cuda", generator=gen)
+    res_p, _ = vq.quantize_keywords(kw.detach().view(-1, D)[perm].view(B, K, D), table)
+    assert torch.equal(res_p["targets"].view(-1), idx[perm])
+    # exact arg-max on a random sample of rows (fp64 on the GPU)
+    sample = torch.randint(0, B * K, (64,), device="cuda", generator=gen)
+    ks = kw.detach().view(-1, D)[sample].double()
+    cos = (ks / ks.norm(dim=1, keepdim=True)) @ (table.double() / table.double().norm(dim=1, keepdim=True)).t()
+    cos[:, [0, 2, 3]] = float("-inf")
+    assert torch.equal(cos.argmax(-1), idx[sample])
+    # the gradient through the normalisation is orthogonal to the keyword
+    gout = torch.randn(B, K, D, device="cuda", generator=gen)
+    (gk,) = torch.autograd.grad(out, [kw], grad_outputs=gout)
+    dots = (gk * kw.detach()).sum(-1).abs().max().item()
+    assert dots < 1e-3 * (gk.norm(dim=-1) * kw.detach().norm(dim=-1)).max().item()
+    assert torch.isfinite(gk).all()
+
+
+# =====================================================================================================================
+# S3 masked InfoNCE, N0 normalise + pack, C0 compute_loss
+# =====================================================================================================================
+def _crit_from_golden(scp, g):
+    return scp.MaskedContrastiveLoss(temperature=float(g["temperature"]), temperature_trainable=g["trainable"],
+                                     margin=float(g["margin"]), dcl=g["dcl"], a2b=g["a2b"], b2a=g["b2a"]).cuda()
+
+
+@pytest.mark.parametrize("name", golden_names("nce_"))
+def test_nce_golden(scp, name):
+    g = load_golden(name)
+    crit = _crit_from_golden(scp, g)
+    a = g["feat_a"].cuda().requires_grad_(True)
+    b = g["feat_b"].cuda().requires_grad_(True)
+    ids = g["ids"].cuda() if g["has_ids"] else None
+    loss = crit(a, b, ids)
+    assert loss.dim() == 0
+    assert rel_err(loss, g["loss"]) < TOL
+    assert math.isclose(crit.current_temperature, float(g["current_temperature"]), rel_tol=1e-5)
+    params = [a, b] + ([crit.temperature] if g["trainable"] else [])
+    grads = torch.autograd.grad(loss, params)
+    assert norm_err(grads[0], g["grad_a"]) < TOL
+    assert norm_err(grads[1], g["grad_b"]) < TOL
+    if g["trainable"]:
+        assert rel_err(grads[2], g["grad_temperature"]) < TOL
+
+
+@pytest.mark.parametrize("N,D", [(256, 512), (1024, 512), (512, 768), (2048, 512), (33, 64)])
+def test_nce_vs_oracle(scp, N, D):
+    gen = torch.Generator().manual_seed(N + D)
+    a = torch.nn.functional.normalize(torch.randn(N, D, generator=gen), dim=-1)
+    b = torch.nn.functional.normalize(torch.randn(N, D, generator=gen) + 0.5 * a, dim=-1)
+    ids = torch.randint(0, max(N // 5, 3), (N,), generator=gen)
+    crit = scp.MaskedContrastiveLoss(temperature=0.07, temperature_trainable=True).cuda()
+    ad, bd = a.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    loss = crit(ad, bd, ids.cuda())
+    ga, gb, gt = torch.autograd.grad(loss, [ad, bd, crit.temperature])
+    scale = 1 / 0.07
+    l_ref = oracle.nce_forward(a.double(), b.double(), ids, scale)
+    da, db, dl = oracle.nce_grads(a.double(), b.double(), ids, scale)
+    assert rel_err(loss, l_ref) < TOL
+    assert norm_err(ga, da) < TOL and norm_err(gb, db) < TOL
+    assert rel_err(gt, dl) < TOL
+
+
+def test_nce_local_rows_match_full(scp):
+    """The multi-GPU layout: every rank evaluates the global loss and back-propagates into its own rows only."""
+    N, D, world = 96, 64, 4
+    gen = torch.Generator().manual_seed(9)
+    a = torch.nn.functional.normalize(torch.randn(N, D, generator=gen), dim=-1).cuda()
+    b = torch.nn.functional.normalize(torch.randn(N, D, generator=gen), dim=-1).cuda()
+    ids = torch.randint(0, 20, (N,), generator=gen).cuda()
+    crit = scp.MaskedContrastiveLoss(temperature=0.07, temperature_trainable=True).cuda()
+    af, bf = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    full = crit(af, bf, ids)
+    gaf, gbf, gtf = torch.autograd.grad(full, [af, bf, crit.temperature])
+    n = N // world
+    ga_sum, gt_sum = torch.zeros_like(a), torch.zeros(())
+    for r in range(world):
+        ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        loss_r = crit(ar, br, ids, local_rows=(r * n, (r + 1) * n))
+        assert torch.equal(loss_r, full)
+        gar, gbr, gtr = torch.autograd.grad(loss_r, [ar, br, crit.temperature])
+        assert gar[:r * n].abs().max().item() == 0 if r else True
+        assert rel_err(gar[r * n:(r + 1) * n], gaf[r * n:(r + 1) * n]) < 1e-5
+        assert rel_err(gbr[r * n:(r + 1) * n], gbf[r * n:(r + 1) * n]) < 1e-5
+        ga_sum += gar
+        gt_sum = gt_sum + gtr.cpu()
+    assert rel_err(ga_sum, gaf) < 1e-5
+    assert rel_err(gt_sum, gtf) < 1e-4  # the scale gradient is the sum of the ranks' partial sums
+
+
+def test_nce_large_logits_do_not_overflow(scp):
+    """The reference exponentiates raw logits (losses.py:232) and overflows for a large learnt scale; LSE does not."""
+    N, D = 64, 64
+    gen = torch.Generator().manual_seed(2)
+    a = torch.nn.functional.normalize(torch.randn(N, D, generator=gen), dim=-1)
+    crit = scp.MaskedContrastiveLoss(temperature=1.0 / 200.0, temperature_trainable=False).cuda()
+    loss = crit(a.cuda(), a.cuda(), None)
+    ref = oracle.nce_forward(a.double(), a.double(), None, 200.0)
+    assert torch.isfinite(loss) and rel_err(loss, ref) < TOL
+
+
+def test_gather_and_compute_loss_golden(scp):
+    """N0 + G0 + C0 on one process: un-normalised features -> normalise/pack/(gather) -> hybrid loss (kwClip.py:999-1040)."""
+    g = load_golden("hybrid_loss")
+    gen = torch.Generator().manual_seed(4)
+    # the fixture holds NORMALISED features; scale rows arbitrarily to exercise the normalisation and its backward
+    s1 = torch.rand(32, 1, generator=gen) * 3 + 0.5
+    s2 = torch.rand(32, 1, generator=gen) * 3 + 0.5
+    img = (g["image_feat"] * s1).cuda()
+    ca = (g["cascaded_audio_feat"] * s2).cuda().requires_grad_(True)
+    pa = (g["parallel_audio_feat"] * s1).cuda().requires_grad_(True)
+    crit = scp.MaskedContrastiveLoss(temperature=float(g["temperature"]), temperature_trainable=True).cuda()
+    feats = {"id": g["ids"].cuda(), "image_feat": img, "cascaded_audio_feat": ca, "parallel_audio_feat": pa,
+             "cif_quantity_out": g["cif_quantity_out"].cuda(), "cif_target_len": g["cif_target_len"].cuda()}
+    gathered, rows = scp.gather_loss_feats(feats)
+    assert rows == (0, 32)
+    assert rel_err(gathered["cascaded_audio_feat"], g["cascaded_audio_feat"]) < 1e-5
+    assert torch.equal(gathered["id"].cpu(), g["ids"])
+    out = scp.compute_loss(gathered, crit, float(g["cascaded_weight"]), float(g["parallel_weight"]),
+                           quantity_loss_weight=float(g["quantity_loss_weight"]),
+                           quantity_loss_criteria=torch.nn.L1Loss(), local_rows=rows)
+    for key in ("loss", "c_cl_loss", "p_cl_loss", "quantity_loss"):
+        assert rel_err(out[key], g[key]) < TOL, key
+    gca, gpa, gt = torch.autograd.grad(out["loss"], [ca, pa, crit.temperature])
+    assert rel_err(gt, g["grad_temperature"]) < TOL
+    # reference gradient w.r.t. the un-normalised features through the oracle (normalise -> loss)
+    car = (g["cascaded_audio_feat"] * s2).double().requires_grad_(True)
+    par = (g["parallel_audio_feat"] * s1).double().requires_grad_(True)
+    ref = oracle.hybrid_loss({"id": g["ids"], "image_feat": g["image_feat"].double(),
+                              "cascaded_audio_feat": oracle.l2_normalise(car),
+                              "parallel_audio_feat": oracle.l2_normalise(par)},
+                             1.0 / float(g["temperature"]), float(g["cascaded_weight"]), float(g["parallel_weight"]))
+    rca, rpa = torch.autograd.grad(ref["loss"], [car, par])
+    assert norm_err(gca, rca) < TOL and norm_err(gpa, rpa) < TOL
+
+
+def test_install_patches_reference_namespaces(scp):
+    import sys
+    import types
+    pkg = "fake_avssl"
+    mods = {}
+    for name in [pkg, f"{pkg}.module", f"{pkg}.module.losses", f"{pkg}.module.weighted_sum",
+                 f"{pkg}.module.speech_encoder_plus", f"{pkg}.module.speechclip_c_modules",
+                 f"{pkg}.module.speechclip_c_modules.my_vector_quantizer",
+                 f"{pkg}.module.speechclip_c_modules.vector_quantizers", f"{pkg}.model", f"{pkg}.model.kw_branches"]:
+        mods[name] = types.ModuleType(name)
+        sys.modules[name] = mods[name]
+
+    class GeneralBranch:  # noqa: D401
+        pass
+
+    mods[f"{pkg}.model.kw_branches"].GeneralBranch = GeneralBranch
+    try:
+        done = scp.install(pkg, strict=True)
+        assert all(done.values())
+        assert mods[f"{pkg}.module.losses"].MaskedContrastiveLoss is scp.MaskedContrastiveLoss
+        assert getattr(mods[f"{pkg}.module.speechclip_c_modules.vector_quantizers"], "SimpleVectorQuantizer") \
+            is scp.SimpleVectorQuantizer
+        # the patched method runs the fused path on a duck-typed branch (projection = identity)
+        V, D = 512, 64
+        table = torch.randn(V, D).cuda() * 0.02
+        emb = torch.nn.Embedding(V, D).cuda()
+        emb.weight.data.copy_(table)
+        emb.weight.requires_grad_(False)
+        br = GeneralBranch()
+        br.project_feats_to_CLIPspace = lambda x: x
+        br.clip = types.SimpleNamespace(model=types.SimpleNamespace(token_embedding=emb))
+        br.vector_quantizer = scp.SimpleVectorQuantizer("fixed=0.1").cuda()
+        res, kws = br.vq_audio_features(torch.randn(2, 3, D).cuda())
+        assert kws.shape == (2, 3, D) and res["targets"].shape == (2, 3, 1)
+    finally:
+        for name in mods:
+            sys.modules.pop(name, None)

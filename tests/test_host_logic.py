@@ -1,0 +1,121 @@
+"""CPU: host-side logic of the drop-in modules (constructor semantics, state_dict keys, error behaviour)."""
+import math
+
+import pytest
+import torch
+
+import speechclip_plus_b200 as scp
+from speechclip_plus_b200.model import kw_glue
+from speechclip_plus_b200.module.vector_quantizers import _masked_array
+
+
+def test_weighted_sum_layer_contract():
+    layer = scp.WeightedSumLayer(n_weights=13, normalize_features=True)
+    assert layer.n_weights == 13 and layer.normalize_features
+    assert list(layer.state_dict().keys()) == ["weights"]                      # weighted_sum.py:21
+    assert layer.weights.shape == (13,) and layer.weights.dtype == torch.float32
+    assert torch.count_nonzero(layer.weights) == 0
+    with pytest.raises(AssertionError):
+        layer([torch.zeros(1, 2, 4)] * 12)                                       # weighted_sum.py:36
+    with pytest.raises(scp.ScpError):
+        layer([torch.zeros(1, 2, 4)] * 13)                                       # CPU tensors: no fallback
+    with pytest.raises(scp.ScpError):
+        scp.WeightedSumLayer(n_weights=64)
+
+
+def test_vector_quantizer_constructor_semantics():
+    fixed = scp.SimpleVectorQuantizer("fixed=0.1")
+    assert fixed.temp_type == "fixed" and "curr_temp" in dict(fixed.named_buffers())
+    assert list(fixed.state_dict().keys()) == ["curr_temp"]
+    assert fixed.curr_temp.shape == (1,) and math.isclose(fixed.curr_temp.item(), 0.1, rel_tol=1e-6)
+    learn = scp.SimpleVectorQuantizer("learnable=0.07")
+    assert learn.temp_type == "learnable" and isinstance(learn.curr_temp, torch.nn.Parameter)
+    assert list(learn.state_dict().keys()) == ["curr_temp"]
+    sched = scp.SimpleVectorQuantizer("(2.0, 0.5, 0.9)")
+    assert sched.temp_type == "scheduled"
+    sched.set_num_updates(3)                                                     # my_vector_quantizer.py:58-62
+    assert math.isclose(sched.curr_temp.item(), 2.0 * 0.9 ** 3, rel_tol=1e-6)
+    sched.set_num_updates(1000)
+    assert math.isclose(sched.curr_temp.item(), 0.5, rel_tol=1e-6)
+    assert list(sched.state_dict().keys()) == []                                  # a python float in the reference
+    fixed.set_num_updates(10)
+    assert math.isclose(fixed.curr_temp.item(), 0.1, rel_tol=1e-6)
+    with pytest.raises(NotImplementedError):
+        scp.SimpleVectorQuantizer("fixed=0.1", use_gumbel=True)
+    with pytest.raises(scp.ScpError):
+        fixed(torch.zeros(1, 2, 8))                                              # CPU tensor
+    gtp = scp.SimpleVectorQuantizer("fixed=0.1", groundTruthPerplexity=10.0)
+    assert isinstance(gtp.perplexity_criteria, torch.nn.MSELoss)
+
+
+def test_masked_array_validation():
+    arr, n = _masked_array((0, 2, 3), 100)
+    assert n == 3 and list(arr)[:3] == [0, 2, 3]
+    arr, n = _masked_array((), 100)
+    assert n == 0
+    with pytest.raises(IndexError):
+        _masked_array((0, 100), 100)
+    with pytest.raises(scp.ScpError):
+        _masked_array(tuple(range(9)), 100)
+
+
+def test_contrastive_loss_contract():
+    crit = scp.MaskedContrastiveLoss(temperature=0.07, temperature_trainable=True)
+    sd = crit.state_dict()
+    assert set(sd.keys()) == {"temperature", "eye_mat", "neg_eye_mat", "eye_mat_fl"}   # losses.py:161-168
+    assert sd["eye_mat"].shape == (256, 256) and sd["eye_mat"].dtype == torch.bool
+    assert math.isclose(crit.temperature.item(), math.log(1 / 0.07), rel_tol=1e-6)
+    assert math.isclose(crit.current_temperature, 1 / 0.07, rel_tol=1e-5)
+    fixed = scp.MaskedContrastiveLoss(temperature=0.1)
+    assert isinstance(fixed.temperature, float) and math.isclose(fixed.current_temperature, 10.0)
+    assert set(fixed.state_dict().keys()) == {"eye_mat", "neg_eye_mat", "eye_mat_fl"}
+    with pytest.raises(AssertionError):
+        scp.MaskedContrastiveLoss(a2b=False, b2a=False)
+    with pytest.raises(AssertionError):
+        crit(torch.zeros(4, 8), torch.zeros(5, 8))                               # losses.py:199
+    with pytest.raises(scp.ScpError):
+        crit(torch.zeros(4, 64), torch.zeros(4, 64))
+    # a checkpoint written by the reference class loads into the drop-in
+    ref_like = {"temperature": torch.tensor(3.0), "eye_mat": torch.eye(256, dtype=torch.bool),
+                "neg_eye_mat": ~torch.eye(256, dtype=torch.bool), "eye_mat_fl": torch.eye(256)}
+    crit.load_state_dict(ref_like)
+    assert crit.temperature.item() == 3.0
+
+
+def test_pack_layout_roundtrip_on_host():
+    n, D, n_feats, world = 6, 8, 3, 4
+    assert kw_glue.pack_nbytes(n_feats, n, D) == n_feats * n * D * 4 + n * 8
+    gen = torch.Generator().manual_seed(0)
+    feats = [torch.randn(world * n, D, generator=gen) for _ in range(n_feats)]
+    ids = torch.randint(0, 1000, (world * n,), generator=gen)
+    rows = []
+    for r in range(world):
+        r0, r1 = kw_glue.shard_rows(n, r)
+        parts = [f[r0:r1].contiguous().view(torch.uint8).reshape(-1) for f in feats]
+        parts.append(ids[r0:r1].contiguous().view(torch.uint8).reshape(-1))
+        rows.append(torch.cat(parts))
+    gathered = torch.stack(rows)
+    assert gathered.shape[1] == kw_glue.pack_nbytes(n_feats, n, D)
+    out_feats, out_ids = kw_glue.unpack_gathered(gathered, n_feats, n, D)
+    for a, b in zip(out_feats, feats):
+        assert torch.equal(a, b)
+    assert torch.equal(out_ids, ids)
+    assert kw_glue.shard_rows(5, 3) == (15, 20)
+    assert kw_glue.ddp_grad_scale(8) == 8.0
+
+
+def test_compute_loss_key_contract():
+    calls = []
+
+    def fake_criterion(feat_A, feat_B, index, **kw):
+        calls.append((feat_A.shape, feat_B.shape, kw))
+        return feat_A.sum() * 0 + 1.0
+
+    feats = {"id": torch.arange(4), "image_feat": torch.ones(4, 8), "cascaded_audio_feat": torch.ones(4, 8),
+             "parallel_audio_feat": torch.ones(4, 8)}
+    out = scp.compute_loss(feats, fake_criterion, 1.5, 0.5)
+    assert set(out) == {"loss", "c_cl_loss", "p_cl_loss"} and math.isclose(float(out["loss"]), 2.0)
+    out = scp.compute_loss(feats, fake_criterion, 0.0, 1.0, local_rows=(0, 2))
+    assert set(out) == {"loss", "p_cl_loss"} and calls[-1][2] == {"local_rows": (0, 2)}
+    with pytest.raises(AssertionError):
+        scp.compute_loss({"id": torch.arange(4)}, fake_criterion, 1.0, 0.0)        # kwClip.py:1006-1010
