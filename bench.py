@@ -50,53 +50,64 @@ def load_peaks():
 # clocks sampler
 # =====================================================================================================================
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and clock-event (throttle) reasons through NVML from a background thread while the timed
+    regions run (nvidia-smi -lms buffers its pipe output for seconds, too coarse for a sub-second region)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, gpu_index: int):
-        self.gpu_index = gpu_index
+    def __init__(self, cuda_index: int):
+        self.cuda_index = cuda_index
         self.samples = []
-        self.proc = None
+        self.stop_flag = threading.Event()
         self.thread = None
+        self.handle = None
+        self.nv = None
+        self.sm_max = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
+            import pynvml as nv
+            import torch
+            nv.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(self.cuda_index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            try:
+                self.handle = nv.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.handle = nv.nvmlDeviceGetHandleByIndex(self.cuda_index)
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            self.nv = nv
         except Exception:
-            self.proc = None
+            self.nv = None
             return
-        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread = threading.Thread(target=self._poll, daemon=True)
         self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) >= 8:
-                self.samples.append(parts)
+    def _poll(self):
+        nv = self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                util = nv.nvmlDeviceGetUtilizationRates(self.handle).gpu
+                self.samples.append((sm, int(get_reasons(self.handle)), util))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=5)
-            except Exception:
-                self.proc.kill()
-        sm, smax, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        sm = [s[0] for s in self.samples]
+        mask = 0
         for s in self.samples:
-            try:
-                sm.append(float(s[1]))
-                smax = max(smax, float(s[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, s[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=smax or None,
-                    reasons=sorted(reasons), samples=len(sm))
+            mask |= s[1]
+        reasons = sorted(name for bit, name in self.REASONS.items() if mask & bit)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=self.sm_max, reasons=reasons,
+                    samples=len(sm), source="NVML polled every 2 ms during the timed regions")
 
 
 # =====================================================================================================================
@@ -355,21 +366,28 @@ def run_gpu_arm(args):
     launches0 = _lib.num_launches()
     ms = time_region(torch, dist, world, hp.step, args.steps)
     launches = (_lib.num_launches() - launches0)
-    clocks = sampler.stop() if rank == 0 else None
     pairs_per_s = B * world * args.steps / (ms * 1e-3)
 
     # ---- end to end: host buffers, H2D of every input and D2H of the results inside the timed region
-    hp.make_host_buffers()
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        hp.step_e2e()
-    ms_e2e = time_region(torch, dist, world, hp.step_e2e, e2e_steps)
-    e2e = dict(value=B * world * e2e_steps / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=int(hp.h2d_bytes),
-               d2h_bytes_per_step=int(hp.d2h_bytes), steps=e2e_steps, ms_per_step=ms_e2e / e2e_steps)
+    e2e = None
+    if not args.no_e2e:
+        hp.make_host_buffers()
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            hp.step_e2e()
+        ms_e2e = time_region(torch, dist, world, hp.step_e2e, e2e_steps)
+        e2e = dict(value=B * world * e2e_steps / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=int(hp.h2d_bytes),
+                   d2h_bytes_per_step=int(hp.d2h_bytes), steps=e2e_steps, ms_per_step=ms_e2e / e2e_steps)
 
     line = None
-    if rank == 0:
+    if rank == 0 and args.no_breakdown:
+        clocks = sampler.stop()
+        print(json.dumps(dict(metric=METRIC, value=pairs_per_s, unit=UNIT, n_gpus=world, steps=args.steps,
+                              ms_per_step=ms / args.steps, gpu_launches=int(launches), clocks=clocks,
+                              note="profiling run: no roofline / e2e legs")), flush=True)
+    elif rank == 0:
         kb = kernel_breakdown(hp)
+        clocks = sampler.stop()
         dom = max(kb, key=lambda k: kb[k]["seconds"])
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -410,6 +428,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
+    ap.add_argument("--no-breakdown", action="store_true", help="skip the per-kernel timing leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

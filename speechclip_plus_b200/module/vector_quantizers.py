@@ -120,7 +120,10 @@ class _FusedVQFn(torch.autograd.Function):
         out = kw_out.view(B, K, D)
         if avg_probs is None:
             avg_probs = torch.empty(0, device=dev)
-        ctx.mark_non_differentiable(idx, metrics, row_stats, code_hist, avg_probs)
+        if training:
+            ctx.mark_non_differentiable(idx, metrics, row_stats, code_hist, avg_probs)
+        else:  # eval: subword_prob is the one-hot (my_vector_quantizer.py:138-139): no gradient path at all
+            ctx.mark_non_differentiable(out, idx, metrics, row_stats, code_hist, avg_probs)
         return out, idx, metrics, row_stats, code_hist, avg_probs
 
     @staticmethod
