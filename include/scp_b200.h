@@ -149,6 +149,7 @@ size_t scp_nce_workspace_bytes(int64_t N, int64_t D);
  *   loss    (1,) f32, lse_row (N,) f32 = log sum_j mask*exp(S_ij), lse_col (N,) f32 = log sum_i mask*exp(S_ij) */
 int scp_nce_fwd(const float* A, const float* Bm, const int64_t* ids, int64_t N, int64_t D,
                 const float* log_scale, float fixed_scale, float margin, int dcl, int a2b, int b2a,
+                int prepare_bwd /* also stage the transposed operands of the backward GEMM in `workspace` */,
                 float* loss, float* lse_row, float* lse_col,
                 void* workspace, size_t workspace_bytes, scp_stream_t stream);
 
@@ -158,7 +159,9 @@ int scp_nce_fwd(const float* A, const float* Bm, const int64_t* ids, int64_t N, 
 int scp_nce_bwd(const float* A, const float* Bm, const int64_t* ids, int64_t N, int64_t D,
                 const float* log_scale, float fixed_scale, float margin, int dcl, int a2b, int b2a,
                 const float* lse_row, const float* lse_col, const float* g_loss,
-                int64_t row_begin, int64_t row_end, float* dA, float* dB, float* d_log_scale,
+                int64_t row_begin, int64_t row_end,
+                int fwd_state_valid /* `workspace` is the untouched workspace of scp_nce_fwd(prepare_bwd=1) on the same inputs */,
+                float* dA, float* dB, float* d_log_scale,
                 void* workspace, size_t workspace_bytes, scp_stream_t stream);
 
 #ifdef __cplusplus

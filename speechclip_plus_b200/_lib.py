@@ -59,9 +59,9 @@ SIGNATURES = {
     "scp_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "scp_nce_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "scp_nce_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_float, c_float, c_int, c_int,
-                            c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                            c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "scp_nce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_float, c_float, c_int, c_int,
-                            c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                            c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                             c_void_p, c_size_t, c_void_p]),
 }
 

@@ -33,18 +33,16 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
 // warp <-> sample row.  Writes the stacked split operands and the positive-pair dot product.
 //   x3 (2*Np, 3D): rows [0,Np) = [Ahi Ahi Alo], rows [Np,2Np) = [Bhi Bhi Blo]
 //   y3 (2*Np, 3D): rows [0,Np) = [Bhi Blo Bhi], rows [Np,2Np) = [Ahi Alo Ahi]
-//   t3 (2*D, 3*Np) (optional, backward): rows [0,D) = [Bhi^T Blo^T Bhi^T], rows [D,2D) = [Ahi^T Alo^T Ahi^T]
 __global__ void nce_prep_kernel(const float* __restrict__ A, const float* __restrict__ B, int64_t N, int64_t Np, int D,
-                                __half* __restrict__ x3, __half* __restrict__ y3, __half* __restrict__ t3,
-                                float* __restrict__ pos) {
+                                __half* __restrict__ x3, __half* __restrict__ y3, float* __restrict__ pos) {
   const int lane = threadIdx.x & 31;
   const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= Np) return;
   const int64_t K3 = 3 * (int64_t)D;
-  __half* xa = x3 ? x3 + i * K3 : nullptr;
-  __half* xb = x3 ? x3 + (Np + i) * K3 : nullptr;
-  __half* ya = y3 ? y3 + i * K3 : nullptr;
-  __half* yb = y3 ? y3 + (Np + i) * K3 : nullptr;
+  __half* xa = x3 + i * K3;
+  __half* xb = x3 + (Np + i) * K3;
+  __half* ya = y3 + i * K3;
+  __half* yb = y3 + (Np + i) * K3;
   float dot = 0.f;
   for (int d = lane; d < D; d += 32) {
     const float a = i < N ? A[i * D + d] : 0.f;
@@ -53,43 +51,43 @@ __global__ void nce_prep_kernel(const float* __restrict__ A, const float* __rest
     __half ah, al, bh, bl;
     split_f16(a * kFeatScale, ah, al);
     split_f16(b * kFeatScale, bh, bl);
-    if (x3) {
-      xa[d] = ah; xa[D + d] = ah; xa[2 * D + d] = al;
-      xb[d] = bh; xb[D + d] = bh; xb[2 * D + d] = bl;
-    }
-    if (y3) {
-      ya[d] = bh; ya[D + d] = bl; ya[2 * D + d] = bh;
-      yb[d] = ah; yb[D + d] = al; yb[2 * D + d] = ah;
-    }
-    if (t3) {
-      const int64_t ld = 3 * Np;
-      __half* tb = t3 + (int64_t)d * ld;
-      __half* ta = t3 + ((int64_t)D + d) * ld;
-      tb[i] = bh; tb[Np + i] = bl; tb[2 * Np + i] = bh;
-      ta[i] = ah; ta[Np + i] = al; ta[2 * Np + i] = ah;
-    }
-  }
-  dot = warp_sum(dot);
-  if (pos && lane == 0 && i < N) pos[i] = dot;
-}
-
-// split operands of the LOCAL rows only (backward X operand): x3l (2*Lp, 3D)
-__global__ void nce_prep_local_kernel(const float* __restrict__ A, const float* __restrict__ B, int64_t row_begin,
-                                      int64_t n_local, int64_t Lp, int D, __half* __restrict__ x3l) {
-  const int lane = threadIdx.x & 31;
-  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= Lp) return;
-  const int64_t K3 = 3 * (int64_t)D;
-  __half* xa = x3l + i * K3;
-  __half* xb = x3l + (Lp + i) * K3;
-  for (int d = lane; d < D; d += 32) {
-    const float a = i < n_local ? A[(row_begin + i) * D + d] : 0.f;
-    const float b = i < n_local ? B[(row_begin + i) * D + d] : 0.f;
-    __half ah, al, bh, bl;
-    split_f16(a * kFeatScale, ah, al);
-    split_f16(b * kFeatScale, bh, bl);
     xa[d] = ah; xa[D + d] = ah; xa[2 * D + d] = al;
     xb[d] = bh; xb[D + d] = bh; xb[2 * D + d] = bl;
+    ya[d] = bh; ya[D + d] = bl; ya[2 * D + d] = bh;
+    yb[d] = ah; yb[D + d] = al; yb[2 * D + d] = ah;
+  }
+  dot = warp_sum(dot);
+  if (lane == 0 && i < N) pos[i] = dot;
+}
+
+// transposed split operands for the backward GEMM (K = sample index):
+//   t3 (2*D, 3*Np): rows [0,D) = [Bhi^T Blo^T Bhi^T], rows [D,2D) = [Ahi^T Alo^T Ahi^T]
+// 32 x 32 tiles through shared memory so that both the reads (along d) and the writes (along i) are coalesced.
+__global__ void nce_prep_t_kernel(const float* __restrict__ A, const float* __restrict__ B, int64_t N, int64_t Np, int D,
+                                  __half* __restrict__ t3) {
+  __shared__ float ta[32][33], tb[32][33];
+  const int64_t i0 = (int64_t)blockIdx.x * 32;
+  const int d0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t i = i0 + r;
+    const int d = d0 + threadIdx.x;
+    ta[r][threadIdx.x] = (i < N && d < D) ? A[i * D + d] : 0.f;
+    tb[r][threadIdx.x] = (i < N && d < D) ? B[i * D + d] : 0.f;
+  }
+  __syncthreads();
+  const int64_t ld = 3 * Np;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int d = d0 + r;
+    const int64_t i = i0 + threadIdx.x;
+    if (d < D && i < Np) {
+      __half ah, al, bh, bl;
+      split_f16(ta[threadIdx.x][r] * kFeatScale, ah, al);
+      split_f16(tb[threadIdx.x][r] * kFeatScale, bh, bl);
+      __half* rb = t3 + (int64_t)d * ld;
+      __half* ra = t3 + ((int64_t)D + d) * ld;
+      rb[i] = bh; rb[Np + i] = bl; rb[2 * Np + i] = bh;
+      ra[i] = ah; ra[Np + i] = al; ra[2 * Np + i] = ah;
+    }
   }
 }
 
@@ -204,19 +202,19 @@ struct NceBwdEpi {
     const float* lse_row;  // (N,)
     const float* lse_col;  // (N,)
     __half* g3;            // (2*Lp, 3*Np): [hi | hi | lo]
-    float* dscale_part;    // (Lp,) sum_j Ghat_ij * raw_ij   (direction 0 rows only)
-    int Np, Lp, row_begin, n_local;
+    float* dscale_part;    // (Lp, n_groups) sum_j Ghat_ij * raw_ij   (direction 0 rows only)
+    int Np, Lp, row_begin, n_local, n_groups;
     int a2b, b2a;
   };
   static constexpr int kSmemBytes = 0;
   const Params& p;
-  int r, own, dir;
+  int r, own, dir, group;
   bool own_valid;
   int64_t own_id;
   float k, own_lse_l2, own_a, col_a, dsum;
   const float* col_lse;
   __device__ __forceinline__ NceBwdEpi(const Params& p_, const WorkInfo& w, int row_in_tile, uint8_t*)
-      : p(p_), r(w.m_tile * tc::kTileM + row_in_tile) {
+      : p(p_), r(w.m_tile * tc::kTileM + row_in_tile), group(w.n_group) {
     dir = r >= p.Lp;
     const int loc = r - dir * p.Lp;
     own_valid = loc < p.n_local;
@@ -275,7 +273,7 @@ struct NceBwdEpi {
     }
   }
   __device__ __forceinline__ void finish() {
-    if (!dir) p.dscale_part[r] = own_valid ? dsum : 0.f;
+    if (!dir) p.dscale_part[(int64_t)r * p.n_groups + group] = own_valid ? dsum : 0.f;
   }
 };
 
@@ -305,7 +303,7 @@ struct NceStoreEpi {
 // dA / dB = coef * sum_ks out ; d_log_scale = g * sum_i dscale_part / (N ndir)
 __global__ void nce_bwd_finalize_kernel(const float* __restrict__ out, int k_splits, int64_t Lp, int D, int64_t n_local,
                                         NceCommon c, int ndir, const float* __restrict__ g_loss,
-                                        const float* __restrict__ dscale_part, float* __restrict__ dA,
+                                        const float* __restrict__ dscale_part, int n_groups, float* __restrict__ dA,
                                         float* __restrict__ dB, float* __restrict__ d_log_scale) {
   const float g = *g_loss / ((float)c.N * (float)ndir);
   const float coef = g * c.scale() / (kGScale * kFeatScale);
@@ -323,7 +321,7 @@ __global__ void nce_bwd_finalize_kernel(const float* __restrict__ out, int k_spl
   }
   if (d_log_scale && blockIdx.x == 0 && threadIdx.x < 32) {
     float s = 0.f;
-    for (int64_t i = threadIdx.x; i < n_local; i += 32) s += dscale_part[i];
+    for (int64_t i = threadIdx.x; i < n_local * n_groups; i += 32) s += dscale_part[i];
     s = warp_sum(s);
     if (threadIdx.x == 0) *d_log_scale = s * g;
   }
@@ -378,7 +376,6 @@ struct NceWs {
   __half* x3;
   __half* y3;
   __half* t3;
-  __half* x3l;
   __half* g3;
   float* pos;
   float* partials;
@@ -407,11 +404,10 @@ static NceWs nce_ws(void* base, int64_t N, int64_t D, int64_t n_local) {
   w.x3 = static_cast<__half*>(take((size_t)2 * Np * 3 * D * 2));
   w.y3 = static_cast<__half*>(take((size_t)2 * Np * 3 * D * 2));
   w.t3 = static_cast<__half*>(take((size_t)2 * D * 3 * Np * 2));
-  w.x3l = static_cast<__half*>(take((size_t)2 * Lp * 3 * D * 2));
   w.g3 = static_cast<__half*>(take((size_t)2 * Lp * 3 * Np * 2));
   w.pos = static_cast<float*>(take((size_t)Np * 4));
   w.partials = static_cast<float*>(take((size_t)2 * Np * w.n_groups * 8));
-  w.dscale_part = static_cast<float*>(take((size_t)Lp * 4));
+  w.dscale_part = static_cast<float*>(take((size_t)Lp * kNumSMs * 4));
   // split-K partials: k_splits * out_items <= 148 bounds the size independently of n_local
   w.out = static_cast<float*>(take(std::max((size_t)2 * Np * 2 * D * 4, (size_t)kNumSMs * tc::kTileM * 256 * 2 * 4)));
   w.total = off;
@@ -434,6 +430,7 @@ static Sched nce_sweep_sched(int64_t rows_half_p, int64_t Np, int64_t D, int n_g
   sc.n_groups = n_groups;
   sc.k_chunks = (int)(3 * D / tc::kChunkK);
   sc.k_splits = 1;
+  sc.x_upper_row_off = 0;
   return sc;
 }
 
@@ -445,8 +442,8 @@ extern "C" size_t scp_nce_workspace_bytes(int64_t N, int64_t D) { return nce_ws(
 
 extern "C" int scp_nce_fwd(const float* A, const float* Bm, const int64_t* ids, int64_t N, int64_t D,
                            const float* log_scale, float fixed_scale, float margin, int dcl, int a2b, int b2a,
-                           float* loss, float* lse_row, float* lse_col, void* workspace, size_t workspace_bytes,
-                           scp_stream_t stream) {
+                           int prepare_bwd, float* loss, float* lse_row, float* lse_col, void* workspace,
+                           size_t workspace_bytes, scp_stream_t stream) {
   int rc = check_device_arch();
   if (rc) return rc;
   rc = check_nce_shape(N, D);
@@ -459,8 +456,13 @@ extern "C" int scp_nce_fwd(const float* A, const float* Bm, const int64_t* ids, 
   const int64_t Np = round_up(N, tc::kTileM);
   NceCommon c{ids, log_scale, fixed_scale, margin, dcl, (int)N};
 
-  nce_prep_kernel<<<(unsigned)ceil_div(Np, 8), 256, 0, s>>>(A, Bm, N, Np, (int)D, ws.x3, ws.y3, nullptr, ws.pos);
+  nce_prep_kernel<<<(unsigned)ceil_div(Np, 8), 256, 0, s>>>(A, Bm, N, Np, (int)D, ws.x3, ws.y3, ws.pos);
   SCP_CUDA_LAUNCH_CHECK("nce_prep");
+  if (prepare_bwd) {
+    dim3 tb(32, 8), tg((unsigned)(Np / 32), (unsigned)ceil_div(D, 32));
+    nce_prep_t_kernel<<<tg, tb, 0, s>>>(A, Bm, N, Np, (int)D, ws.t3);
+    SCP_CUDA_LAUNCH_CHECK("nce_prep_t");
+  }
   GemmMaps maps{};
   if ((rc = tc::make_tmap_f16(&maps.x[0], ws.x3, 2 * Np, 3 * D, 3 * D, tc::kTileM))) return rc;
   maps.x[1] = maps.x[0];
@@ -482,8 +484,8 @@ static int launch_nce_out(const GemmMaps& maps, const Sched& sc, const NceStoreE
 extern "C" int scp_nce_bwd(const float* A, const float* Bm, const int64_t* ids, int64_t N, int64_t D,
                            const float* log_scale, float fixed_scale, float margin, int dcl, int a2b, int b2a,
                            const float* lse_row, const float* lse_col, const float* g_loss, int64_t row_begin,
-                           int64_t row_end, float* dA, float* dB, float* d_log_scale, void* workspace,
-                           size_t workspace_bytes, scp_stream_t stream) {
+                           int64_t row_end, int fwd_state_valid, float* dA, float* dB, float* d_log_scale,
+                           void* workspace, size_t workspace_bytes, scp_stream_t stream) {
   int rc = check_device_arch();
   if (rc) return rc;
   rc = check_nce_shape(N, D);
@@ -497,20 +499,25 @@ extern "C" int scp_nce_bwd(const float* A, const float* Bm, const int64_t* ids, 
   const int64_t Np = round_up(N, tc::kTileM), Lp = round_up(n_local, tc::kTileM);
   NceCommon c{ids, log_scale, fixed_scale, margin, dcl, (int)N};
 
-  nce_prep_kernel<<<(unsigned)ceil_div(Np, 8), 256, 0, s>>>(A, Bm, N, Np, (int)D, nullptr, ws.y3, ws.t3, nullptr);
-  SCP_CUDA_LAUNCH_CHECK("nce_prep");
-  nce_prep_local_kernel<<<(unsigned)ceil_div(Lp, 8), 256, 0, s>>>(A, Bm, row_begin, n_local, Lp, (int)D, ws.x3l);
-  SCP_CUDA_LAUNCH_CHECK("nce_prep_local");
-  // ---- sweep: G~
+  if (!fwd_state_valid) {  // the split operands of the forward call are not in `workspace`: rebuild them
+    nce_prep_kernel<<<(unsigned)ceil_div(Np, 8), 256, 0, s>>>(A, Bm, N, Np, (int)D, ws.x3, ws.y3, ws.pos);
+    SCP_CUDA_LAUNCH_CHECK("nce_prep");
+    dim3 tb(32, 8), tg((unsigned)(Np / 32), (unsigned)ceil_div(D, 32));
+    nce_prep_t_kernel<<<tg, tb, 0, s>>>(A, Bm, N, Np, (int)D, ws.t3);
+    SCP_CUDA_LAUNCH_CHECK("nce_prep_t");
+  }
+  const int sweep_m_tiles = (int)(2 * Lp / tc::kTileM);
+  const int sweep_groups = std::max(1, std::min((int)(Np / kNceBN), kNumSMs / sweep_m_tiles));
+  // ---- sweep: G~ for the local rows.  X = the local rows of the stacked split operands, addressed in place:
+  //      lower-half tiles start at row_begin (tensor-map base), upper-half tiles Np - Lp rows further.
   {
     GemmMaps maps{};
-    if ((rc = tc::make_tmap_f16(&maps.x[0], ws.x3l, 2 * Lp, 3 * D, 3 * D, tc::kTileM))) return rc;
+    if ((rc = tc::make_tmap_f16(&maps.x[0], ws.x3 + row_begin * 3 * D, 2 * Np - row_begin, 3 * D, 3 * D, tc::kTileM)))
+      return rc;
     maps.x[1] = maps.x[0];
     if ((rc = tc::make_tmap_f16(&maps.y, ws.y3, 2 * Np, 3 * D, 3 * D, kNceBN))) return rc;
-    const int m_tiles = (int)(2 * Lp / tc::kTileM);
-    const int n_groups = 1;  // every CTA walks all column tiles of its rows (G rows are written, not reduced)
-    Sched sc = nce_sweep_sched(Lp, Np, D, n_groups);
-    (void)m_tiles;
+    Sched sc = nce_sweep_sched(Lp, Np, D, sweep_groups);
+    sc.x_upper_row_off = (int)(Np - Lp);
     NceBwdEpi::Params ep{};
     ep.c = c;
     ep.lse_row = lse_row;
@@ -518,6 +525,7 @@ extern "C" int scp_nce_bwd(const float* A, const float* Bm, const int64_t* ids, 
     ep.g3 = ws.g3;
     ep.dscale_part = ws.dscale_part;
     ep.Np = (int)Np; ep.Lp = (int)Lp; ep.row_begin = (int)row_begin; ep.n_local = (int)n_local;
+    ep.n_groups = sweep_groups;
     ep.a2b = a2b; ep.b2a = b2a;
     if ((rc = tc::launch_stream_gemm<kNceBN, 1, 6, NceBwdEpi>(maps, sc, ep, s, "nce_bwd_sweep"))) return rc;
   }
@@ -539,6 +547,7 @@ extern "C" int scp_nce_bwd(const float* A, const float* Bm, const int64_t* ids, 
     sc.n_groups = sc.n_tiles;
     sc.k_chunks = k_chunks;
     sc.k_splits = k_splits;
+    sc.x_upper_row_off = 0;
     NceStoreEpi<1>::Params ep{ws.out, 2 * Lp, (int)(2 * D)};
     if (bn == 256) rc = launch_nce_out<256>(maps, sc, ep, s);
     else if (bn == 128) rc = launch_nce_out<128>(maps, sc, ep, s);
@@ -547,7 +556,7 @@ extern "C" int scp_nce_bwd(const float* A, const float* Bm, const int64_t* ids, 
   }
   const int64_t total = n_local * D;
   nce_bwd_finalize_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, 256), 1024), 256, 0, s>>>(
-      ws.out, k_splits, Lp, (int)D, n_local, c, a2b + b2a, g_loss, ws.dscale_part, dA, dB, d_log_scale);
+      ws.out, k_splits, Lp, (int)D, n_local, c, a2b + b2a, g_loss, ws.dscale_part, sweep_groups, dA, dB, d_log_scale);
   SCP_CUDA_LAUNCH_CHECK("nce_bwd_finalize");
   return SCP_OK;
 }

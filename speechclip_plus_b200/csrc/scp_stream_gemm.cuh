@@ -29,13 +29,15 @@ struct Sched {
   int k_chunks;  // total 64-element K chunks
   int k_splits;  // the k_chunks are partitioned into k_splits contiguous ranges
   // two-direction launches (InfoNCE): CTAs whose m_tile >= m_half walk Y tiles shifted by n_upper_off
-  int m_half;       // == m_tiles when unused
-  int n_upper_off;  // == 0 when unused
+  int m_half;           // == m_tiles when unused
+  int n_upper_off;      // == 0 when unused
+  int x_upper_row_off;  // extra X row offset of the upper-half tiles (== 0 when unused)
   __host__ __device__ int grid() const { return m_tiles * n_groups * k_splits; }
 };
 
 struct WorkInfo {
   int m_tile, n_group, k_split;
+  int x_row;     // first X row of this CTA's tile (TMA coordinate)
   int nt0, nt1;  // N-tile range
   int kc0, kc1;  // K-chunk range
 };
@@ -49,9 +51,11 @@ __device__ __forceinline__ WorkInfo decode_work(const Sched& s) {
   w.k_split = b / s.n_groups;
   w.nt0 = (int)((long long)s.n_tiles * w.n_group / s.n_groups);
   w.nt1 = (int)((long long)s.n_tiles * (w.n_group + 1) / s.n_groups);
+  w.x_row = w.m_tile * kTileM;
   if (w.m_tile >= s.m_half) {
     w.nt0 += s.n_upper_off;
     w.nt1 += s.n_upper_off;
+    w.x_row += s.x_upper_row_off;
   }
   w.kc0 = (int)((long long)s.k_chunks * w.k_split / s.k_splits);
   w.kc1 = (int)((long long)s.k_chunks * (w.k_split + 1) / s.k_splits);
@@ -136,7 +140,7 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
 #pragma unroll
           for (int x = 0; x < NX; ++x)
-            tma_load_2d(st + x * kXTileBytes, &maps.x[x], kc * kChunkK, work.m_tile * kTileM, &full_bar[stage]);
+            tma_load_2d(st + x * kXTileBytes, &maps.x[x], kc * kChunkK, work.x_row, &full_bar[stage]);
           tma_load_2d(st + NX * kXTileBytes, &maps.y, kc * kChunkK, nt * BN, &full_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }

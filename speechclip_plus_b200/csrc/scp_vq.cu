@@ -209,58 +209,106 @@ __device__ __forceinline__ Best better(const Best& a, const Best& b) {
   return a;
 }
 
+constexpr int kSelMaxCand = 64;  // candidate chunks buffered per pass (more candidates -> more passes)
+
+// Exact re-scoring of one 32-column chunk by a 128-thread block: warp w scores columns [8w, 8w+8); the 32 lanes of a
+// warp split the D axis (coalesced 16-byte loads of the fp32 table row, all 8 rows' loads in flight together), fp64
+// FMAs, butterfly reduction.  kreg holds this lane's slice of the keyword row in fp64.
+template <int NV>  // float4 vectors per lane: D <= 128*NV
+__device__ __forceinline__ Best rescore_chunk(const float* __restrict__ table, int V, int D, int chunk,
+                                              const double (&kreg)[NV][4], const MaskedCols& mc, int warp, int lane) {
+  Best best{0.0, -1};
+  const int nvec = D >> 2;
+  constexpr int CB = NV <= 4 ? 8 : 4;  // columns whose loads are in flight together (register budget)
+#pragma unroll 1
+  for (int cb = 0; cb < 8; cb += CB) {
+    float4 x[CB][NV];
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+      const int v = chunk * 32 + warp * 8 + cb + c;
+      const float4* e = reinterpret_cast<const float4*>(table + (int64_t)min(v, V - 1) * D);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int q = lane + 32 * j;
+        x[c][j] = q < nvec ? __ldg(e + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+      const int v = chunk * 32 + warp * 8 + cb + c;
+      double dot = 0.0, nn = 0.0;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const double x0 = x[c][j].x, x1 = x[c][j].y, x2 = x[c][j].z, x3 = x[c][j].w;
+        dot = fma(kreg[j][0], x0, dot); nn = fma(x0, x0, nn);
+        dot = fma(kreg[j][1], x1, dot); nn = fma(x1, x1, nn);
+        dot = fma(kreg[j][2], x2, dot); nn = fma(x2, x2, nn);
+        dot = fma(kreg[j][3], x3, dot); nn = fma(x3, x3, nn);
+      }
+      dot = warp_sum(dot);
+      nn = warp_sum(nn);
+      if (v < V && !is_masked(mc, v)) {
+        const double score = dot / fmax(sqrt(nn), 1e-8);  // the common factor 1/||kw|| does not change the order
+        best = better(best, Best{score, v});
+      }
+    }
+  }
+  return best;  // identical in every lane of the warp
+}
+
+template <int NV>
 __global__ void __launch_bounds__(128)
 vq_select_kernel(const float* __restrict__ kw, const float* __restrict__ table, int64_t M, int V, int D,
                  const float* __restrict__ chunk_max, int n_chunks, const float* __restrict__ partials, int n_groups,
                  const float* __restrict__ tau_ptr, MaskedCols mc, int64_t* __restrict__ idx_out,
                  float* __restrict__ keywords, float* __restrict__ row_stats, float* __restrict__ code_hist) {
-  extern __shared__ double s_kw[];  // D doubles
   __shared__ float s_red[4];
   __shared__ Best s_best[4];
+  __shared__ int s_cand[kSelMaxCand];
+  __shared__ int s_ncand;
   const int64_t m = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int d = tid; d < D; d += 128) s_kw[d] = (double)kw[m * D + d];
-  // approximate row maximum
+  // this lane's slice of the keyword row, in fp64
+  double kreg[NV][4];
+  const int nvec = D >> 2;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int q = lane + 32 * j;
+    const float4 k4 = q < nvec ? __ldg(reinterpret_cast<const float4*>(kw + m * D) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    kreg[j][0] = k4.x; kreg[j][1] = k4.y; kreg[j][2] = k4.z; kreg[j][3] = k4.w;
+  }
+  // approximate (fp16-product) row maximum
   const float* cm = chunk_max + m * n_chunks;
   float mx = kNegBig;
-  for (int c = tid; c < n_chunks; c += 128) mx = fmaxf(mx, cm[c]);
+  for (int c = tid; c < n_chunks; c += 128) mx = fmaxf(mx, __ldg(cm + c));
   mx = warp_max(mx);
   if (lane == 0) s_red[warp] = mx;
+  if (tid == 0) s_ncand = 0;
   __syncthreads();
   mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
   const float thr = mx - kRescueMargin;
-  // exact re-scoring of every candidate chunk: lane <-> column
+  // every chunk whose maximum could hide the true arg-max is re-scored exactly (usually one or two per row)
   Best best{0.0, -1};
-  for (int c0 = warp * 32; c0 < n_chunks; c0 += 128) {
-    const int c = c0 + lane;
-    const bool cand = c < n_chunks && cm[c] >= thr;
-    unsigned ballot = __ballot_sync(0xffffffffu, cand);
-    while (ballot) {
-      const int b = __ffs(ballot) - 1;
-      ballot &= ballot - 1;
-      const int v = (c0 + b) * 32 + lane;
-      if (v < V && !is_masked(mc, v)) {
-        const float4* e = reinterpret_cast<const float4*>(table + (int64_t)v * D);
-        double dot = 0.0, nn = 0.0;
-        for (int d4 = 0; d4 < D / 4; ++d4) {
-          const float4 x = __ldg(e + d4);
-          const double x0 = x.x, x1 = x.y, x2 = x.z, x3 = x.w;
-          dot = fma(s_kw[4 * d4 + 0], x0, dot); nn = fma(x0, x0, nn);
-          dot = fma(s_kw[4 * d4 + 1], x1, dot); nn = fma(x1, x1, nn);
-          dot = fma(s_kw[4 * d4 + 2], x2, dot); nn = fma(x2, x2, nn);
-          dot = fma(s_kw[4 * d4 + 3], x3, dot); nn = fma(x3, x3, nn);
-        }
-        const double score = dot / fmax(sqrt(nn), 1e-8);  // common factor 1/||kw|| does not change the order
-        best = better(best, Best{score, v});
+  for (int base = 0; base < n_chunks; base += 128 * 8) {  // bounded passes keep the candidate buffer small
+    const int hi = min(n_chunks, base + 128 * 8);
+    for (int c0 = base; c0 < hi; c0 += 128) {
+      const int c = c0 + tid;
+      if (c < hi && __ldg(cm + c) >= thr) {
+        const int slot = atomicAdd(&s_ncand, 1);
+        if (slot < kSelMaxCand) s_cand[slot] = c;
       }
     }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    Best other;
-    other.val = __shfl_xor_sync(0xffffffffu, best.val, o);
-    other.idx = __shfl_xor_sync(0xffffffffu, best.idx, o);
-    best = better(best, other);
+    __syncthreads();
+    int ncand = s_ncand;
+    if (ncand > kSelMaxCand) {
+      // degenerate row (e.g. a zero keyword: every cosine ties): fall back to scoring every chunk of this pass
+      for (int c = base; c < hi; ++c) best = better(best, rescore_chunk<NV>(table, V, D, c, kreg, mc, warp, lane));
+    } else {
+      for (int i = 0; i < ncand; ++i) best = better(best, rescore_chunk<NV>(table, V, D, s_cand[i], kreg, mc, warp, lane));
+    }
+    __syncthreads();
+    if (tid == 0) s_ncand = 0;
+    __syncthreads();
   }
   if (lane == 0) s_best[warp] = best;
   __syncthreads();
@@ -346,28 +394,16 @@ struct Sweep2Epi {
 // =====================================================================================================================
 // metrics: code_perplexity, prob_perplexity, diversity_loss, ent_per_t      (one block)
 // =====================================================================================================================
-__device__ __forceinline__ float block_sum_1024(float v, float* s_red) {
-  v = warp_sum(v);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __syncthreads();
-  if (lane == 0) s_red[warp] = v;
-  __syncthreads();
-  float t = (int)threadIdx.x < (int)(blockDim.x >> 5) ? s_red[threadIdx.x] : 0.f;
-  if (warp == 0) {
-    t = warp_sum(t);
-    if (lane == 0) s_red[0] = t;
-  }
-  __syncthreads();
-  return s_red[0];
-}
+constexpr int kMetricBlocks = 64;
 
-__global__ void __launch_bounds__(1024)
-vq_metrics_kernel(const float* __restrict__ code_hist, const float* __restrict__ avg_probs,
-                  const float* __restrict__ row_stats, int64_t M, int K, int V, float* __restrict__ metrics) {
-  __shared__ float s_red[32];
+// stage 1: per-block partial sums of h log(h + 1e-7) over the code histogram and the average softmax
+__global__ void __launch_bounds__(256)
+vq_metrics_partial_kernel(const float* __restrict__ code_hist, const float* __restrict__ avg_probs, int64_t M, int V,
+                          float* __restrict__ partial /* (kMetricBlocks, 2) */) {
+  __shared__ float s_red[2][8];
   const float inv_m = 1.0f / (float)M;
   float hc = 0.f, hp = 0.f;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+  for (int v = blockIdx.x * 256 + threadIdx.x; v < V; v += kMetricBlocks * 256) {
     const float h = code_hist[v] * inv_m;  // my_vector_quantizer.py:94-99
     hc += h * logf(h + 1e-7f);
     if (avg_probs) {
@@ -375,13 +411,33 @@ vq_metrics_kernel(const float* __restrict__ code_hist, const float* __restrict__
       hp += a * logf(a + 1e-7f);
     }
   }
-  hc = block_sum_1024(hc, s_red);
-  hp = block_sum_1024(hp, s_red);
-  if (threadIdx.x == 0) {
-    metrics[0] = expf(-hc);
-    const float pp = avg_probs ? expf(-hp) : nanf("");
-    metrics[1] = pp;
-    metrics[2] = ((float)V - pp) / (float)V;  // diversity_loss, :155-158
+  hc = warp_sum(hc);
+  hp = warp_sum(hp);
+  if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = hc; s_red[1][threadIdx.x >> 5] = hp; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += s_red[threadIdx.x][i];
+    partial[blockIdx.x * 2 + threadIdx.x] = t;
+  }
+}
+
+// stage 2 (one block): fixed-order sum of the partials, perplexities, diversity loss, ent_per_t
+__global__ void __launch_bounds__(256)
+vq_metrics_kernel(const float* __restrict__ partial, int has_avg, const float* __restrict__ row_stats, int64_t M,
+                  int K, int V, float* __restrict__ metrics) {
+  if (threadIdx.x < 32) {
+    float hc = 0.f, hp = 0.f;
+    for (int i = threadIdx.x; i < kMetricBlocks; i += 32) { hc += partial[2 * i]; hp += partial[2 * i + 1]; }
+    hc = warp_sum(hc);
+    hp = warp_sum(hp);
+    if (threadIdx.x == 0) {
+      metrics[0] = expf(-hc);
+      const float pp = has_avg ? expf(-hp) : nanf("");
+      metrics[1] = pp;
+      metrics[2] = ((float)V - pp) / (float)V;  // diversity_loss, :155-158
+    }
   }
   // ent_per_t[i] = mean_b entropy[b*K + i]     (:104-116)
   const int64_t Bsz = M / K;
@@ -551,26 +607,30 @@ __global__ void vq_bwd_finalize_kernel(const float* __restrict__ uw /* (k_splits
   const float s_adj = sp > 0.f ? sq / sp : 0.f;
   const float scale = g_aux[m * 2] * table_mean[D] / (kPScale * tau);
   const float inv_norm = row_stats[m * 4 + 3];
+  float gk[32];  // D <= 1024 (checked on the host): this lane's slice of g_khat stays in registers
   float proj = 0.f;
-  for (int d = lane; d < D; d += 32) {
-    float u = 0.f, w = 0.f;
-    for (int ks = 0; ks < k_splits; ++ks) {
-      u += uw[(((int64_t)ks * 2 + 0) * Mp + m) * D + d];
-      w += uw[(((int64_t)ks * 2 + 1) * Mp + m) * D + d];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int d = lane + 32 * j;
+    gk[j] = 0.f;
+    if (d < D) {
+      float u = 0.f, w = 0.f;
+      for (int ks = 0; ks < k_splits; ++ks) {
+        u += uw[(((int64_t)ks * 2 + 0) * Mp + m) * D + d];
+        w += uw[(((int64_t)ks * 2 + 1) * Mp + m) * D + d];
+      }
+      gk[j] = (u - s_adj * w) * scale;
+      proj = fmaf(gk[j], kw[m * D + d] * inv_norm, proj);
     }
-    const float gk = (u - s_adj * w) * scale;
-    proj = fmaf(gk, kw[m * D + d] * inv_norm, proj);
   }
   proj = warp_sum(proj);
-  for (int d = lane; d < D; d += 32) {
-    float u = 0.f, w = 0.f;
-    for (int ks = 0; ks < k_splits; ++ks) {
-      u += uw[(((int64_t)ks * 2 + 0) * Mp + m) * D + d];
-      w += uw[(((int64_t)ks * 2 + 1) * Mp + m) * D + d];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int d = lane + 32 * j;
+    if (d < D) {
+      const float kh = kw[m * D + d] * inv_norm;
+      g_kw[m * D + d] = (gk[j] - proj * kh) * inv_norm;
     }
-    const float gk = (u - s_adj * w) * scale;
-    const float kh = kw[m * D + d] * inv_norm;
-    g_kw[m * D + d] = (gk - proj * kh) * inv_norm;
   }
   if (g_tau && lane == 0) {
     // d/dtau = -(1/tau^2) sum_v P (T - s) c      (T in true units = T' * |g| * norm_ref)
@@ -719,6 +779,7 @@ struct VqFwdWs {
   float* chunk_max;
   float* partials;
   float* lse1_l2;
+  float* metric_part;
   size_t total;
   int n_chunks, n_groups;
 };
@@ -744,6 +805,7 @@ static VqFwdWs vq_fwd_ws(void* base, int64_t M, int64_t V) {
   w.chunk_max = static_cast<float*>(take((size_t)Mp * w.n_chunks * 4));
   w.partials = static_cast<float*>(take((size_t)Mp * w.n_groups * 16));
   w.lse1_l2 = static_cast<float*>(take((size_t)round_up(M, 256) * 4));
+  w.metric_part = static_cast<float*>(take((size_t)kMetricBlocks * 2 * 4));
   w.total = off;
   return w;
 }
@@ -785,7 +847,7 @@ static VqBwdWs vq_bwd_ws(void* base, int64_t M, int64_t V, int64_t D) {
 
 static int check_vq_shape(int64_t M, int64_t V, int64_t D) {
   SCP_CHECK_ARG(M > 0 && V > 0 && D > 0, "vq: non-positive shape");
-  if (D % 64 != 0 || D > 4096) return fail(SCP_ERR_UNSUPPORTED, "vq: D must be a multiple of 64 (<= 4096), got %lld", (long long)D);
+  if (D % 64 != 0 || D > 1024) return fail(SCP_ERR_UNSUPPORTED, "vq: D must be a multiple of 64 (<= 1024), got %lld", (long long)D);
   if (V < 2) return fail(SCP_ERR_UNSUPPORTED, "vq: V must be >= 2");
   return SCP_OK;
 }
@@ -873,9 +935,17 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
     if ((rc = tc::launch_stream_gemm<kVqBN, 1, 4, Sweep1Epi>(maps, sc, ep, s, "vq_sweep1"))) return rc;
   }
   // ---- exact arg-max, statistics, gather
-  vq_select_kernel<<<(unsigned)M, 128, (size_t)D * sizeof(double), s>>>(
-      kw, table, M, (int)V, (int)D, ws.chunk_max, ws.n_chunks, ws.partials, ws.n_groups, tau, mc, idx, keywords,
-      row_stats, code_hist);
+#define SCP_SELECT(NVV)                                                                                              \
+  vq_select_kernel<NVV><<<(unsigned)M, 128, 0, s>>>(kw, table, M, (int)V, (int)D, ws.chunk_max, ws.n_chunks,          \
+                                                    ws.partials, ws.n_groups, tau, mc, idx, keywords, row_stats,     \
+                                                    code_hist)
+  if (D <= 128) SCP_SELECT(1);
+  else if (D <= 256) SCP_SELECT(2);
+  else if (D <= 512) SCP_SELECT(4);
+  else if (D <= 768) SCP_SELECT(6);
+  else if (D <= 1024) SCP_SELECT(8);
+  else return fail(SCP_ERR_UNSUPPORTED, "vq_fwd: D > 1024 is not supported by the exact arg-max kernel (got %lld)", (long long)D);
+#undef SCP_SELECT
   SCP_CUDA_LAUNCH_CHECK("vq_select");
   // ---- sweep 2 (column sums) -- skipped when the caller does not want prob_perplexity
   if (avg_probs) {
@@ -902,7 +972,9 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
     ep.mc = mc;
     if ((rc = tc::launch_stream_gemm<256, 1, 4, Sweep2Epi>(maps, sc, ep, s, "vq_sweep2"))) return rc;
   }
-  vq_metrics_kernel<<<1, 1024, 0, s>>>(code_hist, avg_probs, row_stats, M, (int)K, (int)V, metrics);
+  vq_metrics_partial_kernel<<<kMetricBlocks, 256, 0, s>>>(code_hist, avg_probs, M, (int)V, ws.metric_part);
+  SCP_CUDA_LAUNCH_CHECK("vq_metrics_partial");
+  vq_metrics_kernel<<<1, 256, 0, s>>>(ws.metric_part, avg_probs != nullptr, row_stats, M, (int)K, (int)V, metrics);
   SCP_CUDA_LAUNCH_CHECK("vq_metrics");
   return SCP_OK;
 }
@@ -998,13 +1070,15 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
   return SCP_OK;
 }
 
-extern "C" size_t scp_vq_dense_workspace_bytes(int64_t, int64_t) { return 256; }
+extern "C" size_t scp_vq_dense_workspace_bytes(int64_t, int64_t) { return (size_t)kMetricBlocks * 2 * 4; }
 
 extern "C" int scp_vq_dense_fwd(float* x, int64_t M, int64_t K, int64_t V, int64_t ldx, const int32_t* masked_cols,
                                 int n_masked, const float* tau, int training, int64_t* idx, float* row_stats,
-                                float* code_hist, float* avg_probs, float* metrics, float* subword_prob, void*, size_t,
-                                scp_stream_t stream) {
-  SCP_CHECK_ARG(x && tau && idx && row_stats && code_hist && metrics, "vq_dense_fwd: null pointer");
+                                float* code_hist, float* avg_probs, float* metrics, float* subword_prob,
+                                void* workspace, size_t workspace_bytes, scp_stream_t stream) {
+  SCP_CHECK_ARG(x && tau && idx && row_stats && code_hist && metrics && workspace, "vq_dense_fwd: null pointer");
+  if (workspace_bytes < scp_vq_dense_workspace_bytes(M, V))
+    return fail(SCP_ERR_WORKSPACE, "vq_dense_fwd: workspace %zu < %zu", workspace_bytes, scp_vq_dense_workspace_bytes(M, V));
   SCP_CHECK_ARG(M > 0 && V > 1 && K > 0 && M % K == 0 && ldx >= V, "vq_dense_fwd: bad shape");
   SCP_CHECK_ARG(V < (1ll << 31), "vq_dense_fwd: V too large");
   SCP_CHECK_ARG(n_masked >= 0 && n_masked <= SCP_MAX_MASKED && (n_masked == 0 || masked_cols), "vq_dense_fwd: masked cols");
@@ -1018,7 +1092,10 @@ extern "C" int scp_vq_dense_fwd(float* x, int64_t M, int64_t K, int64_t V, int64
     vq_dense_colsum_kernel<<<(unsigned)ceil_div(V, 128), 128, 0, s>>>(x, M, (int)V, ldx, row_stats, avg_probs);
     SCP_CUDA_LAUNCH_CHECK("vq_dense_colsum");
   }
-  vq_metrics_kernel<<<1, 1024, 0, s>>>(code_hist, avg_probs, row_stats, M, (int)K, (int)V, metrics);
+  float* part = reinterpret_cast<float*>(workspace);
+  vq_metrics_partial_kernel<<<kMetricBlocks, 256, 0, s>>>(code_hist, avg_probs, M, (int)V, part);
+  SCP_CUDA_LAUNCH_CHECK("vq_metrics_partial");
+  vq_metrics_kernel<<<1, 256, 0, s>>>(part, avg_probs != nullptr, row_stats, M, (int)K, (int)V, metrics);
   SCP_CUDA_LAUNCH_CHECK("vq_metrics");
   return SCP_OK;
 }

@@ -46,12 +46,14 @@ class _MaskedNceFn(torch.autograd.Function):
         lse_col = torch.empty(N, dtype=torch.float32, device=dev)
         ws_bytes = lib.scp_nce_workspace_bytes(N, D)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        need_bwd = any(ctx.needs_input_grad[:3])
         with torch.cuda.device(dev):
             st = lib.scp_nce_fwd(_lib.ptr(a), _lib.ptr(b), _lib.ptr(ids), N, D, _lib.ptr(ls), float(fixed_scale),
-                                 float(margin), int(dcl), int(a2b), int(b2a), _lib.ptr(loss), _lib.ptr(lse_row),
-                                 _lib.ptr(lse_col), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
+                                 float(margin), int(dcl), int(a2b), int(b2a), int(need_bwd), _lib.ptr(loss),
+                                 _lib.ptr(lse_row), _lib.ptr(lse_col), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
         _lib.check(st, "scp_nce_fwd")
-        ctx.save_for_backward(a, b, ids, ls, lse_row, lse_col)
+        # the workspace holds the split fp16 operands; keeping it alive lets the backward skip their re-computation
+        ctx.save_for_backward(a, b, ids, ls, lse_row, lse_col, ws if need_bwd else None)
         ctx.cfg = (float(fixed_scale), float(margin), int(dcl), int(a2b), int(b2a), int(row_begin), int(row_end))
         ctx.in_dtypes = (feat_a.dtype, feat_b.dtype)
         return loss.reshape(())
@@ -59,7 +61,7 @@ class _MaskedNceFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss):
         lib = _lib.load()
-        a, b, ids, ls, lse_row, lse_col = ctx.saved_tensors
+        a, b, ids, ls, lse_row, lse_col, ws = ctx.saved_tensors
         fixed_scale, margin, dcl, a2b, b2a, row_begin, row_end = ctx.cfg
         N, D = a.shape
         dev = a.device
@@ -71,12 +73,14 @@ class _MaskedNceFn(torch.autograd.Function):
         dB = torch.empty((n_local, D), dtype=torch.float32, device=dev) if need_b else None
         dT = torch.empty(1, dtype=torch.float32, device=dev) if need_t else None
         ws_bytes = lib.scp_nce_workspace_bytes(N, D)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        state_valid = ws is not None
+        if ws is None:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             st = lib.scp_nce_bwd(_lib.ptr(a), _lib.ptr(b), _lib.ptr(ids), N, D, _lib.ptr(ls), fixed_scale, margin,
                                  dcl, a2b, b2a, _lib.ptr(lse_row), _lib.ptr(lse_col), _lib.ptr(g), row_begin,
-                                 row_end, _lib.ptr(dA), _lib.ptr(dB), _lib.ptr(dT), _lib.ptr(ws), ws_bytes,
-                                 _lib.stream_ptr(dev))
+                                 row_end, int(state_valid), _lib.ptr(dA), _lib.ptr(dB), _lib.ptr(dT), _lib.ptr(ws),
+                                 ws_bytes, _lib.stream_ptr(dev))
         _lib.check(st, "scp_nce_bwd")
 
         def full(local: Optional[torch.Tensor], dtype) -> Optional[torch.Tensor]:

@@ -170,10 +170,12 @@ class _DenseVQFn(torch.autograd.Function):
         avg_probs = torch.empty(V, dtype=torch.float32, device=dev)
         metrics = torch.empty(3 + K, dtype=torch.float32, device=dev)
         sub = torch.empty((M, V), dtype=torch.float32, device=dev)
+        ws_bytes = lib.scp_vq_dense_workspace_bytes(M, V)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             st = lib.scp_vq_dense_fwd(_lib.ptr(x2), M, K, V, x2.stride(0), masked, n_masked, _lib.ptr(tau_f),
                                       int(training), _lib.ptr(idx), _lib.ptr(row_stats), _lib.ptr(code_hist),
-                                      _lib.ptr(avg_probs), _lib.ptr(metrics), _lib.ptr(sub), None, 0,
+                                      _lib.ptr(avg_probs), _lib.ptr(metrics), _lib.ptr(sub), _lib.ptr(ws), ws_bytes,
                                       _lib.stream_ptr(dev))
         _lib.check(st, "scp_vq_dense_fwd")
         ctx.training = training
