@@ -110,7 +110,7 @@ __device__ __forceinline__ bool nce_in_denominator(bool diag, bool same_id, int 
 struct NceFwdEpi {
   struct Params {
     NceCommon c;
-    float* partials;  // (2*Np, n_groups, 2): running max, sum
+    float* partials;  // (2*Np, 2*n_groups, 2): running max, sum
     int Np, n_groups;
   };
   static constexpr int kSmemBytes = 0;
@@ -119,8 +119,8 @@ struct NceFwdEpi {
   bool own_valid;
   int64_t own_id;
   float k, run_max, sum;
-  __device__ __forceinline__ NceFwdEpi(const Params& p_, const WorkInfo& w, int row_in_tile, uint8_t*)
-      : p(p_), r(w.m_tile * tc::kTileM + row_in_tile), group(w.n_group) {
+  __device__ __forceinline__ NceFwdEpi(const Params& p_, const WorkInfo& w, const tc::EpiCtx& ctx)
+      : p(p_), r(w.m_tile * tc::kTileM + ctx.row_in_tile), group(w.n_group * 2 + ctx.half) {
     dir = r >= p.Np;
     own = r - dir * p.Np;
     own_valid = own < p.c.N;
@@ -146,17 +146,18 @@ struct NceFwdEpi {
       l[i] = inc ? x : kNegBigN;
       cmax = fmaxf(cmax, l[i]);
     }
+    if (cmax <= kNegBigN) return;  // nothing of this chunk is in the denominator
     if (cmax > run_max) {
-      sum *= exp2f((run_max - cmax) * kLog2eN);
+      sum *= tc::fast_ex2((run_max - cmax) * kLog2eN);
       run_max = cmax;
     }
     const float shift = run_max * kLog2eN;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) sum += exp2f(fmaf(l[i], kLog2eN, -shift));
+    for (int i = 0; i < 32; ++i) sum += tc::fast_ex2(fmaf(l[i], kLog2eN, -shift));
   }
   __device__ __forceinline__ void finish() {
     float2 o = make_float2(run_max, sum);
-    *reinterpret_cast<float2*>(p.partials + ((int64_t)r * p.n_groups + group) * 2) = o;
+    *reinterpret_cast<float2*>(p.partials + ((int64_t)r * (2 * p.n_groups) + group) * 2) = o;
   }
 };
 
@@ -213,8 +214,8 @@ struct NceBwdEpi {
   int64_t own_id;
   float k, own_lse_l2, own_a, col_a, dsum;
   const float* col_lse;
-  __device__ __forceinline__ NceBwdEpi(const Params& p_, const WorkInfo& w, int row_in_tile, uint8_t*)
-      : p(p_), r(w.m_tile * tc::kTileM + row_in_tile), group(w.n_group) {
+  __device__ __forceinline__ NceBwdEpi(const Params& p_, const WorkInfo& w, const tc::EpiCtx& ctx)
+      : p(p_), r(w.m_tile * tc::kTileM + ctx.row_in_tile), group(w.n_group * 2 + ctx.half) {
     dir = r >= p.Lp;
     const int loc = r - dir * p.Lp;
     own_valid = loc < p.n_local;
@@ -249,7 +250,7 @@ struct NceBwdEpi {
         const float x = (diag ? raw - p.c.margin : raw) * kLog2eN;
         const float cl = jv ? __ldg(col_lse + j) * kLog2eN : 0.f;
         float g = 0.f;
-        if (inc) g = own_a * exp2f(x - own_lse_l2) + col_a * exp2f(x - cl);
+        if (inc) g = own_a * tc::fast_ex2(x - own_lse_l2) + col_a * tc::fast_ex2(x - cl);
         if (diag && jv) g -= (own_a + col_a);
         dsum = fmaf(g, raw, dsum);
         g2[h] = g * kGScale;
@@ -273,7 +274,7 @@ struct NceBwdEpi {
     }
   }
   __device__ __forceinline__ void finish() {
-    if (!dir) p.dscale_part[(int64_t)r * p.n_groups + group] = own_valid ? dsum : 0.f;
+    if (!dir) p.dscale_part[(int64_t)r * (2 * p.n_groups) + group] = own_valid ? dsum : 0.f;
   }
 };
 
@@ -288,8 +289,8 @@ struct NceStoreEpi {
   const Params& p;
   int64_t row;
   int ks;
-  __device__ __forceinline__ NceStoreEpi(const Params& p_, const WorkInfo& w, int row_in_tile, uint8_t*)
-      : p(p_), row((int64_t)w.m_tile * tc::kTileM + row_in_tile), ks(w.k_split) {}
+  __device__ __forceinline__ NceStoreEpi(const Params& p_, const WorkInfo& w, const tc::EpiCtx& ctx)
+      : p(p_), row((int64_t)w.m_tile * tc::kTileM + ctx.row_in_tile), ks(w.k_split) {}
   __device__ __forceinline__ void tile_begin(int) {}
   __device__ __forceinline__ void tile_end(int) {}
   __device__ __forceinline__ void chunk(int col0, float (&v)[NX][32]) {
@@ -406,8 +407,8 @@ static NceWs nce_ws(void* base, int64_t N, int64_t D, int64_t n_local) {
   w.t3 = static_cast<__half*>(take((size_t)2 * D * 3 * Np * 2));
   w.g3 = static_cast<__half*>(take((size_t)2 * Lp * 3 * Np * 2));
   w.pos = static_cast<float*>(take((size_t)Np * 4));
-  w.partials = static_cast<float*>(take((size_t)2 * Np * w.n_groups * 8));
-  w.dscale_part = static_cast<float*>(take((size_t)Lp * kNumSMs * 4));
+  w.partials = static_cast<float*>(take((size_t)2 * Np * w.n_groups * 2 * 8));
+  w.dscale_part = static_cast<float*>(take((size_t)Lp * kNumSMs * 2 * 4));
   // split-K partials: k_splits * out_items <= 148 bounds the size independently of n_local
   w.out = static_cast<float*>(take(std::max((size_t)2 * Np * 2 * D * 4, (size_t)kNumSMs * tc::kTileM * 256 * 2 * 4)));
   w.total = off;
@@ -470,7 +471,7 @@ extern "C" int scp_nce_fwd(const float* A, const float* Bm, const int64_t* ids, 
   const Sched sc = nce_sweep_sched(Np, Np, D, ws.n_groups);
   NceFwdEpi::Params ep{c, ws.partials, (int)Np, ws.n_groups};
   if ((rc = tc::launch_stream_gemm<kNceBN, 1, 6, NceFwdEpi>(maps, sc, ep, s, "nce_fwd_sweep"))) return rc;
-  nce_loss_kernel<<<1, 1024, 0, s>>>(ws.partials, (int)Np, ws.n_groups, ws.pos, c, a2b, b2a, loss, lse_row, lse_col);
+  nce_loss_kernel<<<1, 1024, 0, s>>>(ws.partials, (int)Np, 2 * ws.n_groups, ws.pos, c, a2b, b2a, loss, lse_row, lse_col);
   SCP_CUDA_LAUNCH_CHECK("nce_loss");
   return SCP_OK;
 }
@@ -556,7 +557,7 @@ extern "C" int scp_nce_bwd(const float* A, const float* Bm, const int64_t* ids, 
   }
   const int64_t total = n_local * D;
   nce_bwd_finalize_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, 256), 1024), 256, 0, s>>>(
-      ws.out, k_splits, Lp, (int)D, n_local, c, a2b + b2a, g_loss, ws.dscale_part, sweep_groups, dA, dB, d_log_scale);
+      ws.out, k_splits, Lp, (int)D, n_local, c, a2b + b2a, g_loss, ws.dscale_part, 2 * sweep_groups, dA, dB, d_log_scale);
   SCP_CUDA_LAUNCH_CHECK("nce_bwd_finalize");
   return SCP_OK;
 }

@@ -6,8 +6,9 @@
 // (thread <-> row, 32 columns at a time), so that row reductions (max / arg-max / log-sum-exp / dot products) are
 // thread-serial and the logits never leave the SM.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2..5 = epilogue (warp w reads TMEM lanes 32*(w%4) .. +32).
+// Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..9 = epilogue: warp w reads TMEM lanes 32*(w%4) .. +32; the two warps that share a lane quadrant split the
+// tile's 32-column chunks between them ("halves"), so every SM sub-partition has two epilogue warps to hide latency.
 // Pipelines: STAGES-deep smem ring (full/empty mbarriers, TMA <-> MMA) and ACC_STAGES TMEM accumulator sets
 // (tmem_full/tmem_empty mbarriers, MMA <-> epilogue) so that the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
@@ -19,6 +20,19 @@ namespace tc {
 struct GemmMaps {
   CUtensorMap x[2];
   CUtensorMap y;
+  CUtensorMap o;  // optional output map for epilogues that store tiles with TMA
+};
+
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kEpiBarrierId = 1;
+
+struct EpiCtx {
+  int row_in_tile;  // 0..127: TMEM lane == X row inside the CTA tile
+  int half;         // 0/1: which half of every tile's column chunks this warp consumes
+  int tid;          // 0..255 inside the epilogue group
+  uint8_t* smem;    // Epi::kSmemBytes bytes, 1024-byte aligned, shared by the epilogue group
+  const GemmMaps* maps;
 };
 
 // CTA -> work decomposition.  blockIdx.x = m_tile + m_tiles * (n_group + n_groups * k_split)
@@ -62,7 +76,7 @@ __device__ __forceinline__ WorkInfo decode_work(const Sched& s) {
   return w;
 }
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 64 + kEpiThreads;
 constexpr int kXTileBytes = kTileM * kChunkK * 2;  // 16 KB
 
 template <int BN, int NX, int STAGES>
@@ -71,22 +85,25 @@ struct GemmCfg {
   static constexpr int kStageBytes = NX * kXTileBytes + kYTileBytes;
   static constexpr int kAccCols = NX * BN;
   static constexpr int kAccStages = (int)kTmemCols / kAccCols >= 2 ? 2 : 1;
-  static constexpr int kBarrierBytes = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int kBarrierBytes = 1024;  // mbarriers + TMEM slot; keeps the epilogue scratch 1024-aligned
   // 1024 B slack for manual alignment of the dynamic smem base
   static constexpr int smem_bytes(int epi_bytes) { return 1024 + STAGES * kStageBytes + kBarrierBytes + epi_bytes; }
   static_assert(kAccCols <= (int)kTmemCols, "accumulators exceed TMEM");
-  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
+  static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN");
+  static_assert((2 * STAGES + 4) * 8 + 16 <= kBarrierBytes, "barrier area");
   static_assert(STAGES * kStageBytes <= 220 * 1024, "smem ring too large");
 };
 
 // Epi interface (all __device__ __forceinline__):
 //   struct Params;                      POD passed by value to the kernel
-//   static constexpr int kSmemBytes;    extra shared memory (shared by the 4 epilogue warps)
-//   Epi(const Params&, const WorkInfo&, int row_in_tile, uint8_t* epi_smem)
+//   static constexpr int kSmemBytes;    extra shared memory (shared by the 8 epilogue warps)
+//   Epi(const Params&, const WorkInfo&, const EpiCtx&)
 //   void tile_begin(int n_tile);
 //   void chunk(int col0, float (&v)[NX][32]);      // columns [col0, col0+32) of Y-row space (global index)
 //   void tile_end(int n_tile);
 //   void finish();
+// Per-row state lives in the two warps ("halves") that own the row; epilogues combine the halves themselves
+// (separate partial slots, or through ctx.smem + named_bar_sync(kEpiBarrierId, kEpiThreads)).
 template <int BN, int NX, int STAGES, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, const typename Epi::Params ep) {
@@ -116,7 +133,7 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull_bar[a], 1);
-        mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+        mbar_init(&tempty_bar[a], kEpiWarps);  // one arrive per epilogue warp
       }
       fence_barrier_init();
     }
@@ -178,8 +195,14 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
   } else {
     // ---------------- epilogue warps ----------------
     const int quad = warp & 3;
-    const int row_in_tile = quad * 32 + lane;
-    Epi epi(ep, work, row_in_tile, epi_smem);
+    EpiCtx ctx;
+    ctx.row_in_tile = quad * 32 + lane;
+    ctx.half = (warp - 2) >> 2;
+    ctx.tid = threadIdx.x - 64;
+    ctx.smem = epi_smem;
+    ctx.maps = &maps;
+    Epi epi(ep, work, ctx);
+    constexpr int kChunksPerHalf = BN / 64;
     int as = 0;
     uint32_t aphase = 0;
     for (int nt = work.nt0; nt < work.nt1; ++nt) {
@@ -188,7 +211,8 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
       epi.tile_begin(nt);
       const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * Cfg::kAccCols);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int cc = 0; cc < kChunksPerHalf; ++cc) {
+        const int c = ctx.half * kChunksPerHalf + cc;
         float v[NX][32];
         __syncwarp();
 #pragma unroll

@@ -143,7 +143,7 @@ __global__ void vq_prep_kw_kernel(const float* __restrict__ kw, int64_t M, int64
 struct Sweep1Epi {
   struct Params {
     float* chunk_max;   // (Mp, n_chunks)
-    float* partials;    // (Mp, n_groups, 4): sum e^c, sum c e^c, running max, sum e^{(c-max)/tau}
+    float* partials;    // (Mp, n_slots, 4): sum e^c, sum c e^c, running max, sum e^{(c-max)/tau};  n_slots = 2*n_groups
     const float* tau;   // device scalar
     int n_chunks;
     int n_groups;
@@ -153,12 +153,12 @@ struct Sweep1Epi {
   static constexpr int kSmemBytes = 0;
   const Params& p;
   int64_t row;
-  int group;
+  int slot;
   float k_tau;  // log2(e)/tau
   float sum_e1, sum_ce1, run_max, sum_et;
 
-  __device__ __forceinline__ Sweep1Epi(const Params& p_, const WorkInfo& w, int row_in_tile, uint8_t*)
-      : p(p_), row((int64_t)w.m_tile * tc::kTileM + row_in_tile), group(w.n_group) {
+  __device__ __forceinline__ Sweep1Epi(const Params& p_, const WorkInfo& w, const tc::EpiCtx& ctx)
+      : p(p_), row((int64_t)w.m_tile * tc::kTileM + ctx.row_in_tile), slot(w.n_group * 2 + ctx.half) {
     k_tau = kLog2e / __ldg(p.tau);
     sum_e1 = 0.f; sum_ce1 = 0.f; run_max = kNegBig; sum_et = 0.f;
   }
@@ -175,22 +175,23 @@ struct Sweep1Epi {
 #pragma unroll
     for (int i = 1; i < 32; ++i) cmax = fmaxf(cmax, c[i]);
     p.chunk_max[row * p.n_chunks + (col0 >> 5)] = cmax;
+    if (cmax <= kNegBig) return;  // fully masked / padding chunk: contributes nothing (and has no finite maximum)
     if (cmax > run_max) {  // rescale the temperature-tau sum to the new running maximum
-      sum_et *= exp2f((run_max - cmax) * k_tau);
+      sum_et *= tc::fast_ex2((run_max - cmax) * k_tau);
       run_max = cmax;
     }
     const float shift = run_max * k_tau;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      const float e1 = exp2f(c[i] * kLog2e);  // |c| <= 1: no shift needed at temperature 1
+      const float e1 = tc::fast_ex2(c[i] * kLog2e);  // |c| <= 1: no shift needed at temperature 1
       sum_e1 += e1;
       sum_ce1 = fmaf(c[i], e1, sum_ce1);
-      sum_et += exp2f(fmaf(c[i], k_tau, -shift));
+      sum_et += tc::fast_ex2(fmaf(c[i], k_tau, -shift));
     }
   }
   __device__ __forceinline__ void finish() {
     float4 o = make_float4(sum_e1, sum_ce1, run_max, sum_et);
-    *reinterpret_cast<float4*>(p.partials + (row * p.n_groups + group) * 4) = o;
+    *reinterpret_cast<float4*>(p.partials + (row * (2 * p.n_groups) + slot) * 4) = o;
   }
 };
 
@@ -212,15 +213,22 @@ __device__ __forceinline__ Best better(const Best& a, const Best& b) {
 constexpr int kSelMaxCand = 64;  // candidate chunks buffered per pass (more candidates -> more passes)
 
 // Exact re-scoring of one 32-column chunk by a 128-thread block: warp w scores columns [8w, 8w+8); the 32 lanes of a
-// warp split the D axis (coalesced 16-byte loads of the fp32 table row, all 8 rows' loads in flight together), fp64
-// FMAs, butterfly reduction.  kreg holds this lane's slice of the keyword row in fp64.
+// warp split the D axis (coalesced 16-byte loads of the fp32 table row, all loads of the batch in flight together).
+// Two precision levels keep the fp64 pipe almost idle:
+//   1. fp32 scores of the 8 columns (16 products per lane + butterfly: error <= ~1.3e-6 * ||kw||),
+//   2. only the columns within 4e-6 * ||kw|| of the best fp32 score of the group (normally exactly one) are evaluated
+//      in fp64 (exact products of fp32 numbers, fp64 accumulation) -- the group's true maximum is always among them.
+// kreg holds this lane's slice of the keyword row.
 template <int NV>  // float4 vectors per lane: D <= 128*NV
-__device__ __forceinline__ Best rescore_chunk(const float* __restrict__ table, int V, int D, int chunk,
-                                              const double (&kreg)[NV][4], const MaskedCols& mc, int warp, int lane) {
+__device__ __forceinline__ Best rescore_chunk(const float* __restrict__ table, const float* __restrict__ table_norm,
+                                              int V, int D, int chunk, const float (&kreg)[NV][4], float margin2,
+                                              const MaskedCols& mc, int warp, int lane) {
   Best best{0.0, -1};
   const int nvec = D >> 2;
-  constexpr int CB = NV <= 4 ? 8 : 4;  // columns whose loads are in flight together (register budget)
-#pragma unroll 1
+  constexpr int CB = NV <= 2 ? 8 : 4;  // columns whose loads are in flight together (register budget)
+  float sc[8];
+  float gmax = -INFINITY;
+#pragma unroll
   for (int cb = 0; cb < 8; cb += CB) {
     float4 x[CB][NV];
 #pragma unroll
@@ -236,21 +244,41 @@ __device__ __forceinline__ Best rescore_chunk(const float* __restrict__ table, i
 #pragma unroll
     for (int c = 0; c < CB; ++c) {
       const int v = chunk * 32 + warp * 8 + cb + c;
+      float dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        dot = fmaf(kreg[j][0], x[c][j].x, dot);
+        dot = fmaf(kreg[j][1], x[c][j].y, dot);
+        dot = fmaf(kreg[j][2], x[c][j].z, dot);
+        dot = fmaf(kreg[j][3], x[c][j].w, dot);
+      }
+      dot = warp_sum(dot);
+      const bool ok = v < V && !is_masked(mc, v);
+      sc[cb + c] = ok ? dot / __ldg(table_norm + min(v, V - 1)) : -INFINITY;
+      gmax = fmaxf(gmax, sc[cb + c]);
+    }
+  }
+  const float thr2 = gmax - margin2;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if (sc[c] >= thr2 && sc[c] > -INFINITY) {  // warp-uniform; normally true for exactly one column
+      const int v = chunk * 32 + warp * 8 + c;
+      const float4* e = reinterpret_cast<const float4*>(table + (int64_t)v * D);
       double dot = 0.0, nn = 0.0;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        const double x0 = x[c][j].x, x1 = x[c][j].y, x2 = x[c][j].z, x3 = x[c][j].w;
-        dot = fma(kreg[j][0], x0, dot); nn = fma(x0, x0, nn);
-        dot = fma(kreg[j][1], x1, dot); nn = fma(x1, x1, nn);
-        dot = fma(kreg[j][2], x2, dot); nn = fma(x2, x2, nn);
-        dot = fma(kreg[j][3], x3, dot); nn = fma(x3, x3, nn);
+        const int q = lane + 32 * j;
+        const float4 xv = q < nvec ? __ldg(e + q) : make_float4(0.f, 0.f, 0.f, 0.f);  // L1/L2 hit
+        const double x0 = xv.x, x1 = xv.y, x2 = xv.z, x3 = xv.w;
+        dot = fma((double)kreg[j][0], x0, dot); nn = fma(x0, x0, nn);
+        dot = fma((double)kreg[j][1], x1, dot); nn = fma(x1, x1, nn);
+        dot = fma((double)kreg[j][2], x2, dot); nn = fma(x2, x2, nn);
+        dot = fma((double)kreg[j][3], x3, dot); nn = fma(x3, x3, nn);
       }
       dot = warp_sum(dot);
       nn = warp_sum(nn);
-      if (v < V && !is_masked(mc, v)) {
-        const double score = dot / fmax(sqrt(nn), 1e-8);  // the common factor 1/||kw|| does not change the order
-        best = better(best, Best{score, v});
-      }
+      const double score = dot / fmax(sqrt(nn), 1e-8);  // the common factor 1/||kw|| does not change the order
+      best = better(best, Best{score, v});
     }
   }
   return best;  // identical in every lane of the warp
@@ -258,8 +286,8 @@ __device__ __forceinline__ Best rescore_chunk(const float* __restrict__ table, i
 
 template <int NV>
 __global__ void __launch_bounds__(128)
-vq_select_kernel(const float* __restrict__ kw, const float* __restrict__ table, int64_t M, int V, int D,
-                 const float* __restrict__ chunk_max, int n_chunks, const float* __restrict__ partials, int n_groups,
+vq_select_kernel(const float* __restrict__ kw, const float* __restrict__ table, const float* __restrict__ table_norm,
+                 int64_t M, int V, int D, const float* __restrict__ chunk_max, int n_chunks, const float* __restrict__ partials, int n_groups,
                  const float* __restrict__ tau_ptr, MaskedCols mc, int64_t* __restrict__ idx_out,
                  float* __restrict__ keywords, float* __restrict__ row_stats, float* __restrict__ code_hist) {
   __shared__ float s_red[4];
@@ -268,15 +296,18 @@ vq_select_kernel(const float* __restrict__ kw, const float* __restrict__ table, 
   __shared__ int s_ncand;
   const int64_t m = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // this lane's slice of the keyword row, in fp64
-  double kreg[NV][4];
+  // this lane's slice of the keyword row
+  float kreg[NV][4];
   const int nvec = D >> 2;
+  float kss = 0.f;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const int q = lane + 32 * j;
     const float4 k4 = q < nvec ? __ldg(reinterpret_cast<const float4*>(kw + m * D) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
     kreg[j][0] = k4.x; kreg[j][1] = k4.y; kreg[j][2] = k4.z; kreg[j][3] = k4.w;
+    kss += k4.x * k4.x + k4.y * k4.y + k4.z * k4.z + k4.w * k4.w;
   }
+  const float margin2 = 4e-6f * sqrtf(warp_sum(kss));  // 2 x the fp32 dot-product error bound, see rescore_chunk
   // approximate (fp16-product) row maximum
   const float* cm = chunk_max + m * n_chunks;
   float mx = kNegBig;
@@ -302,9 +333,9 @@ vq_select_kernel(const float* __restrict__ kw, const float* __restrict__ table, 
     int ncand = s_ncand;
     if (ncand > kSelMaxCand) {
       // degenerate row (e.g. a zero keyword: every cosine ties): fall back to scoring every chunk of this pass
-      for (int c = base; c < hi; ++c) best = better(best, rescore_chunk<NV>(table, V, D, c, kreg, mc, warp, lane));
+      for (int c = base; c < hi; ++c) best = better(best, rescore_chunk<NV>(table, table_norm, V, D, c, kreg, margin2, mc, warp, lane));
     } else {
-      for (int i = 0; i < ncand; ++i) best = better(best, rescore_chunk<NV>(table, V, D, s_cand[i], kreg, mc, warp, lane));
+      for (int i = 0; i < ncand; ++i) best = better(best, rescore_chunk<NV>(table, table_norm, V, D, s_cand[i], kreg, margin2, mc, warp, lane));
     }
     __syncthreads();
     if (tid == 0) s_ncand = 0;
@@ -367,12 +398,14 @@ struct Sweep2Epi {
     int V;
     MaskedCols mc;
   };
-  static constexpr int kSmemBytes = 0;
+  static constexpr int kSmemBytes = tc::kTileM * 4;
   const Params& p;
-  int v;
+  int v, half, row_in_tile;
   float acc;
-  __device__ __forceinline__ Sweep2Epi(const Params& p_, const WorkInfo& w, int row_in_tile, uint8_t*)
-      : p(p_), v(w.m_tile * tc::kTileM + row_in_tile), acc(0.f) {}
+  float* s_acc;
+  __device__ __forceinline__ Sweep2Epi(const Params& p_, const WorkInfo& w, const tc::EpiCtx& ctx)
+      : p(p_), v(w.m_tile * tc::kTileM + ctx.row_in_tile), half(ctx.half), row_in_tile(ctx.row_in_tile), acc(0.f),
+        s_acc(reinterpret_cast<float*>(ctx.smem)) {}
   __device__ __forceinline__ void tile_begin(int) {}
   __device__ __forceinline__ void tile_end(int) {}
   __device__ __forceinline__ void chunk(int col0, float (&c)[1][32]) {
@@ -380,14 +413,17 @@ struct Sweep2Epi {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float4 l = __ldg(l4 + i);
-      acc += exp2f(fmaf(c[0][4 * i + 0], kLog2e, -l.x));
-      acc += exp2f(fmaf(c[0][4 * i + 1], kLog2e, -l.y));
-      acc += exp2f(fmaf(c[0][4 * i + 2], kLog2e, -l.z));
-      acc += exp2f(fmaf(c[0][4 * i + 3], kLog2e, -l.w));
+      acc += tc::fast_ex2(fmaf(c[0][4 * i + 0], kLog2e, -l.x));
+      acc += tc::fast_ex2(fmaf(c[0][4 * i + 1], kLog2e, -l.y));
+      acc += tc::fast_ex2(fmaf(c[0][4 * i + 2], kLog2e, -l.z));
+      acc += tc::fast_ex2(fmaf(c[0][4 * i + 3], kLog2e, -l.w));
     }
   }
   __device__ __forceinline__ void finish() {
-    p.avg_probs[v] = (v < p.V && !is_masked(p.mc, v)) ? acc * p.inv_m : 0.f;
+    // the two warps that own a row add their halves in a fixed order
+    if (half == 1) s_acc[row_in_tile] = acc;
+    tc::named_bar_sync(tc::kEpiBarrierId, tc::kEpiThreads);
+    if (half == 0) p.avg_probs[v] = (v < p.V && !is_masked(p.mc, v)) ? (acc + s_acc[row_in_tile]) * p.inv_m : 0.f;
   }
 };
 
@@ -490,20 +526,24 @@ struct Sweep3Epi {
     const float* table_norm;  // (Vp,)
     const float* table_mean;  // [D] = norm_ref
     const float* tau;
-    __half* pq;               // (2*Mp, Vp): rows [0,Mp) = Q~, rows [Mp,2Mp) = P~
-    float* partials;          // (Mp, n_groups, 4): sum Q, sum P, sum Q c, sum P c
-    int64_t M, Mp, Vp;
+    float* partials;          // (Mp, 2*n_groups, 4): sum Q, sum P, sum Q c, sum P c
+    int64_t M, Mp;
     int n_groups, V, D;
     MaskedCols mc;
   };
-  static constexpr int kSmemBytes = 0;
+  // staging for the TMA store of one 128 x 128 tile of Q~ and of P~: 4 boxes {64 cols, 128 rows} in the SWIZZLE_128B
+  // layout (row r at r*128 B, 16-byte units XOR-ed with r & 7).  pq (2*Mp, Vp): rows [0,Mp) = Q~, rows [Mp,2Mp) = P~.
+  static constexpr int kBoxBytes = tc::kTileM * 128;
+  static constexpr int kSmemBytes = 4 * kBoxBytes;
   const Params& p;
+  const tc::EpiCtx& ctx;
   int64_t row;
-  int group;
+  int slot, tile_col0, m_row0;
   float k_tau, lse_l2, s0, inv_norm_ref;
   float sq, sp, sqc, spc;
-  __device__ __forceinline__ Sweep3Epi(const Params& p_, const WorkInfo& w, int row_in_tile, uint8_t*)
-      : p(p_), row((int64_t)w.m_tile * tc::kTileM + row_in_tile), group(w.n_group) {
+  __device__ __forceinline__ Sweep3Epi(const Params& p_, const WorkInfo& w, const tc::EpiCtx& ctx_)
+      : p(p_), ctx(ctx_), row((int64_t)w.m_tile * tc::kTileM + ctx_.row_in_tile), slot(w.n_group * 2 + ctx_.half),
+        tile_col0(0), m_row0(w.m_tile * tc::kTileM) {
     k_tau = kLog2e / __ldg(p.tau);
     const bool valid = row < p.M;
     lse_l2 = valid ? p.row_stats[row * 4 + 1] * kLog2e : 1.0e30f;  // padding rows: P = 0
@@ -511,8 +551,11 @@ struct Sweep3Epi {
     inv_norm_ref = 1.0f / p.table_mean[p.D];
     sq = sp = sqc = spc = 0.f;
   }
-  __device__ __forceinline__ void tile_begin(int) {}
-  __device__ __forceinline__ void tile_end(int) {}
+  __device__ __forceinline__ void tile_begin(int nt) {
+    tile_col0 = nt * 128;
+    if (ctx.tid == 0) tc::bulk_wait_read_all();  // the previous tile's stores have drained the staging buffer
+    tc::named_bar_sync(tc::kEpiBarrierId, tc::kEpiThreads);
+  }
   __device__ __forceinline__ void chunk(int col0, float (&v)[2][32]) {
     float(&c)[32] = v[0];
     float(&t)[32] = v[1];
@@ -531,8 +574,8 @@ struct Sweep3Epi {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float cc = c[4 * i + j];
-        const float pj = exp2f(fmaf(cc, k_tau, -lse_l2));           // softmax_tau
-        const float tj = fmaf(t[4 * i + j] * nn[j], inv_norm_ref, -s0);  // (g . e_v)/(|g| norm_ref) - s0
+        const float pj = tc::fast_ex2(fmaf(cc, k_tau, -lse_l2));           // softmax_tau
+        const float tj = fmaf(t[4 * i + j] * nn[j], inv_norm_ref, -s0);    // (g . e_v)/(|g| norm_ref) - s0
         const float qj = pj * tj;
         sp += pj;
         sq += qj;
@@ -548,16 +591,34 @@ struct Sweep3Epi {
       h = __floats2half2_rn(pv[0], pv[1]); pk_p[2 * i] = *reinterpret_cast<uint32_t*>(&h);
       h = __floats2half2_rn(pv[2], pv[3]); pk_p[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h);
     }
-    uint4* dq = reinterpret_cast<uint4*>(p.pq + row * p.Vp + col0);
-    uint4* dp = reinterpret_cast<uint4*>(p.pq + (p.Mp + row) * p.Vp + col0);
+    // this chunk = 32 columns = four 16-byte units of this thread's row inside box (chunk / 2)
+    const int cin = (col0 - tile_col0) >> 5;  // chunk index inside the tile: 0..3
+    const int box = cin >> 1;
+    const int r = ctx.row_in_tile;
+    uint8_t* qbox = ctx.smem + box * kBoxBytes + r * 128;
+    uint8_t* pbox = ctx.smem + (2 + box) * kBoxBytes + r * 128;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      dq[i] = make_uint4(pk_q[4 * i], pk_q[4 * i + 1], pk_q[4 * i + 2], pk_q[4 * i + 3]);
-      dp[i] = make_uint4(pk_p[4 * i], pk_p[4 * i + 1], pk_p[4 * i + 2], pk_p[4 * i + 3]);
+      const int unit = ((cin & 1) * 4 + i) ^ (r & 7);
+      *reinterpret_cast<uint4*>(qbox + unit * 16) = make_uint4(pk_q[4 * i], pk_q[4 * i + 1], pk_q[4 * i + 2], pk_q[4 * i + 3]);
+      *reinterpret_cast<uint4*>(pbox + unit * 16) = make_uint4(pk_p[4 * i], pk_p[4 * i + 1], pk_p[4 * i + 2], pk_p[4 * i + 3]);
+    }
+  }
+  __device__ __forceinline__ void tile_end(int) {
+    tc::fence_proxy_async_smem();  // st.shared above must be visible to the TMA (async proxy)
+    tc::named_bar_sync(tc::kEpiBarrierId, tc::kEpiThreads);
+    if (ctx.tid == 0) {
+#pragma unroll
+      for (int box = 0; box < 2; ++box) {
+        tc::tma_store_2d(&ctx.maps->o, ctx.smem + box * kBoxBytes, tile_col0 + 64 * box, m_row0);
+        tc::tma_store_2d(&ctx.maps->o, ctx.smem + (2 + box) * kBoxBytes, tile_col0 + 64 * box, (int)p.Mp + m_row0);
+      }
+      tc::bulk_commit_group();
     }
   }
   __device__ __forceinline__ void finish() {
-    *reinterpret_cast<float4*>(p.partials + (row * p.n_groups + group) * 4) = make_float4(sq, sp, sqc, spc);
+    if (ctx.tid == 0) tc::bulk_wait_all();
+    *reinterpret_cast<float4*>(p.partials + (row * (2 * p.n_groups) + slot) * 4) = make_float4(sq, sp, sqc, spc);
   }
 };
 
@@ -573,8 +634,8 @@ struct StoreEpi {
   const Params& p;
   int64_t row;
   int ks;
-  __device__ __forceinline__ StoreEpi(const Params& p_, const WorkInfo& w, int row_in_tile, uint8_t*)
-      : p(p_), row((int64_t)w.m_tile * tc::kTileM + row_in_tile), ks(w.k_split) {}
+  __device__ __forceinline__ StoreEpi(const Params& p_, const WorkInfo& w, const tc::EpiCtx& ctx)
+      : p(p_), row((int64_t)w.m_tile * tc::kTileM + ctx.row_in_tile), ks(w.k_split) {}
   __device__ __forceinline__ void tile_begin(int) {}
   __device__ __forceinline__ void tile_end(int) {}
   __device__ __forceinline__ void chunk(int col0, float (&v)[NX][32]) {
@@ -803,7 +864,7 @@ static VqFwdWs vq_fwd_ws(void* base, int64_t M, int64_t V) {
     return p;
   };
   w.chunk_max = static_cast<float*>(take((size_t)Mp * w.n_chunks * 4));
-  w.partials = static_cast<float*>(take((size_t)Mp * w.n_groups * 16));
+  w.partials = static_cast<float*>(take((size_t)Mp * w.n_groups * 2 * 16));
   w.lse1_l2 = static_cast<float*>(take((size_t)round_up(M, 256) * 4));
   w.metric_part = static_cast<float*>(take((size_t)kMetricBlocks * 2 * 4));
   w.total = off;
@@ -839,7 +900,7 @@ static VqBwdWs vq_bwd_ws(void* base, int64_t M, int64_t V, int64_t D) {
   w.g_hat = static_cast<__half*>(take((size_t)Mp * D * 2));
   w.g_aux = static_cast<float*>(take((size_t)Mp * 2 * 4));
   w.pq = static_cast<__half*>(take((size_t)2 * Mp * Vp * 2));
-  w.partials = static_cast<float*>(take((size_t)Mp * w.n_groups * 16));
+  w.partials = static_cast<float*>(take((size_t)Mp * w.n_groups * 2 * 16));
   w.uw = static_cast<float*>(take((size_t)w.k_splits * 2 * Mp * D * 4));
   w.total = off;
   return w;
@@ -936,8 +997,8 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
   }
   // ---- exact arg-max, statistics, gather
 #define SCP_SELECT(NVV)                                                                                              \
-  vq_select_kernel<NVV><<<(unsigned)M, 128, 0, s>>>(kw, table, M, (int)V, (int)D, ws.chunk_max, ws.n_chunks,          \
-                                                    ws.partials, ws.n_groups, tau, mc, idx, keywords, row_stats,     \
+  vq_select_kernel<NVV><<<(unsigned)M, 128, 0, s>>>(kw, table, table_norm, M, (int)V, (int)D, ws.chunk_max, ws.n_chunks, \
+                                                    ws.partials, 2 * ws.n_groups, tau, mc, idx, keywords, row_stats, \
                                                     code_hist)
   if (D <= 128) SCP_SELECT(1);
   else if (D <= 256) SCP_SELECT(2);
@@ -1030,14 +1091,14 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
     ep.table_norm = table_norm;
     ep.table_mean = table_mean;
     ep.tau = tau;
-    ep.pq = ws.pq;
     ep.partials = ws.partials;
-    ep.M = M; ep.Mp = Mp; ep.Vp = Vp;
+    ep.M = M; ep.Mp = Mp;
+    if ((rc = tc::make_tmap_f16(&maps.o, ws.pq, 2 * Mp, Vp, Vp, tc::kTileM))) return rc;
     ep.n_groups = ws.n_groups;
     ep.V = (int)V;
     ep.D = (int)D;
     ep.mc = mc;
-    if ((rc = tc::launch_stream_gemm<128, 2, 4, Sweep3Epi>(maps, sc, ep, s, "vq_sweep3"))) return rc;
+    if ((rc = tc::launch_stream_gemm<128, 2, 3, Sweep3Epi>(maps, sc, ep, s, "vq_sweep3"))) return rc;
   }
   // ---- U = Q~ Ehat, W = P~ Ehat   (K = Vp, split-K partials)
   {
@@ -1064,7 +1125,7 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
   }
   if (g_tau && cudaMemsetAsync(g_tau, 0, 4, s) != cudaSuccess) return fail(SCP_ERR_CUDA, "memset g_tau");
   vq_bwd_finalize_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, s>>>(ws.uw, ws.k_splits, M, Mp, (int)D, ws.partials,
-                                                                  ws.n_groups, ws.g_aux, kw, row_stats, table_mean,
+                                                                  2 * ws.n_groups, ws.g_aux, kw, row_stats, table_mean,
                                                                   tau, g_kw, g_tau);
   SCP_CUDA_LAUNCH_CHECK("vq_bwd_finalize");
   return SCP_OK;
