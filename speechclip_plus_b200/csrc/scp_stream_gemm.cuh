@@ -11,6 +11,14 @@
 // tile's 32-column chunks between them ("halves"), so every SM sub-partition has two epilogue warps to hide latency.
 // Pipelines: STAGES-deep smem ring (full/empty mbarriers, TMA <-> MMA) and ACC_STAGES TMEM accumulator sets
 // (tmem_full/tmem_empty mbarriers, MMA <-> epilogue) so that the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Thread-block clusters (CL = 1, 2 or 4 CTAs) cut the L2 -> SM operand traffic, which is what bounds these kernels:
+// the CTAs of a cluster walk their tiles in lock-step and the operand they share is fetched ONCE per cluster -- every
+// CTA loads 1/CL of it and TMA-multicasts the slice into the same smem stage of all CTAs:
+//   MC_Y: cluster along the X-tile axis (different rows, same Y tiles)  -> Y slices are multicast
+//   MC_X: cluster along the Y-tile axis (same rows, different Y tiles)  -> X slices are multicast
+// A stage may be refilled only after ALL CTAs of the cluster consumed it: the MMA issuer's tcgen05.commit arrives on the
+// stage's `empty` barrier of every CTA (multicast commit), and each `empty` barrier counts CL arrivals.
 #pragma once
 #include "scp_tc.cuh"
 
@@ -18,14 +26,16 @@ namespace scp {
 namespace tc {
 
 struct GemmMaps {
-  CUtensorMap x[2];
-  CUtensorMap y;
-  CUtensorMap o;  // optional output map for epilogues that store tiles with TMA
+  CUtensorMap x[2];  // box {64, 128} (or {64, 128/CL} under MC_X)
+  CUtensorMap y;     // box {64, BN}  (or {64, BN/CL} under MC_Y)
+  CUtensorMap o;     // optional output map for epilogues that store tiles with TMA
 };
 
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kEpiBarrierId = 1;
+
+enum { MC_NONE = 0, MC_X = 1, MC_Y = 2 };
 
 struct EpiCtx {
   int row_in_tile;  // 0..127: TMEM lane == X row inside the CTA tile
@@ -35,40 +45,85 @@ struct EpiCtx {
   const GemmMaps* maps;
 };
 
-// CTA -> work decomposition.  blockIdx.x = m_tile + m_tiles * (n_group + n_groups * k_split)
+// CTA -> work decomposition (see decode_work)
 struct Sched {
   int m_tiles;   // 128-row tiles of X
   int n_tiles;   // BN-row tiles of Y
-  int n_groups;  // the n_tiles are partitioned into n_groups contiguous ranges
+  int n_groups;  // the n_tiles are partitioned into n_groups contiguous ranges (multiple of CL under MC_X)
   int k_chunks;  // total 64-element K chunks
   int k_splits;  // the k_chunks are partitioned into k_splits contiguous ranges
-  // two-direction launches (InfoNCE): CTAs whose m_tile >= m_half walk Y tiles shifted by n_upper_off
+  // two-direction launches (InfoNCE, CL == 1 only): CTAs whose m_tile >= m_half walk Y tiles shifted by n_upper_off
   int m_half;           // == m_tiles when unused
   int n_upper_off;      // == 0 when unused
   int x_upper_row_off;  // extra X row offset of the upper-half tiles (== 0 when unused)
-  __host__ __device__ int grid() const { return m_tiles * n_groups * k_splits; }
 };
+
+template <int CL, int MC>
+__host__ __device__ inline int sched_grid(const Sched& s) {
+  if (MC == MC_Y) return CL * ((s.m_tiles + CL - 1) / CL) * s.n_groups * s.k_splits;
+  return s.m_tiles * s.n_groups * s.k_splits;
+}
 
 struct WorkInfo {
   int m_tile, n_group, k_split;
-  int x_row;     // first X row of this CTA's tile (TMA coordinate)
-  int nt0, nt1;  // N-tile range
-  int kc0, kc1;  // K-chunk range
+  int x_row;                               // first X row of this CTA's tile (TMA coordinate)
+  int nt_first, nt_stride, nt_end, iters;  // tile i of this CTA: nt_first + i*nt_stride, real iff < nt_end
+  int kc0, kc1;                            // K-chunk range
+  int rank;                                // CTA rank inside the cluster
+  bool valid_m;                            // false for the padding CTAs of an MC_Y cluster (m_tile >= m_tiles)
 };
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int CL, int MC>
 __device__ __forceinline__ WorkInfo decode_work(const Sched& s) {
   WorkInfo w;
-  int b = blockIdx.x;
-  w.m_tile = b % s.m_tiles;
-  b /= s.m_tiles;
-  w.n_group = b % s.n_groups;
-  w.k_split = b / s.n_groups;
-  w.nt0 = (int)((long long)s.n_tiles * w.n_group / s.n_groups);
-  w.nt1 = (int)((long long)s.n_tiles * (w.n_group + 1) / s.n_groups);
+  w.rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  int c = CL > 1 ? (int)blockIdx.x / CL : (int)blockIdx.x;
+  int ng, nt0, nt1;
+  if (MC == MC_Y) {  // the cluster spans CL consecutive X tiles
+    const int m_ct = (s.m_tiles + CL - 1) / CL;
+    w.m_tile = (c % m_ct) * CL + w.rank;
+    c /= m_ct;
+    ng = c % s.n_groups;
+    w.k_split = c / s.n_groups;
+    nt0 = (int)((long long)s.n_tiles * ng / s.n_groups);
+    nt1 = (int)((long long)s.n_tiles * (ng + 1) / s.n_groups);
+    w.n_group = ng;
+    w.nt_first = nt0; w.nt_stride = 1; w.nt_end = nt1; w.iters = nt1 - nt0;
+  } else if (MC == MC_X) {  // the cluster spans CL consecutive n_groups; its tile range is dealt round-robin
+    w.m_tile = c % s.m_tiles;
+    c /= s.m_tiles;
+    const int ncg = s.n_groups / CL;
+    ng = c % ncg;
+    w.k_split = c / ncg;
+    nt0 = (int)((long long)s.n_tiles * ng / ncg);
+    nt1 = (int)((long long)s.n_tiles * (ng + 1) / ncg);
+    w.n_group = ng * CL + w.rank;
+    w.nt_first = nt0 + w.rank; w.nt_stride = CL; w.nt_end = nt1; w.iters = (nt1 - nt0 + CL - 1) / CL;
+  } else {
+    w.m_tile = c % s.m_tiles;
+    c /= s.m_tiles;
+    ng = c % s.n_groups;
+    w.k_split = c / s.n_groups;
+    nt0 = (int)((long long)s.n_tiles * ng / s.n_groups);
+    nt1 = (int)((long long)s.n_tiles * (ng + 1) / s.n_groups);
+    w.n_group = ng;
+    w.nt_first = nt0; w.nt_stride = 1; w.nt_end = nt1; w.iters = nt1 - nt0;
+  }
+  w.valid_m = w.m_tile < s.m_tiles;
   w.x_row = w.m_tile * kTileM;
   if (w.m_tile >= s.m_half) {
-    w.nt0 += s.n_upper_off;
-    w.nt1 += s.n_upper_off;
+    w.nt_first += s.n_upper_off;
+    w.nt_end += s.n_upper_off;
     w.x_row += s.x_upper_row_off;
   }
   w.kc0 = (int)((long long)s.k_chunks * w.k_split / s.k_splits);
@@ -104,10 +159,14 @@ struct GemmCfg {
 //   void finish();
 // Per-row state lives in the two warps ("halves") that own the row; epilogues combine the halves themselves
 // (separate partial slots, or through ctx.smem + named_bar_sync(kEpiBarrierId, kEpiThreads)).
-template <int BN, int NX, int STAGES, class Epi>
+template <int BN, int NX, int STAGES, class Epi, int CL, int MC>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, const typename Epi::Params ep) {
   using Cfg = GemmCfg<BN, NX, STAGES>;
+  static_assert(CL == 1 || CL == 2 || CL == 4, "cluster size");
+  static_assert((CL == 1) == (MC == MC_NONE), "clusters exist to multicast");
+  static_assert(MC != MC_X || (kTileM / CL) % 8 == 0, "X slice must be whole swizzle atoms");
+  static_assert(MC != MC_Y || (BN / CL) % 8 == 0, "Y slice must be whole swizzle atoms");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
@@ -118,7 +177,8 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
   uint8_t* epi_smem = smem + STAGES * Cfg::kStageBytes + Cfg::kBarrierBytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const WorkInfo work = decode_work(sched);
+  const WorkInfo work = decode_work<CL, MC>(sched);
+  constexpr uint16_t kClusterMask = (uint16_t)((1u << CL) - 1);
 
   if (warp == 0 && lane == 0) {
 #pragma unroll
@@ -129,7 +189,7 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
         mbar_init(&full_bar[s], 1);
-        mbar_init(&empty_bar[s], 1);
+        mbar_init(&empty_bar[s], CL);  // every CTA of the cluster must release the stage
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull_bar[a], 1);
@@ -141,7 +201,9 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
     tmem_alloc(tmem_slot, kTmemCols);
   }
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();  // barrier.cluster is .aligned: the single-lane branches above must have reconverged
+  if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts into them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
@@ -150,15 +212,31 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int nt = work.nt0; nt < work.nt1; ++nt) {
+      for (int it = 0; it < work.iters; ++it) {
+        int nt = work.nt_first + it * work.nt_stride;
+        if (nt >= work.nt_end) nt = work.nt_end - 1;  // lock-step padding tile (the epilogue ignores it)
         for (int kc = work.kc0; kc < work.kc1; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * Cfg::kStageBytes;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (MC == MC_X) {
+            constexpr int kRows = kTileM / CL;
 #pragma unroll
-          for (int x = 0; x < NX; ++x)
-            tma_load_2d(st + x * kXTileBytes, &maps.x[x], kc * kChunkK, work.x_row, &full_bar[stage]);
-          tma_load_2d(st + NX * kXTileBytes, &maps.y, kc * kChunkK, nt * BN, &full_bar[stage]);
+            for (int x = 0; x < NX; ++x)
+              tma_load_2d_mc(st + x * kXTileBytes + work.rank * kRows * 128, &maps.x[x], kc * kChunkK,
+                             work.x_row + work.rank * kRows, &full_bar[stage], kClusterMask);
+          } else {
+#pragma unroll
+            for (int x = 0; x < NX; ++x)
+              tma_load_2d(st + x * kXTileBytes, &maps.x[x], kc * kChunkK, work.x_row, &full_bar[stage]);
+          }
+          if (MC == MC_Y) {
+            constexpr int kRows = BN / CL;
+            tma_load_2d_mc(st + NX * kXTileBytes + work.rank * kRows * 128, &maps.y, kc * kChunkK,
+                           nt * BN + work.rank * kRows, &full_bar[stage], kClusterMask);
+          } else {
+            tma_load_2d(st + NX * kXTileBytes, &maps.y, kc * kChunkK, nt * BN, &full_bar[stage]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -169,7 +247,7 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
       constexpr uint32_t idesc = make_idesc_f16(BN);
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
-      for (int nt = work.nt0; nt < work.nt1; ++nt) {
+      for (int it = 0; it < work.iters; ++it) {
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         for (int kc = work.kc0; kc < work.kc1; ++kc) {
@@ -185,7 +263,9 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
             for (int k = 0; k < kChunkK / kUmmaK; ++k)
               umma_f16(d, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kc > work.kc0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          // smem slot reusable once these MMAs retire -- signalled to every CTA that may refill it
+          if (CL > 1) umma_commit_mc(&empty_bar[stage], kClusterMask);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[as]);  // accumulator set complete
@@ -195,49 +275,67 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
   } else {
     // ---------------- epilogue warps ----------------
     const int quad = warp & 3;
-    EpiCtx ctx;
-    ctx.row_in_tile = quad * 32 + lane;
-    ctx.half = (warp - 2) >> 2;
-    ctx.tid = threadIdx.x - 64;
-    ctx.smem = epi_smem;
-    ctx.maps = &maps;
-    Epi epi(ep, work, ctx);
-    constexpr int kChunksPerHalf = BN / 64;
     int as = 0;
     uint32_t aphase = 0;
-    for (int nt = work.nt0; nt < work.nt1; ++nt) {
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
-      epi.tile_begin(nt);
-      const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * Cfg::kAccCols);
+    if (work.valid_m) {
+      EpiCtx ctx;
+      ctx.row_in_tile = quad * 32 + lane;
+      ctx.half = (warp - 2) >> 2;
+      ctx.tid = threadIdx.x - 64;
+      ctx.smem = epi_smem;
+      ctx.maps = &maps;
+      Epi epi(ep, work, ctx);
+      constexpr int kChunksPerHalf = BN / 64;
+      for (int it = 0; it < work.iters; ++it) {
+        const int nt = work.nt_first + it * work.nt_stride;
+        const bool real = nt < work.nt_end;
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        if (real) {
+          epi.tile_begin(nt);
+          const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * Cfg::kAccCols);
 #pragma unroll 1
-      for (int cc = 0; cc < kChunksPerHalf; ++cc) {
-        const int c = ctx.half * kChunksPerHalf + cc;
-        float v[NX][32];
-        __syncwarp();
+          for (int cc = 0; cc < kChunksPerHalf; ++cc) {
+            const int c = ctx.half * kChunksPerHalf + cc;
+            float v[NX][32];
+            __syncwarp();
 #pragma unroll
-        for (int x = 0; x < NX; ++x) tmem_ld32(tbase + (uint32_t)(x * BN + c * 32), v[x]);
-        epi.chunk(nt * BN + c * 32, v);
+            for (int x = 0; x < NX; ++x) tmem_ld32(tbase + (uint32_t)(x * BN + c * 32), v[x]);
+            epi.chunk(nt * BN + c * 32, v);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (real) epi.tile_end(nt);
+        if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      epi.tile_end(nt);
-      if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
+      epi.finish();
+    } else {
+      // padding CTA of an MC_Y cluster: keeps the lock-step (its loads feed the peers), produces nothing
+      for (int it = 0; it < work.iters; ++it) {
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
+      }
     }
-    epi.finish();
   }
 
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if (CL > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into it / signal its barriers
+  else __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-template <int BN, int NX, int STAGES, class Epi>
+template <int BN, int NX, int STAGES, class Epi, int CL = 1, int MC = MC_NONE>
 int launch_stream_gemm(const GemmMaps& maps, const Sched& sched, const typename Epi::Params& ep, cudaStream_t stream,
                        const char* name) {
   using Cfg = GemmCfg<BN, NX, STAGES>;
-  auto kern = stream_gemm_kernel<BN, NX, STAGES, Epi>;
+  auto kern = stream_gemm_kernel<BN, NX, STAGES, Epi, CL, MC>;
   const int smem = Cfg::smem_bytes(Epi::kSmemBytes);
   static thread_local bool configured = false;  // per instantiation
   if (!configured) {
@@ -245,8 +343,25 @@ int launch_stream_gemm(const GemmMaps& maps, const Sched& sched, const typename 
     if (e != cudaSuccess) return fail(SCP_ERR_CUDA, "%s: cudaFuncSetAttribute(%d B): %s", name, smem, cudaGetErrorString(e));
     configured = true;
   }
-  if (sched.grid() <= 0) return SCP_OK;
-  kern<<<sched.grid(), kGemmThreads, smem, stream>>>(maps, sched, ep);
+  const int grid = sched_grid<CL, MC>(sched);
+  if (grid <= 0) return SCP_OK;
+  if (MC == MC_X && sched.n_groups % CL != 0) return fail(SCP_ERR_INVALID, "%s: n_groups %% cluster != 0", name);
+  if (CL > 1 && (sched.m_half != sched.m_tiles || sched.n_upper_off != 0))
+    return fail(SCP_ERR_INVALID, "%s: two-direction schedules do not support clusters", name);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps, sched, ep);
+  if (e != cudaSuccess) return fail(SCP_ERR_CUDA, "%s: launch failed: %s", name, cudaGetErrorString(e));
   SCP_CUDA_LAUNCH_CHECK(name);
   return SCP_OK;
 }

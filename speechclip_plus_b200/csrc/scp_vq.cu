@@ -844,10 +844,18 @@ struct VqFwdWs {
   size_t total;
   int n_chunks, n_groups;
 };
+// Clusters of 4 CTAs cannot use all 148 SMs (GPC granularity): at most 132 CTAs are co-resident.
+static int max_resident_ctas(int cl) { return cl == 4 ? 132 : kNumSMs; }
+// cluster size for a launch whose clustered axis has `extent` tiles
+static int pick_cluster(int extent) { return extent >= 4 ? 4 : (extent >= 2 ? 2 : 1); }
+
+static int vq_sweep1_cluster(int64_t Mp) { return pick_cluster((int)(Mp / tc::kTileM)); }
 static int vq_sweep1_groups(int64_t Mp, int64_t Vp) {
   const int m_tiles = (int)(Mp / tc::kTileM);
   const int n_tiles = (int)(Vp / kVqBN);
-  int g = kNumSMs / m_tiles;
+  const int cl = vq_sweep1_cluster(Mp);
+  const int m_ctas = cl * (int)ceil_div(m_tiles, cl);  // padded to whole clusters (MC_Y)
+  int g = max_resident_ctas(cl) / m_ctas;
   if (g < 1) g = 1;
   if (g > n_tiles) g = n_tiles;
   return g;
@@ -878,7 +886,7 @@ struct VqBwdWs {
   float* partials;
   float* uw;
   size_t total;
-  int n_groups, k_splits, bn_out;
+  int n_groups, k_splits, bn_out, cl3, cl_out;
 };
 static int vq_out_bn(int64_t D) { return D % 256 == 0 ? 256 : (D % 128 == 0 ? 128 : 64); }
 static VqBwdWs vq_bwd_ws(void* base, int64_t M, int64_t V, int64_t D) {
@@ -886,11 +894,15 @@ static VqBwdWs vq_bwd_ws(void* base, int64_t M, int64_t V, int64_t D) {
   VqBwdWs w{};
   const int m_tiles = (int)(Mp / tc::kTileM);
   const int n_tiles3 = (int)(Vp / 128);
-  w.n_groups = std::max(1, std::min(n_tiles3, kNumSMs / m_tiles));
+  // sweep 3 clusters along the column groups (X multicast): n_groups is a multiple of the cluster size
+  w.cl3 = pick_cluster(n_tiles3);
+  w.n_groups = std::max(w.cl3, std::min(n_tiles3, max_resident_ctas(w.cl3) / m_tiles) / w.cl3 * w.cl3);
   w.bn_out = vq_out_bn(D);
-  const int out_items = m_tiles * (int)(D / w.bn_out);
+  // gemm_out clusters along the row tiles (Y multicast)
+  w.cl_out = pick_cluster(m_tiles);
+  const int out_items = w.cl_out * (int)ceil_div(m_tiles, w.cl_out) * (int)(D / w.bn_out);
   const int k_chunks = (int)(Vp / tc::kChunkK);
-  w.k_splits = std::max(1, std::min(k_chunks, kNumSMs / out_items));
+  w.k_splits = std::max(1, std::min(k_chunks, max_resident_ctas(w.cl_out) / out_items));
   size_t off = 0;
   auto take = [&](size_t bytes) {
     void* p = base ? static_cast<uint8_t*>(base) + off : nullptr;
@@ -976,7 +988,8 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
     GemmMaps maps{};
     if ((rc = tc::make_tmap_f16(&maps.x[0], kw_hat, Mp, D, D, tc::kTileM))) return rc;
     maps.x[1] = maps.x[0];
-    if ((rc = tc::make_tmap_f16(&maps.y, table_hat, Vp, D, D, kVqBN))) return rc;
+    const int cl = vq_sweep1_cluster(Mp);
+    if ((rc = tc::make_tmap_f16(&maps.y, table_hat, Vp, D, D, kVqBN / cl))) return rc;
     Sched sc{};
     sc.m_tiles = (int)(Mp / tc::kTileM);
     sc.n_tiles = (int)(Vp / kVqBN);
@@ -993,7 +1006,10 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
     ep.n_groups = ws.n_groups;
     ep.V = (int)V;
     ep.mc = mc;
-    if ((rc = tc::launch_stream_gemm<kVqBN, 1, 4, Sweep1Epi>(maps, sc, ep, s, "vq_sweep1"))) return rc;
+    if (cl == 4) rc = tc::launch_stream_gemm<kVqBN, 1, 4, Sweep1Epi, 4, tc::MC_Y>(maps, sc, ep, s, "vq_sweep1");
+    else if (cl == 2) rc = tc::launch_stream_gemm<kVqBN, 1, 4, Sweep1Epi, 2, tc::MC_Y>(maps, sc, ep, s, "vq_sweep1");
+    else rc = tc::launch_stream_gemm<kVqBN, 1, 4, Sweep1Epi>(maps, sc, ep, s, "vq_sweep1");
+    if (rc) return rc;
   }
   // ---- exact arg-max, statistics, gather
 #define SCP_SELECT(NVV)                                                                                              \
@@ -1016,7 +1032,8 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
     GemmMaps maps{};
     if ((rc = tc::make_tmap_f16(&maps.x[0], table_hat, Vp, D, D, tc::kTileM))) return rc;
     maps.x[1] = maps.x[0];
-    if ((rc = tc::make_tmap_f16(&maps.y, kw_hat, Mp, D, D, 256))) return rc;
+    const int cl = pick_cluster((int)(Vp / tc::kTileM));
+    if ((rc = tc::make_tmap_f16(&maps.y, kw_hat, Mp, D, D, 256 / cl))) return rc;
     Sched sc{};
     sc.m_tiles = (int)(Vp / tc::kTileM);
     sc.n_tiles = (int)(Mp2 / 256);
@@ -1031,7 +1048,9 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
     ep.inv_m = 1.0f / (float)M;
     ep.V = (int)V;
     ep.mc = mc;
-    if ((rc = tc::launch_stream_gemm<256, 1, 4, Sweep2Epi>(maps, sc, ep, s, "vq_sweep2"))) return rc;
+    if (cl == 4) rc = tc::launch_stream_gemm<256, 1, 4, Sweep2Epi, 4, tc::MC_Y>(maps, sc, ep, s, "vq_sweep2");
+    else rc = tc::launch_stream_gemm<256, 1, 4, Sweep2Epi, 2, tc::MC_Y>(maps, sc, ep, s, "vq_sweep2");
+    if (rc) return rc;
   }
   vq_metrics_partial_kernel<<<kMetricBlocks, 256, 0, s>>>(code_hist, avg_probs, M, (int)V, ws.metric_part);
   SCP_CUDA_LAUNCH_CHECK("vq_metrics_partial");
@@ -1045,8 +1064,10 @@ extern "C" size_t scp_vq_bwd_workspace_bytes(int64_t M, int64_t V, int64_t D) {
 }
 
 template <int BN>
-static int launch_gemm_out(const GemmMaps& maps, const Sched& sc, const StoreEpi<2>::Params& ep, cudaStream_t s) {
+static int launch_gemm_out(const GemmMaps& maps, const Sched& sc, const StoreEpi<2>::Params& ep, int cl, cudaStream_t s) {
   constexpr int kStages = BN == 256 ? 3 : 4;
+  if (cl == 4) return tc::launch_stream_gemm<BN, 2, kStages, StoreEpi<2>, 4, tc::MC_Y>(maps, sc, ep, s, "vq_gemm_out");
+  if (cl == 2) return tc::launch_stream_gemm<BN, 2, kStages, StoreEpi<2>, 2, tc::MC_Y>(maps, sc, ep, s, "vq_gemm_out");
   return tc::launch_stream_gemm<BN, 2, kStages, StoreEpi<2>>(maps, sc, ep, s, "vq_gemm_out");
 }
 
@@ -1074,8 +1095,8 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
   // ---- sweep 3: P~, Q~ and row sums
   {
     GemmMaps maps{};
-    if ((rc = tc::make_tmap_f16(&maps.x[0], kw_hat, Mp, D, D, tc::kTileM))) return rc;
-    if ((rc = tc::make_tmap_f16(&maps.x[1], ws.g_hat, Mp, D, D, tc::kTileM))) return rc;
+    if ((rc = tc::make_tmap_f16(&maps.x[0], kw_hat, Mp, D, D, tc::kTileM / ws.cl3))) return rc;
+    if ((rc = tc::make_tmap_f16(&maps.x[1], ws.g_hat, Mp, D, D, tc::kTileM / ws.cl3))) return rc;
     if ((rc = tc::make_tmap_f16(&maps.y, table_hat, Vp, D, D, 128))) return rc;
     Sched sc{};
     sc.m_tiles = (int)(Mp / tc::kTileM);
@@ -1098,14 +1119,17 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
     ep.V = (int)V;
     ep.D = (int)D;
     ep.mc = mc;
-    if ((rc = tc::launch_stream_gemm<128, 2, 3, Sweep3Epi>(maps, sc, ep, s, "vq_sweep3"))) return rc;
+    if (ws.cl3 == 4) rc = tc::launch_stream_gemm<128, 2, 3, Sweep3Epi, 4, tc::MC_X>(maps, sc, ep, s, "vq_sweep3");
+    else if (ws.cl3 == 2) rc = tc::launch_stream_gemm<128, 2, 3, Sweep3Epi, 2, tc::MC_X>(maps, sc, ep, s, "vq_sweep3");
+    else rc = tc::launch_stream_gemm<128, 2, 3, Sweep3Epi>(maps, sc, ep, s, "vq_sweep3");
+    if (rc) return rc;
   }
   // ---- U = Q~ Ehat, W = P~ Ehat   (K = Vp, split-K partials)
   {
     GemmMaps maps{};
     if ((rc = tc::make_tmap_f16(&maps.x[0], ws.pq, Mp, Vp, Vp, tc::kTileM))) return rc;
     if ((rc = tc::make_tmap_f16(&maps.x[1], ws.pq + Mp * Vp, Mp, Vp, Vp, tc::kTileM))) return rc;
-    if ((rc = tc::make_tmap_f16(&maps.y, table_hat_t, D, Vp, Vp, ws.bn_out))) return rc;
+    if ((rc = tc::make_tmap_f16(&maps.y, table_hat_t, D, Vp, Vp, ws.bn_out / ws.cl_out))) return rc;
     Sched sc{};
     sc.m_tiles = (int)(Mp / tc::kTileM);
     sc.n_tiles = (int)(D / ws.bn_out);
@@ -1118,9 +1142,9 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
     ep.out = ws.uw;
     ep.rows = Mp;
     ep.ld = (int)D;
-    if (ws.bn_out == 256) rc = launch_gemm_out<256>(maps, sc, ep, s);
-    else if (ws.bn_out == 128) rc = launch_gemm_out<128>(maps, sc, ep, s);
-    else rc = launch_gemm_out<64>(maps, sc, ep, s);
+    if (ws.bn_out == 256) rc = launch_gemm_out<256>(maps, sc, ep, ws.cl_out, s);
+    else if (ws.bn_out == 128) rc = launch_gemm_out<128>(maps, sc, ep, ws.cl_out, s);
+    else rc = launch_gemm_out<64>(maps, sc, ep, ws.cl_out, s);
     if (rc) return rc;
   }
   if (g_tau && cudaMemsetAsync(g_tau, 0, 4, s) != cudaSuccess) return fail(SCP_ERR_CUDA, "memset g_tau");
