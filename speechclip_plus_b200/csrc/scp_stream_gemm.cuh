@@ -19,6 +19,12 @@
 //   MC_X: cluster along the Y-tile axis (same rows, different Y tiles)  -> X slices are multicast
 // A stage may be refilled only after ALL CTAs of the cluster consumed it: the MMA issuer's tcgen05.commit arrives on the
 // stage's `empty` barrier of every CTA (multicast commit), and each `empty` barrier counts CL arrivals.
+//   MC_PAIR: CTA pair (tcgen05 cta_group::2): the two CTAs own adjacent 128-row X tiles and walk the same Y tiles; ONE
+//            M=256 MMA issued by the even ("leader") CTA spans both SMs, each CTA stages only its own X rows and HALF of
+//            the Y tile, so a pipeline stage carries 1/3 fewer bytes per MMA cycle -- with ~1.5 us of TMA latency to
+//            cover and 227 KB of smem, bytes per MMA cycle is what decides whether the tensor pipe stays fed.
+//            Both CTAs' loads complete on the leader's `full` barrier; the leader's commits release the stage (and
+//            publish the accumulators) in both CTAs; both CTAs' epilogue warps arrive on the leader's `tmem_empty`.
 #pragma once
 #include "scp_tc.cuh"
 
@@ -35,7 +41,7 @@ constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kEpiBarrierId = 1;
 
-enum { MC_NONE = 0, MC_X = 1, MC_Y = 2 };
+enum { MC_NONE = 0, MC_X = 1, MC_Y = 2, MC_PAIR = 3 };
 
 struct EpiCtx {
   int row_in_tile;  // 0..127: TMEM lane == X row inside the CTA tile
@@ -60,7 +66,7 @@ struct Sched {
 
 template <int CL, int MC>
 __host__ __device__ inline int sched_grid(const Sched& s) {
-  if (MC == MC_Y) return CL * ((s.m_tiles + CL - 1) / CL) * s.n_groups * s.k_splits;
+  if (MC == MC_Y || MC == MC_PAIR) return CL * ((s.m_tiles + CL - 1) / CL) * s.n_groups * s.k_splits;
   return s.m_tiles * s.n_groups * s.k_splits;
 }
 
@@ -89,7 +95,7 @@ __device__ __forceinline__ WorkInfo decode_work(const Sched& s) {
   w.rank = CL > 1 ? (int)cluster_ctarank() : 0;
   int c = CL > 1 ? (int)blockIdx.x / CL : (int)blockIdx.x;
   int ng, nt0, nt1;
-  if (MC == MC_Y) {  // the cluster spans CL consecutive X tiles
+  if (MC == MC_Y || MC == MC_PAIR) {  // the cluster spans CL consecutive X tiles
     const int m_ct = (s.m_tiles + CL - 1) / CL;
     w.m_tile = (c % m_ct) * CL + w.rank;
     c /= m_ct;
@@ -134,9 +140,9 @@ __device__ __forceinline__ WorkInfo decode_work(const Sched& s) {
 constexpr int kGemmThreads = 64 + kEpiThreads;
 constexpr int kXTileBytes = kTileM * kChunkK * 2;  // 16 KB
 
-template <int BN, int NX, int STAGES>
+template <int BN, int NX, int STAGES, bool PAIR = false>
 struct GemmCfg {
-  static constexpr int kYTileBytes = BN * kChunkK * 2;
+  static constexpr int kYTileBytes = (PAIR ? BN / 2 : BN) * kChunkK * 2;  // a pair CTA stages half of the Y tile
   static constexpr int kStageBytes = NX * kXTileBytes + kYTileBytes;
   static constexpr int kAccCols = NX * BN;
   static constexpr int kAccStages = (int)kTmemCols / kAccCols >= 2 ? 2 : 1;
@@ -162,9 +168,11 @@ struct GemmCfg {
 template <int BN, int NX, int STAGES, class Epi, int CL, int MC>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, const typename Epi::Params ep) {
-  using Cfg = GemmCfg<BN, NX, STAGES>;
+  constexpr bool kPair = MC == MC_PAIR;
+  using Cfg = GemmCfg<BN, NX, STAGES, kPair>;
   static_assert(CL == 1 || CL == 2 || CL == 4, "cluster size");
-  static_assert((CL == 1) == (MC == MC_NONE), "clusters exist to multicast");
+  static_assert(!kPair || CL == 2, "a CTA pair is a cluster of two");
+  static_assert((CL == 1) == (MC == MC_NONE), "clusters exist to share operands");
   static_assert(MC != MC_X || (kTileM / CL) % 8 == 0, "X slice must be whole swizzle atoms");
   static_assert(MC != MC_Y || (BN / CL) % 8 == 0, "Y slice must be whole swizzle atoms");
   extern __shared__ uint8_t smem_raw[];
@@ -189,16 +197,17 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
         mbar_init(&full_bar[s], 1);
-        mbar_init(&empty_bar[s], CL);  // every CTA of the cluster must release the stage
+        mbar_init(&empty_bar[s], kPair ? 1 : CL);  // multicast: every CTA of the cluster must release the stage
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull_bar[a], 1);
-        mbar_init(&tempty_bar[a], kEpiWarps);  // one arrive per epilogue warp
+        mbar_init(&tempty_bar[a], kPair ? 2 * kEpiWarps : kEpiWarps);  // one arrive per epilogue warp (of both CTAs)
       }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, kTmemCols);
+    if (kPair) tmem_alloc_pair(tmem_slot, kTmemCols);
+    else tmem_alloc(tmem_slot, kTmemCols);
   }
   tc_fence_before();
   __syncwarp();  // barrier.cluster is .aligned: the single-lane branches above must have reconverged
@@ -218,6 +227,17 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
         for (int kc = work.kc0; kc < work.kc1; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * Cfg::kStageBytes;
+          if (kPair) {
+            // both CTAs' bytes are posted on the leader's barrier, which the leader arms for the two of them
+            if (work.rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            const uint32_t lead_bar = mapa_u32(&full_bar[stage], 0);
+#pragma unroll
+            for (int x = 0; x < NX; ++x)
+              tma_load_2d_pair(st + x * kXTileBytes, &maps.x[x], kc * kChunkK, work.x_row, lead_bar);
+            tma_load_2d_pair(st + NX * kXTileBytes, &maps.y, kc * kChunkK, nt * BN + work.rank * (BN / 2), lead_bar);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           if (MC == MC_X) {
             constexpr int kRows = kTileM / CL;
@@ -243,8 +263,8 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(BN);
+    if (lane == 0 && (!kPair || work.rank == 0)) {  // pair: only the leader CTA issues
+      constexpr uint32_t idesc = kPair ? make_idesc_f16_pair(BN) : make_idesc_f16(BN);
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       for (int it = 0; it < work.iters; ++it) {
@@ -260,15 +280,21 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
             const uint64_t a_desc = make_kmajor_sw128_desc(st + x * kXTileBytes);
             const uint32_t d = tmem_base + (uint32_t)(as * Cfg::kAccCols + x * BN);
 #pragma unroll
-            for (int k = 0; k < kChunkK / kUmmaK; ++k)
-              umma_f16(d, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kc > work.kc0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kChunkK / kUmmaK; ++k) {
+              const uint32_t acc = (kc > work.kc0 || k > 0) ? 1u : 0u;
+              if (kPair) umma_f16_pair(d, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, acc);
+              else umma_f16(d, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, acc);
+            }
           }
           // smem slot reusable once these MMAs retire -- signalled to every CTA that may refill it
-          if (CL > 1) umma_commit_mc(&empty_bar[stage], kClusterMask);
+          if (kPair) umma_commit_pair_mc(&empty_bar[stage], kClusterMask);
+          else if (CL > 1) umma_commit_mc(&empty_bar[stage], kClusterMask);
           else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);  // accumulator set complete
+        // accumulator set complete (pair: published to the epilogues of both CTAs)
+        if (kPair) umma_commit_pair_mc(&tfull_bar[as], kClusterMask);
+        else umma_commit(&tfull_bar[as]);
         if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
       }
     }
@@ -306,7 +332,10 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (lane == 0) {
+          if (kPair && work.rank != 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[as], 0));  // the leader's barrier
+          else mbar_arrive(&tempty_bar[as]);
+        }
         if (real) epi.tile_end(nt);
         if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
       }
@@ -318,7 +347,10 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (lane == 0) {
+          if (kPair && work.rank != 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[as], 0));
+          else mbar_arrive(&tempty_bar[as]);
+        }
         if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
       }
     }
@@ -328,13 +360,16 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
   __syncwarp();
   if (CL > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into it / signal its barriers
   else __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 1) {
+    if (kPair) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
 template <int BN, int NX, int STAGES, class Epi, int CL = 1, int MC = MC_NONE>
 int launch_stream_gemm(const GemmMaps& maps, const Sched& sched, const typename Epi::Params& ep, cudaStream_t stream,
                        const char* name) {
-  using Cfg = GemmCfg<BN, NX, STAGES>;
+  using Cfg = GemmCfg<BN, NX, STAGES, MC == MC_PAIR>;
   auto kern = stream_gemm_kernel<BN, NX, STAGES, Epi, CL, MC>;
   const int smem = Cfg::smem_bytes(Epi::kSmemBytes);
   static thread_local bool configured = false;  // per instantiation

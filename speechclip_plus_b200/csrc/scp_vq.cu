@@ -526,24 +526,20 @@ struct Sweep3Epi {
     const float* table_norm;  // (Vp,)
     const float* table_mean;  // [D] = norm_ref
     const float* tau;
+    __half* pq;               // (2*Mp, Vp): rows [0,Mp) = Q~, rows [Mp,2Mp) = P~
     float* partials;          // (Mp, 2*n_groups, 4): sum Q, sum P, sum Q c, sum P c
-    int64_t M, Mp;
+    int64_t M, Mp, Vp;
     int n_groups, V, D;
     MaskedCols mc;
   };
-  // staging for the TMA store of one 128 x 128 tile of Q~ and of P~: 4 boxes {64 cols, 128 rows} in the SWIZZLE_128B
-  // layout (row r at r*128 B, 16-byte units XOR-ed with r & 7).  pq (2*Mp, Vp): rows [0,Mp) = Q~, rows [Mp,2Mp) = P~.
-  static constexpr int kBoxBytes = tc::kTileM * 128;
-  static constexpr int kSmemBytes = 4 * kBoxBytes;
+  static constexpr int kSmemBytes = 0;
   const Params& p;
-  const tc::EpiCtx& ctx;
   int64_t row;
-  int slot, tile_col0, m_row0;
+  int slot;
   float k_tau, lse_l2, s0, inv_norm_ref;
   float sq, sp, sqc, spc;
-  __device__ __forceinline__ Sweep3Epi(const Params& p_, const WorkInfo& w, const tc::EpiCtx& ctx_)
-      : p(p_), ctx(ctx_), row((int64_t)w.m_tile * tc::kTileM + ctx_.row_in_tile), slot(w.n_group * 2 + ctx_.half),
-        tile_col0(0), m_row0(w.m_tile * tc::kTileM) {
+  __device__ __forceinline__ Sweep3Epi(const Params& p_, const WorkInfo& w, const tc::EpiCtx& ctx)
+      : p(p_), row((int64_t)w.m_tile * tc::kTileM + ctx.row_in_tile), slot(w.n_group * 2 + ctx.half) {
     k_tau = kLog2e / __ldg(p.tau);
     const bool valid = row < p.M;
     lse_l2 = valid ? p.row_stats[row * 4 + 1] * kLog2e : 1.0e30f;  // padding rows: P = 0
@@ -551,11 +547,8 @@ struct Sweep3Epi {
     inv_norm_ref = 1.0f / p.table_mean[p.D];
     sq = sp = sqc = spc = 0.f;
   }
-  __device__ __forceinline__ void tile_begin(int nt) {
-    tile_col0 = nt * 128;
-    if (ctx.tid == 0) tc::bulk_wait_read_all();  // the previous tile's stores have drained the staging buffer
-    tc::named_bar_sync(tc::kEpiBarrierId, tc::kEpiThreads);
-  }
+  __device__ __forceinline__ void tile_begin(int) {}
+  __device__ __forceinline__ void tile_end(int) {}
   __device__ __forceinline__ void chunk(int col0, float (&v)[2][32]) {
     float(&c)[32] = v[0];
     float(&t)[32] = v[1];
@@ -565,59 +558,43 @@ struct Sweep3Epi {
         if (col0 + i >= p.V || is_masked(p.mc, col0 + i)) c[i] = kNegBig;
     }
     const float4* n4 = reinterpret_cast<const float4*>(p.table_norm + col0);
-    uint32_t pk_q[16], pk_p[16];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 nv = __ldg(n4 + i);
-      const float nn[4] = {nv.x, nv.y, nv.z, nv.w};
-      float pv[4], qv[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float cc = c[4 * i + j];
-        const float pj = tc::fast_ex2(fmaf(cc, k_tau, -lse_l2));           // softmax_tau
-        const float tj = fmaf(t[4 * i + j] * nn[j], inv_norm_ref, -s0);    // (g . e_v)/(|g| norm_ref) - s0
-        const float qj = pj * tj;
-        sp += pj;
-        sq += qj;
-        const float cf = cc > -2.f ? cc : 0.f;
-        spc = fmaf(pj, cf, spc);
-        sqc = fmaf(qj, cf, sqc);
-        pv[j] = pj * kPScale;
-        qv[j] = qj * kPScale;
-      }
-      __half2 h;
-      h = __floats2half2_rn(qv[0], qv[1]); pk_q[2 * i] = *reinterpret_cast<uint32_t*>(&h);
-      h = __floats2half2_rn(qv[2], qv[3]); pk_q[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h);
-      h = __floats2half2_rn(pv[0], pv[1]); pk_p[2 * i] = *reinterpret_cast<uint32_t*>(&h);
-      h = __floats2half2_rn(pv[2], pv[3]); pk_p[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h);
-    }
-    // this chunk = 32 columns = four 16-byte units of this thread's row inside box (chunk / 2)
-    const int cin = (col0 - tile_col0) >> 5;  // chunk index inside the tile: 0..3
-    const int box = cin >> 1;
-    const int r = ctx.row_in_tile;
-    uint8_t* qbox = ctx.smem + box * kBoxBytes + r * 128;
-    uint8_t* pbox = ctx.smem + (2 + box) * kBoxBytes + r * 128;
+    // every thread owns 32 consecutive columns of its row: 64 contiguous bytes per matrix (two full 32-byte sectors)
+    uint4* dq = reinterpret_cast<uint4*>(p.pq + row * p.Vp + col0);
+    uint4* dp = reinterpret_cast<uint4*>(p.pq + (p.Mp + row) * p.Vp + col0);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int unit = ((cin & 1) * 4 + i) ^ (r & 7);
-      *reinterpret_cast<uint4*>(qbox + unit * 16) = make_uint4(pk_q[4 * i], pk_q[4 * i + 1], pk_q[4 * i + 2], pk_q[4 * i + 3]);
-      *reinterpret_cast<uint4*>(pbox + unit * 16) = make_uint4(pk_p[4 * i], pk_p[4 * i + 1], pk_p[4 * i + 2], pk_p[4 * i + 3]);
-    }
-  }
-  __device__ __forceinline__ void tile_end(int) {
-    tc::fence_proxy_async_smem();  // st.shared above must be visible to the TMA (async proxy)
-    tc::named_bar_sync(tc::kEpiBarrierId, tc::kEpiThreads);
-    if (ctx.tid == 0) {
+      uint32_t pk_q[4], pk_p[4];
 #pragma unroll
-      for (int box = 0; box < 2; ++box) {
-        tc::tma_store_2d(&ctx.maps->o, ctx.smem + box * kBoxBytes, tile_col0 + 64 * box, m_row0);
-        tc::tma_store_2d(&ctx.maps->o, ctx.smem + (2 + box) * kBoxBytes, tile_col0 + 64 * box, (int)p.Mp + m_row0);
+      for (int h = 0; h < 2; ++h) {
+        const float4 nv = __ldg(n4 + 2 * i + h);
+        const float nn[4] = {nv.x, nv.y, nv.z, nv.w};
+        float pv[4], qv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int e = 8 * i + 4 * h + j;
+          const float cc = c[e];
+          const float pj = tc::fast_ex2(fmaf(cc, k_tau, -lse_l2));        // softmax_tau
+          const float tj = fmaf(t[e] * nn[j], inv_norm_ref, -s0);          // (g . e_v)/(|g| norm_ref) - s0
+          const float qj = pj * tj;
+          sp += pj;
+          sq += qj;
+          const float cf = cc > -2.f ? cc : 0.f;
+          spc = fmaf(pj, cf, spc);
+          sqc = fmaf(qj, cf, sqc);
+          pv[j] = pj * kPScale;
+          qv[j] = qj * kPScale;
+        }
+        __half2 hh;
+        hh = __floats2half2_rn(qv[0], qv[1]); pk_q[2 * h] = *reinterpret_cast<uint32_t*>(&hh);
+        hh = __floats2half2_rn(qv[2], qv[3]); pk_q[2 * h + 1] = *reinterpret_cast<uint32_t*>(&hh);
+        hh = __floats2half2_rn(pv[0], pv[1]); pk_p[2 * h] = *reinterpret_cast<uint32_t*>(&hh);
+        hh = __floats2half2_rn(pv[2], pv[3]); pk_p[2 * h + 1] = *reinterpret_cast<uint32_t*>(&hh);
       }
-      tc::bulk_commit_group();
+      dq[i] = make_uint4(pk_q[0], pk_q[1], pk_q[2], pk_q[3]);
+      dp[i] = make_uint4(pk_p[0], pk_p[1], pk_p[2], pk_p[3]);
     }
   }
   __device__ __forceinline__ void finish() {
-    if (ctx.tid == 0) tc::bulk_wait_all();
     *reinterpret_cast<float4*>(p.partials + (row * (2 * p.n_groups) + slot) * 4) = make_float4(sq, sp, sqc, spc);
   }
 };
@@ -844,18 +821,14 @@ struct VqFwdWs {
   size_t total;
   int n_chunks, n_groups;
 };
-// Clusters of 4 CTAs cannot use all 148 SMs (GPC granularity): at most 132 CTAs are co-resident.
-static int max_resident_ctas(int cl) { return cl == 4 ? 132 : kNumSMs; }
-// cluster size for a launch whose clustered axis has `extent` tiles
-static int pick_cluster(int extent) { return extent >= 4 ? 4 : (extent >= 2 ? 2 : 1); }
+// CTA pairs (cta_group::2) need at least two row tiles; single-tile problems run the one-CTA kernel.
+static bool vq_use_pair(int m_tiles) { return m_tiles >= 2; }
+static int vq_m_ctas(int m_tiles) { return vq_use_pair(m_tiles) ? 2 * (int)ceil_div(m_tiles, 2) : m_tiles; }
 
-static int vq_sweep1_cluster(int64_t Mp) { return pick_cluster((int)(Mp / tc::kTileM)); }
 static int vq_sweep1_groups(int64_t Mp, int64_t Vp) {
   const int m_tiles = (int)(Mp / tc::kTileM);
   const int n_tiles = (int)(Vp / kVqBN);
-  const int cl = vq_sweep1_cluster(Mp);
-  const int m_ctas = cl * (int)ceil_div(m_tiles, cl);  // padded to whole clusters (MC_Y)
-  int g = max_resident_ctas(cl) / m_ctas;
+  int g = kNumSMs / vq_m_ctas(m_tiles);
   if (g < 1) g = 1;
   if (g > n_tiles) g = n_tiles;
   return g;
@@ -886,7 +859,7 @@ struct VqBwdWs {
   float* partials;
   float* uw;
   size_t total;
-  int n_groups, k_splits, bn_out, cl3, cl_out;
+  int n_groups, k_splits, bn_out;
 };
 static int vq_out_bn(int64_t D) { return D % 256 == 0 ? 256 : (D % 128 == 0 ? 128 : 64); }
 static VqBwdWs vq_bwd_ws(void* base, int64_t M, int64_t V, int64_t D) {
@@ -894,15 +867,11 @@ static VqBwdWs vq_bwd_ws(void* base, int64_t M, int64_t V, int64_t D) {
   VqBwdWs w{};
   const int m_tiles = (int)(Mp / tc::kTileM);
   const int n_tiles3 = (int)(Vp / 128);
-  // sweep 3 clusters along the column groups (X multicast): n_groups is a multiple of the cluster size
-  w.cl3 = pick_cluster(n_tiles3);
-  w.n_groups = std::max(w.cl3, std::min(n_tiles3, max_resident_ctas(w.cl3) / m_tiles) / w.cl3 * w.cl3);
+  w.n_groups = std::max(1, std::min(n_tiles3, kNumSMs / vq_m_ctas(m_tiles)));
   w.bn_out = vq_out_bn(D);
-  // gemm_out clusters along the row tiles (Y multicast)
-  w.cl_out = pick_cluster(m_tiles);
-  const int out_items = w.cl_out * (int)ceil_div(m_tiles, w.cl_out) * (int)(D / w.bn_out);
+  const int out_items = vq_m_ctas(m_tiles) * (int)(D / w.bn_out);
   const int k_chunks = (int)(Vp / tc::kChunkK);
-  w.k_splits = std::max(1, std::min(k_chunks, max_resident_ctas(w.cl_out) / out_items));
+  w.k_splits = std::max(1, std::min(k_chunks, kNumSMs / out_items));
   size_t off = 0;
   auto take = [&](size_t bytes) {
     void* p = base ? static_cast<uint8_t*>(base) + off : nullptr;
@@ -988,8 +957,8 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
     GemmMaps maps{};
     if ((rc = tc::make_tmap_f16(&maps.x[0], kw_hat, Mp, D, D, tc::kTileM))) return rc;
     maps.x[1] = maps.x[0];
-    const int cl = vq_sweep1_cluster(Mp);
-    if ((rc = tc::make_tmap_f16(&maps.y, table_hat, Vp, D, D, kVqBN / cl))) return rc;
+    const bool pair = vq_use_pair((int)(Mp / tc::kTileM));
+    if ((rc = tc::make_tmap_f16(&maps.y, table_hat, Vp, D, D, pair ? kVqBN / 2 : kVqBN))) return rc;
     Sched sc{};
     sc.m_tiles = (int)(Mp / tc::kTileM);
     sc.n_tiles = (int)(Vp / kVqBN);
@@ -1006,8 +975,7 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
     ep.n_groups = ws.n_groups;
     ep.V = (int)V;
     ep.mc = mc;
-    if (cl == 4) rc = tc::launch_stream_gemm<kVqBN, 1, 4, Sweep1Epi, 4, tc::MC_Y>(maps, sc, ep, s, "vq_sweep1");
-    else if (cl == 2) rc = tc::launch_stream_gemm<kVqBN, 1, 4, Sweep1Epi, 2, tc::MC_Y>(maps, sc, ep, s, "vq_sweep1");
+    if (pair) rc = tc::launch_stream_gemm<kVqBN, 1, 6, Sweep1Epi, 2, tc::MC_PAIR>(maps, sc, ep, s, "vq_sweep1");
     else rc = tc::launch_stream_gemm<kVqBN, 1, 4, Sweep1Epi>(maps, sc, ep, s, "vq_sweep1");
     if (rc) return rc;
   }
@@ -1032,8 +1000,7 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
     GemmMaps maps{};
     if ((rc = tc::make_tmap_f16(&maps.x[0], table_hat, Vp, D, D, tc::kTileM))) return rc;
     maps.x[1] = maps.x[0];
-    const int cl = pick_cluster((int)(Vp / tc::kTileM));
-    if ((rc = tc::make_tmap_f16(&maps.y, kw_hat, Mp, D, D, 256 / cl))) return rc;
+    if ((rc = tc::make_tmap_f16(&maps.y, kw_hat, Mp, D, D, 128))) return rc;  // pair: half of the 256-row Y tile
     Sched sc{};
     sc.m_tiles = (int)(Vp / tc::kTileM);
     sc.n_tiles = (int)(Mp2 / 256);
@@ -1048,9 +1015,7 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
     ep.inv_m = 1.0f / (float)M;
     ep.V = (int)V;
     ep.mc = mc;
-    if (cl == 4) rc = tc::launch_stream_gemm<256, 1, 4, Sweep2Epi, 4, tc::MC_Y>(maps, sc, ep, s, "vq_sweep2");
-    else rc = tc::launch_stream_gemm<256, 1, 4, Sweep2Epi, 2, tc::MC_Y>(maps, sc, ep, s, "vq_sweep2");
-    if (rc) return rc;
+    if ((rc = tc::launch_stream_gemm<256, 1, 6, Sweep2Epi, 2, tc::MC_PAIR>(maps, sc, ep, s, "vq_sweep2"))) return rc;
   }
   vq_metrics_partial_kernel<<<kMetricBlocks, 256, 0, s>>>(code_hist, avg_probs, M, (int)V, ws.metric_part);
   SCP_CUDA_LAUNCH_CHECK("vq_metrics_partial");
@@ -1064,10 +1029,10 @@ extern "C" size_t scp_vq_bwd_workspace_bytes(int64_t M, int64_t V, int64_t D) {
 }
 
 template <int BN>
-static int launch_gemm_out(const GemmMaps& maps, const Sched& sc, const StoreEpi<2>::Params& ep, int cl, cudaStream_t s) {
-  constexpr int kStages = BN == 256 ? 3 : 4;
-  if (cl == 4) return tc::launch_stream_gemm<BN, 2, kStages, StoreEpi<2>, 4, tc::MC_Y>(maps, sc, ep, s, "vq_gemm_out");
-  if (cl == 2) return tc::launch_stream_gemm<BN, 2, kStages, StoreEpi<2>, 2, tc::MC_Y>(maps, sc, ep, s, "vq_gemm_out");
+static int launch_gemm_out(const GemmMaps& maps, const Sched& sc, const StoreEpi<2>::Params& ep, bool pair, cudaStream_t s) {
+  constexpr int kStages = BN == 256 ? 3 : 4;       // one CTA: 32 KB of X + BN*128 B of Y per stage
+  constexpr int kPairStages = BN == 256 ? 4 : 5;   // pair: 32 KB of X + BN*64 B of Y per stage
+  if (pair) return tc::launch_stream_gemm<BN, 2, kPairStages, StoreEpi<2>, 2, tc::MC_PAIR>(maps, sc, ep, s, "vq_gemm_out");
   return tc::launch_stream_gemm<BN, 2, kStages, StoreEpi<2>>(maps, sc, ep, s, "vq_gemm_out");
 }
 
@@ -1095,9 +1060,10 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
   // ---- sweep 3: P~, Q~ and row sums
   {
     GemmMaps maps{};
-    if ((rc = tc::make_tmap_f16(&maps.x[0], kw_hat, Mp, D, D, tc::kTileM / ws.cl3))) return rc;
-    if ((rc = tc::make_tmap_f16(&maps.x[1], ws.g_hat, Mp, D, D, tc::kTileM / ws.cl3))) return rc;
-    if ((rc = tc::make_tmap_f16(&maps.y, table_hat, Vp, D, D, 128))) return rc;
+    const bool pair = vq_use_pair((int)(Mp / tc::kTileM));
+    if ((rc = tc::make_tmap_f16(&maps.x[0], kw_hat, Mp, D, D, tc::kTileM))) return rc;
+    if ((rc = tc::make_tmap_f16(&maps.x[1], ws.g_hat, Mp, D, D, tc::kTileM))) return rc;
+    if ((rc = tc::make_tmap_f16(&maps.y, table_hat, Vp, D, D, pair ? 64 : 128))) return rc;
     Sched sc{};
     sc.m_tiles = (int)(Mp / tc::kTileM);
     sc.n_tiles = (int)(Vp / 128);
@@ -1112,16 +1078,15 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
     ep.table_norm = table_norm;
     ep.table_mean = table_mean;
     ep.tau = tau;
+    ep.pq = ws.pq;
     ep.partials = ws.partials;
-    ep.M = M; ep.Mp = Mp;
-    if ((rc = tc::make_tmap_f16(&maps.o, ws.pq, 2 * Mp, Vp, Vp, tc::kTileM))) return rc;
+    ep.M = M; ep.Mp = Mp; ep.Vp = Vp;
     ep.n_groups = ws.n_groups;
     ep.V = (int)V;
     ep.D = (int)D;
     ep.mc = mc;
-    if (ws.cl3 == 4) rc = tc::launch_stream_gemm<128, 2, 3, Sweep3Epi, 4, tc::MC_X>(maps, sc, ep, s, "vq_sweep3");
-    else if (ws.cl3 == 2) rc = tc::launch_stream_gemm<128, 2, 3, Sweep3Epi, 2, tc::MC_X>(maps, sc, ep, s, "vq_sweep3");
-    else rc = tc::launch_stream_gemm<128, 2, 3, Sweep3Epi>(maps, sc, ep, s, "vq_sweep3");
+    if (pair) rc = tc::launch_stream_gemm<128, 2, 5, Sweep3Epi, 2, tc::MC_PAIR>(maps, sc, ep, s, "vq_sweep3");
+    else rc = tc::launch_stream_gemm<128, 2, 4, Sweep3Epi>(maps, sc, ep, s, "vq_sweep3");
     if (rc) return rc;
   }
   // ---- U = Q~ Ehat, W = P~ Ehat   (K = Vp, split-K partials)
@@ -1129,7 +1094,8 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
     GemmMaps maps{};
     if ((rc = tc::make_tmap_f16(&maps.x[0], ws.pq, Mp, Vp, Vp, tc::kTileM))) return rc;
     if ((rc = tc::make_tmap_f16(&maps.x[1], ws.pq + Mp * Vp, Mp, Vp, Vp, tc::kTileM))) return rc;
-    if ((rc = tc::make_tmap_f16(&maps.y, table_hat_t, D, Vp, Vp, ws.bn_out / ws.cl_out))) return rc;
+    const bool pair = vq_use_pair((int)(Mp / tc::kTileM));
+    if ((rc = tc::make_tmap_f16(&maps.y, table_hat_t, D, Vp, Vp, pair ? ws.bn_out / 2 : ws.bn_out))) return rc;
     Sched sc{};
     sc.m_tiles = (int)(Mp / tc::kTileM);
     sc.n_tiles = (int)(D / ws.bn_out);
@@ -1142,9 +1108,9 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
     ep.out = ws.uw;
     ep.rows = Mp;
     ep.ld = (int)D;
-    if (ws.bn_out == 256) rc = launch_gemm_out<256>(maps, sc, ep, ws.cl_out, s);
-    else if (ws.bn_out == 128) rc = launch_gemm_out<128>(maps, sc, ep, ws.cl_out, s);
-    else rc = launch_gemm_out<64>(maps, sc, ep, ws.cl_out, s);
+    if (ws.bn_out == 256) rc = launch_gemm_out<256>(maps, sc, ep, pair, s);
+    else if (ws.bn_out == 128) rc = launch_gemm_out<128>(maps, sc, ep, pair, s);
+    else rc = launch_gemm_out<64>(maps, sc, ep, pair, s);
     if (rc) return rc;
   }
   if (g_tau && cudaMemsetAsync(g_tau, 0, 4, s) != cudaSuccess) return fail(SCP_ERR_CUDA, "memset g_tau");
