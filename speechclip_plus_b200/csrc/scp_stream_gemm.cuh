@@ -26,6 +26,8 @@
 //            Both CTAs' loads complete on the leader's `full` barrier; the leader's commits release the stage (and
 //            publish the accumulators) in both CTAs; both CTAs' epilogue warps arrive on the leader's `tmem_empty`.
 #pragma once
+#include <cstdlib>
+
 #include "scp_tc.cuh"
 
 namespace scp {
@@ -62,6 +64,7 @@ struct Sched {
   int m_half;           // == m_tiles when unused
   int n_upper_off;      // == 0 when unused
   int x_upper_row_off;  // extra X row offset of the upper-half tiles (== 0 when unused)
+  int debug;            // ablation switches for bring-up (env SCP_DEBUG_ABLATE): 1 = skip epilogue maths, 2 = skip MMAs
 };
 
 template <int CL, int MC>
@@ -281,6 +284,7 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
             const uint32_t d = tmem_base + (uint32_t)(as * Cfg::kAccCols + x * BN);
 #pragma unroll
             for (int k = 0; k < kChunkK / kUmmaK; ++k) {
+              if (sched.debug & 2) continue;
               const uint32_t acc = (kc > work.kc0 || k > 0) ? 1u : 0u;
               if (kPair) umma_f16_pair(d, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, acc);
               else umma_f16(d, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, acc);
@@ -320,14 +324,32 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
         if (real) {
           epi.tile_begin(nt);
           const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * Cfg::kAccCols);
-#pragma unroll 1
-          for (int cc = 0; cc < kChunksPerHalf; ++cc) {
-            const int c = ctx.half * kChunksPerHalf + cc;
-            float v[NX][32];
+          if constexpr (NX == 1) {
+            // software-pipelined: the TMEM load of chunk cc+1 is in flight while chunk cc is consumed
+            uint32_t raw[2][32];
             __syncwarp();
+            tmem_ld32_issue(tbase + (uint32_t)(ctx.half * kChunksPerHalf * 32), raw[0]);
 #pragma unroll
-            for (int x = 0; x < NX; ++x) tmem_ld32(tbase + (uint32_t)(x * BN + c * 32), v[x]);
-            epi.chunk(nt * BN + c * 32, v);
+            for (int cc = 0; cc < kChunksPerHalf; ++cc) {
+              const int c = ctx.half * kChunksPerHalf + cc;
+              tmem_ld32_wait(raw[cc & 1]);
+              if (cc + 1 < kChunksPerHalf) tmem_ld32_issue(tbase + (uint32_t)((c + 1) * 32), raw[(cc + 1) & 1]);
+              float v[1][32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[0][i] = __uint_as_float(raw[cc & 1][i]);
+              if (!(sched.debug & 1)) epi.chunk(nt * BN + c * 32, v);
+              __syncwarp();
+            }
+          } else {
+#pragma unroll 1
+            for (int cc = 0; cc < kChunksPerHalf; ++cc) {
+              const int c = ctx.half * kChunksPerHalf + cc;
+              float v[NX][32];
+              __syncwarp();
+#pragma unroll
+              for (int x = 0; x < NX; ++x) tmem_ld32(tbase + (uint32_t)(x * BN + c * 32), v[x]);
+              if (!(sched.debug & 1)) epi.chunk(nt * BN + c * 32, v);
+            }
           }
         }
         tc_fence_before();
@@ -380,6 +402,11 @@ int launch_stream_gemm(const GemmMaps& maps, const Sched& sched, const typename 
   }
   const int grid = sched_grid<CL, MC>(sched);
   if (grid <= 0) return SCP_OK;
+  Sched sched_dbg = sched;
+  {
+    static const int ablate = [] { const char* e = getenv("SCP_DEBUG_ABLATE"); return e ? atoi(e) : 0; }();
+    sched_dbg.debug = ablate;
+  }
   if (MC == MC_X && sched.n_groups % CL != 0) return fail(SCP_ERR_INVALID, "%s: n_groups %% cluster != 0", name);
   if (CL > 1 && (sched.m_half != sched.m_tiles || sched.n_upper_off != 0))
     return fail(SCP_ERR_INVALID, "%s: two-direction schedules do not support clusters", name);
@@ -395,7 +422,7 @@ int launch_stream_gemm(const GemmMaps& maps, const Sched& sched, const typename 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CL > 1 ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps, sched, ep);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps, sched_dbg, ep);
   if (e != cudaSuccess) return fail(SCP_ERR_CUDA, "%s: launch failed: %s", name, cudaGetErrorString(e));
   SCP_CUDA_LAUNCH_CHECK(name);
   return SCP_OK;

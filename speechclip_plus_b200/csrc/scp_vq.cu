@@ -140,6 +140,19 @@ __global__ void vq_prep_kw_kernel(const float* __restrict__ kw, int64_t M, int64
 // =====================================================================================================================
 // sweep 1: per-row statistics of S = khat * Ehat^T
 // =====================================================================================================================
+// x^N by repeated squaring, N known at compile time (no branches in the epilogue's inner loop)
+template <int N>
+__device__ __forceinline__ float ipow(float x) {
+  if constexpr (N == 1) {
+    return x;
+  } else if constexpr (N % 2 == 0) {
+    const float t = ipow<N / 2>(x);
+    return t * t;
+  } else {
+    return x * ipow<N - 1>(x);
+  }
+}
+
 struct Sweep1Epi {
   struct Params {
     float* chunk_max;   // (Mp, n_chunks)
@@ -154,16 +167,32 @@ struct Sweep1Epi {
   const Params& p;
   int64_t row;
   int slot;
+  int n_pow;    // 1/tau when it is one of the integers {2,4,5,8,10,16,20} (every shipped recipe: tau = 0.1 -> 10), else 0
   float k_tau;  // log2(e)/tau
   float sum_e1, sum_ce1, run_max, sum_et;
 
   __device__ __forceinline__ Sweep1Epi(const Params& p_, const WorkInfo& w, const tc::EpiCtx& ctx)
       : p(p_), row((int64_t)w.m_tile * tc::kTileM + ctx.row_in_tile), slot(w.n_group * 2 + ctx.half) {
-    k_tau = kLog2e / __ldg(p.tau);
+    const float inv_tau = 1.0f / __ldg(p.tau);
+    k_tau = kLog2e * inv_tau;
+    const float n = rintf(inv_tau);
+    const int ni = (int)n;
+    const bool supported = ni == 2 || ni == 4 || ni == 5 || ni == 8 || ni == 10 || ni == 16 || ni == 20;
+    n_pow = (supported && fabsf(inv_tau - n) <= 1e-5f * n) ? ni : 0;
     sum_e1 = 0.f; sum_ce1 = 0.f; run_max = kNegBig; sum_et = 0.f;
   }
   __device__ __forceinline__ void tile_begin(int) {}
   __device__ __forceinline__ void tile_end(int) {}
+  template <int N>
+  __device__ __forceinline__ void pow_chunk(const float (&c)[32]) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float e1 = tc::fast_ex2(c[i] * kLog2e);
+      sum_e1 += e1;
+      sum_ce1 = fmaf(c[i], e1, sum_ce1);
+      sum_et += ipow<N>(e1);
+    }
+  }
   __device__ __forceinline__ void chunk(int col0, float (&v)[1][32]) {
     float(&c)[32] = v[0];
     if (col0 + 32 > p.V || chunk_has_mask(p.mc, col0)) {
@@ -176,6 +205,22 @@ struct Sweep1Epi {
     for (int i = 1; i < 32; ++i) cmax = fmaxf(cmax, c[i]);
     p.chunk_max[row * p.n_chunks + (col0 >> 5)] = cmax;
     if (cmax <= kNegBig) return;  // fully masked / padding chunk: contributes nothing (and has no finite maximum)
+    if (n_pow) {
+      // |c| <= 1 and 1/tau = n <= 20: e^{c/tau} = (e^c)^n cannot overflow, so no running maximum is needed and the
+      // second exponential becomes a few multiplies (repeated squaring) -- ONE SFU op per logit instead of two
+      // (the SFU does only 4 lanes/clk per sub-partition and bounds this epilogue otherwise)
+      run_max = 0.f;  // the partial sum is relative to a shift of 0
+      switch (n_pow) {
+        case 2: pow_chunk<2>(c); break;
+        case 4: pow_chunk<4>(c); break;
+        case 5: pow_chunk<5>(c); break;
+        case 8: pow_chunk<8>(c); break;
+        case 10: pow_chunk<10>(c); break;
+        case 16: pow_chunk<16>(c); break;
+        default: pow_chunk<20>(c); break;
+      }
+      return;
+    }
     if (cmax > run_max) {  // rescale the temperature-tau sum to the new running maximum
       sum_et *= tc::fast_ex2((run_max - cmax) * k_tau);
       run_max = cmax;
@@ -532,14 +577,22 @@ struct Sweep3Epi {
     int n_groups, V, D;
     MaskedCols mc;
   };
-  static constexpr int kSmemBytes = 0;
+  // Each warp owns a private 4 KB staging area (32 rows x 32 columns of Q~ and of P~): the accumulator layout gives
+  // every lane one ROW, but a store instruction in which 32 lanes touch 32 different rows costs 32 LSU transactions;
+  // transposing through shared memory turns it into 64-byte row segments (8 rows per instruction, full sectors).
+  static constexpr int kWarpStage = 2 * 32 * 64;
+  static constexpr int kSmemBytes = tc::kEpiWarps * kWarpStage;
   const Params& p;
-  int64_t row;
-  int slot;
+  int64_t row, row0;
+  int slot, lane;
+  uint8_t* stage;
   float k_tau, lse_l2, s0, inv_norm_ref;
   float sq, sp, sqc, spc;
   __device__ __forceinline__ Sweep3Epi(const Params& p_, const WorkInfo& w, const tc::EpiCtx& ctx)
       : p(p_), row((int64_t)w.m_tile * tc::kTileM + ctx.row_in_tile), slot(w.n_group * 2 + ctx.half) {
+    lane = ctx.tid & 31;
+    row0 = row - lane;
+    stage = ctx.smem + (ctx.tid >> 5) * kWarpStage;
     k_tau = kLog2e / __ldg(p.tau);
     const bool valid = row < p.M;
     lse_l2 = valid ? p.row_stats[row * 4 + 1] * kLog2e : 1.0e30f;  // padding rows: P = 0
@@ -558,9 +611,11 @@ struct Sweep3Epi {
         if (col0 + i >= p.V || is_masked(p.mc, col0 + i)) c[i] = kNegBig;
     }
     const float4* n4 = reinterpret_cast<const float4*>(p.table_norm + col0);
-    // every thread owns 32 consecutive columns of its row: 64 contiguous bytes per matrix (two full 32-byte sectors)
-    uint4* dq = reinterpret_cast<uint4*>(p.pq + row * p.Vp + col0);
-    uint4* dp = reinterpret_cast<uint4*>(p.pq + (p.Mp + row) * p.Vp + col0);
+    // staging layout: row r at r*64 B, its four 16-byte units XOR-swizzled with (r >> 1) & 3 (conflict-free both ways)
+    uint8_t* qs = stage + lane * 64;
+    uint8_t* ps = stage + 32 * 64 + lane * 64;
+    const int sw = (lane >> 1) & 3;
+    __syncwarp();  // the previous chunk's read-out of the staging area is complete
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       uint32_t pk_q[4], pk_p[4];
@@ -590,8 +645,21 @@ struct Sweep3Epi {
         hh = __floats2half2_rn(pv[0], pv[1]); pk_p[2 * h] = *reinterpret_cast<uint32_t*>(&hh);
         hh = __floats2half2_rn(pv[2], pv[3]); pk_p[2 * h + 1] = *reinterpret_cast<uint32_t*>(&hh);
       }
-      dq[i] = make_uint4(pk_q[0], pk_q[1], pk_q[2], pk_q[3]);
-      dp[i] = make_uint4(pk_p[0], pk_p[1], pk_p[2], pk_p[3]);
+      *reinterpret_cast<uint4*>(qs + ((i ^ sw) << 4)) = make_uint4(pk_q[0], pk_q[1], pk_q[2], pk_q[3]);
+      *reinterpret_cast<uint4*>(ps + ((i ^ sw) << 4)) = make_uint4(pk_p[0], pk_p[1], pk_p[2], pk_p[3]);
+    }
+    __syncwarp();
+    // read-out: instruction k covers rows 8k..8k+7, four lanes per row -> 64-byte contiguous global segments
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = 8 * k + (lane >> 2);
+      const int u = lane & 3;
+      const int off = r * 64 + ((u ^ ((r >> 1) & 3)) << 4);
+      const uint4 q4 = *reinterpret_cast<const uint4*>(stage + off);
+      const uint4 p4 = *reinterpret_cast<const uint4*>(stage + 32 * 64 + off);
+      const int64_t grow = row0 + r;
+      *reinterpret_cast<uint4*>(p.pq + grow * p.Vp + col0 + u * 8) = q4;
+      *reinterpret_cast<uint4*>(p.pq + (p.Mp + grow) * p.Vp + col0 + u * 8) = p4;
     }
   }
   __device__ __forceinline__ void finish() {
@@ -1085,8 +1153,8 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
     ep.V = (int)V;
     ep.D = (int)D;
     ep.mc = mc;
-    if (pair) rc = tc::launch_stream_gemm<128, 2, 5, Sweep3Epi, 2, tc::MC_PAIR>(maps, sc, ep, s, "vq_sweep3");
-    else rc = tc::launch_stream_gemm<128, 2, 4, Sweep3Epi>(maps, sc, ep, s, "vq_sweep3");
+    if (pair) rc = tc::launch_stream_gemm<128, 2, 4, Sweep3Epi, 2, tc::MC_PAIR>(maps, sc, ep, s, "vq_sweep3");
+    else rc = tc::launch_stream_gemm<128, 2, 3, Sweep3Epi>(maps, sc, ep, s, "vq_sweep3");
     if (rc) return rc;
   }
   // ---- U = Q~ Ehat, W = P~ Ehat   (K = Vp, split-K partials)
