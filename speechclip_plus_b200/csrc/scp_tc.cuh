@@ -225,7 +225,9 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+  // default semantics (release at CTA scope): the TMEM reads were already completed by tcgen05.wait::ld, nothing has
+  // to be published cluster-wide, and a .release.cluster arrive costs a full MEMBAR per tile
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {  // whole warp, both CTAs
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
