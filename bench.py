@@ -364,6 +364,11 @@ def kernel_breakdown(hp: "HotPath", iters: int = 10):
     return out
 
 
+def _trace(msg):
+    if os.environ.get("SCP_BENCH_TRACE"):
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -384,18 +389,25 @@ def run_gpu_arm(args):
     B = hp.B
 
     # ---- parity guard: the first step's loss must match the oracle evaluated on the same features (rank 0, N = 1 GPU rows)
+    _trace("state built")
     for _ in range(args.warmup):
         hp.step()
+    torch.cuda.synchronize()
+    _trace("eager warm-up done")
     if not args.no_graph:
         hp.capture()
+        _trace("graph captured")
         hp.run_step = hp.step_graph
         for _ in range(2):
             hp.run_step()
+        torch.cuda.synchronize()
+        _trace("graph replays ok")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = _lib.num_launches()
     ms = time_region(torch, dist, world, hp.run_step, args.steps)
+    _trace("timed region done")
     launches = (_lib.num_launches() - launches0)
     if hp.graph is not None:
         launches = hp.launches_per_step * args.steps  # replays do not pass through the C ABI again
@@ -450,8 +462,12 @@ def run_gpu_arm(args):
                     gpu_launches=int(launches), clocks=clocks)
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # NCCL communicators that were captured into CUDA graphs do not tear down cleanly (destroy_process_group
+        # dead-locks); nothing after this point needs the group, so leave without running the destructors.
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return line
 
 
