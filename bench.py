@@ -322,7 +322,7 @@ def kernel_breakdown(hp: "HotPath", iters: int = 10):
     ptrs = _lib.ptr_array(hp.layers)
     v0 = hp.layers[0]
     t = timed(lambda: lib.scp_wsum_fwd(ptrs, L, B, T, Da, v0.stride(0), v0.stride(1), 0, _lib.ptr(w), 0, 1e-5,
-                                       _lib.ptr(y), 0, stream))
+                                       None, _lib.ptr(y), 0, stream))
     by = (L + 1) * B * T * Da * 4
     out["wsum_fwd"] = dict(seconds=t, bound="hbm", algorithmic=by, achieved=by / t / 1e9, unit="GB/s")
     dw = torch.empty(L, device=dev)
@@ -330,7 +330,7 @@ def kernel_breakdown(hp: "HotPath", iters: int = 10):
     ws = torch.empty(ws_b, dtype=torch.uint8, device=dev)
     null_pp = ctypes.cast(None, ctypes.POINTER(ctypes.c_void_p))
     t = timed(lambda: lib.scp_wsum_bwd(ptrs, L, B, T, Da, v0.stride(0), v0.stride(1), 0, _lib.ptr(w), 0, 1e-5,
-                                       _lib.ptr(hp.grad_y), 0, _lib.ptr(dw), null_pp, _lib.ptr(ws), ws_b, stream))
+                                       None, _lib.ptr(hp.grad_y), 0, _lib.ptr(dw), null_pp, _lib.ptr(ws), ws_b, stream))
     out["wsum_bwd"] = dict(seconds=t, bound="hbm", algorithmic=by, achieved=by / t / 1e9, unit="GB/s")
     # S2 forward / backward through the module (includes its small helper kernels)
     kw = hp.kw.detach().clone().requires_grad_(True)

@@ -49,24 +49,38 @@ int scp_version(void);                         /* MAJOR*10000 + MINOR*100 + PATC
 const char* scp_last_error_string(int code);   /* static string for `code`; detail of the last failure on this thread */
 int scp_num_launches(void);                    /* kernels launched by this library in this process (bench accounting) */
 
-/* ---- S1: upstream-feature fusion -- replaces WeightedSumLayer.forward (avssl/module/weighted_sum.py:26-45) -- */
-/* y[b,t,:] = sum_l softmax(weights)_l * LN?(x_l[b,t,:]).  layer_ptrs: HOST array of L device pointers; every layer
+/* ---- S1: upstream-feature fusion -- replaces WeightedSumLayer.forward (avssl/module/weighted_sum.py:26-45) and the
+ *      per-layer rescale of its caller (FairseqSpeechEncoder_Hubert.forward, avssl/module/speech_encoder_plus.py:572-592) -- */
+/* Normalisation applied to every layer BEFORE the weighted sum:
+ *   SCP_NORM_NONE       plain sum                                                   (weighted_sum.py:43)
+ *   SCP_NORM_LAYERNORM  non-affine LayerNorm over D, eps                             (weighted_sum.py:41-42; normalize_type "s3prl")
+ *   SCP_NORM_L2_FRAME   x / (||x||_2 + 1e-8) per frame                               (speech_encoder_plus.py:576-583, "method1")
+ *   SCP_NORM_UTT_MEAN   x / mean_t ||x_t||_2 per (layer, utterance)                  (speech_encoder_plus.py:584-590, "method2");
+ *                       needs utt_scale (L,B) f32 = 1/mean filled by scp_wsum_utt_scale on the same layers           */
+enum { SCP_NORM_NONE = 0, SCP_NORM_LAYERNORM = 1, SCP_NORM_L2_FRAME = 2, SCP_NORM_UTT_MEAN = 3 };
+
+/* y[b,t,:] = sum_l softmax(weights)_l * norm(x_l[b,t,:]).  layer_ptrs: HOST array of L device pointers; every layer
  * is addressed as x_l[b*stride_b + t*stride_t + d] (the reference hands over (T,B,D) storage viewed as (B,T,D):
- * avssl/module/speech_encoder_plus.py:596-599).  y is (B,T,D) contiguous.  layer_norm != 0 applies the non-affine
- * LayerNorm of weighted_sum.py:41-42 to each layer before the sum. */
+ * avssl/module/speech_encoder_plus.py:596-599).  y is (B,T,D) contiguous.  utt_scale: nullable unless
+ * norm_mode == SCP_NORM_UTT_MEAN. */
 int scp_wsum_fwd(const void* const* layer_ptrs, int L, int64_t B, int64_t T, int64_t D,
                  int64_t stride_b, int64_t stride_t, int dtype_in,
-                 const float* weights, int layer_norm, float eps,
+                 const float* weights, int norm_mode, float eps, const float* utt_scale,
                  void* y, int dtype_out, scp_stream_t stream);
+
+/* Statistics pre-pass of SCP_NORM_UTT_MEAN: utt_scale[l*B + b] = 1 / mean_t ||x_l[b,t,:]||_2 (one extra read of the
+ * layers; deterministic). */
+int scp_wsum_utt_scale(const void* const* layer_ptrs, int L, int64_t B, int64_t T, int64_t D,
+                       int64_t stride_b, int64_t stride_t, int dtype_in, float* utt_scale, scp_stream_t stream);
 
 size_t scp_wsum_bwd_workspace_bytes(int L, int64_t B, int64_t T, int64_t D);
 
 /* Backward of the above.  d_weights[l] = d(loss)/d(weights_l) (softmax backward included).  g_layers: nullable HOST
  * array of L device pointers to (B,T,D)-contiguous fp32 buffers receiving d(loss)/d(x_l) (only needed when the
- * upstream encoder is trainable: avssl/module/speech_encoder_plus.py:416-446). */
+ * upstream encoder is trainable: avssl/module/speech_encoder_plus.py:416-446; not available for SCP_NORM_UTT_MEAN). */
 int scp_wsum_bwd(const void* const* layer_ptrs, int L, int64_t B, int64_t T, int64_t D,
                  int64_t stride_b, int64_t stride_t, int dtype_in,
-                 const float* weights, int layer_norm, float eps,
+                 const float* weights, int norm_mode, float eps, const float* utt_scale,
                  const void* g_y, int dtype_g, float* d_weights, void* const* g_layers,
                  void* workspace, size_t workspace_bytes, scp_stream_t stream);
 

@@ -29,6 +29,9 @@ import torch.nn.functional as F
 __all__ = [
     "wsum_forward",
     "wsum_grad_weights",
+    "normalize_hidden_states",
+    "upstream_feat_len",
+    "upstream_tail",
     "cosine_scores_loop",
     "cosine_scores",
     "vq_forward",
@@ -79,6 +82,46 @@ def wsum_grad_weights(layers: Sequence[torch.Tensor], weights: torch.Tensor, gra
         d.append((grad_y * x_l).sum())
     d = torch.stack(d)
     return w * (d - (w * d).sum())
+
+
+# ----------------------------------------------------------------------------------------
+# S1' caller tail of the HuBERT wrapper   avssl/module/speech_encoder_plus.py:572-622
+# ----------------------------------------------------------------------------------------
+def normalize_hidden_states(layers: Sequence[torch.Tensor], normalize_type: str) -> List[torch.Tensor]:
+    """Per-layer rescale applied BEFORE the weighted sum when ``normalize_hiddenstates`` is set and
+    ``normalize_type`` is "method1" / "method2" (speech_encoder_plus.py:574-592):
+      method1  x / (||x||_2 + 1e-8), norm over the feature axis, per frame                    (:578-583)
+      method2  x / mean_t(||x_t||_2) reshaped (-1,1,1): one scalar per utterance and layer    (:586-590)
+    "s3prl" leaves the layers untouched here (it is the LayerNorm flag of the WeightedSumLayer, :472-476).
+    """
+    assert normalize_type in ("s3prl", "method1", "method2"), normalize_type  # :377
+    out = []
+    for x in layers:
+        if normalize_type == "method1":
+            x = x / (torch.norm(x, dim=-1, keepdim=True) + 1e-8)
+        elif normalize_type == "method2":
+            x = x / torch.mean(torch.norm(x, dim=-1), dim=-1).view(-1, 1, 1)
+        out.append(x)
+    return out
+
+
+def upstream_feat_len(wav_len: Sequence[int], downsample_rate: int, max_frames: int) -> torch.Tensor:
+    """feat_len = clamp_max(LongTensor([round(l / rate)]), T)  (speech_encoder_plus.py:604-611; Python ``round``
+    = half to even)."""
+    feat_len = torch.LongTensor([round(int(l) / downsample_rate) for l in wav_len])
+    return torch.clamp_max(feat_len, max_frames)
+
+
+def upstream_tail(layers: Sequence[torch.Tensor], weights: torch.Tensor, normalize_hiddenstates: bool,
+                  normalize_type: str, wav_len: Sequence[int], downsample_rate: int = 320
+                  ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """speech_encoder_plus.py:572-622 with feat_select_idx == "weighted_sum": optional rescale, feat_len, weighted sum
+    (whose LayerNorm flag is ``normalize_hiddenstates and normalize_type == "s3prl"``, :472-476)."""
+    if normalize_hiddenstates and normalize_type.startswith("method"):
+        layers = normalize_hidden_states(layers, normalize_type)
+    feat_len = upstream_feat_len(wav_len, downsample_rate, layers[0].shape[1])
+    y = wsum_forward(layers, weights, normalize_features=normalize_hiddenstates and normalize_type == "s3prl")
+    return y, feat_len
 
 
 # ----------------------------------------------------------------------------------------

@@ -15,6 +15,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libscp_b200.so")
 
 SCP_F32, SCP_F16, SCP_BF16 = 0, 1, 2
+SCP_NORM_NONE, SCP_NORM_LAYERNORM, SCP_NORM_L2_FRAME, SCP_NORM_UTT_MEAN = 0, 1, 2, 3
 SCP_MAX_LAYERS = 32
 SCP_MAX_MASKED = 8
 
@@ -32,10 +33,12 @@ SIGNATURES = {
     "scp_last_error_string": (c_char_p, [c_int]),
     "scp_num_launches": (c_int, []),
     "scp_wsum_fwd": (c_int, [POINTER(c_void_p), c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int,
-                             c_void_p, c_int, c_float, c_void_p, c_int, c_void_p]),
+                             c_void_p, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p]),
+    "scp_wsum_utt_scale": (c_int, [POINTER(c_void_p), c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int,
+                                   c_void_p, c_void_p]),
     "scp_wsum_bwd_workspace_bytes": (c_size_t, [c_int, c_int64, c_int64, c_int64]),
     "scp_wsum_bwd": (c_int, [POINTER(c_void_p), c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int,
-                             c_void_p, c_int, c_float, c_void_p, c_int, c_void_p, POINTER(c_void_p),
+                             c_void_p, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, POINTER(c_void_p),
                              c_void_p, c_size_t, c_void_p]),
     "scp_vq_padded_vocab": (c_int64, [c_int64]),
     "scp_vq_prepare_table": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -25,6 +25,13 @@
 //            cover and 227 KB of smem, bytes per MMA cycle is what decides whether the tensor pipe stays fed.
 //            Both CTAs' loads complete on the leader's `full` barrier; the leader's commits release the stage (and
 //            publish the accumulators) in both CTAs; both CTAs' epilogue warps arrive on the leader's `tmem_empty`.
+//
+// Resident X (XRES): a CTA's X tile (128 rows x K) is the same for every Y tile it walks, yet the streaming pipeline
+// re-fetches it per tile -- half (pair mode) of all L2 -> SM bytes, and those bytes, not the tensor pipe, bound the
+// sweeps (ncu: ~10 TB/s of xbar traffic at 45-50 % tensor-pipe activity).  With XRES the X chunks are loaded ONCE into
+// a resident region in front of the ring (they ride on the `full` barriers of the first tile's stages, so there is no
+// extra prologue), the ring stages carry only Y, and the feed drops to BN/2 rows x 128 B per 128x256x64 MMA.
+// Needs NX * K/64 * 16 KB of shared memory (K <= 512 for NX = 1).
 #pragma once
 #include <cstdlib>
 
@@ -143,15 +150,19 @@ __device__ __forceinline__ WorkInfo decode_work(const Sched& s) {
 constexpr int kGemmThreads = 64 + kEpiThreads;
 constexpr int kXTileBytes = kTileM * kChunkK * 2;  // 16 KB
 
-template <int BN, int NX, int STAGES, bool PAIR = false>
+template <int BN, int NX, int STAGES, bool PAIR = false, bool XRES = false>
 struct GemmCfg {
   static constexpr int kYTileBytes = (PAIR ? BN / 2 : BN) * kChunkK * 2;  // a pair CTA stages half of the Y tile
-  static constexpr int kStageBytes = NX * kXTileBytes + kYTileBytes;
+  static constexpr int kYOffset = XRES ? 0 : NX * kXTileBytes;            // Y tile inside a ring stage
+  static constexpr int kStageBytes = kYOffset + kYTileBytes;
   static constexpr int kAccCols = NX * BN;
   static constexpr int kAccStages = (int)kTmemCols / kAccCols >= 2 ? 2 : 1;
   static constexpr int kBarrierBytes = 1024;  // mbarriers + TMEM slot; keeps the epilogue scratch 1024-aligned
   // 1024 B slack for manual alignment of the dynamic smem base
-  static constexpr int smem_bytes(int epi_bytes) { return 1024 + STAGES * kStageBytes + kBarrierBytes + epi_bytes; }
+  // k_res = K chunks held resident per X operand (XRES only)
+  static constexpr int smem_bytes(int epi_bytes, int k_res = 0) {
+    return 1024 + (XRES ? NX * k_res * kXTileBytes : 0) + STAGES * kStageBytes + kBarrierBytes + epi_bytes;
+  }
   static_assert(kAccCols <= (int)kTmemCols, "accumulators exceed TMEM");
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN");
   static_assert((2 * STAGES + 4) * 8 + 16 <= kBarrierBytes, "barrier area");
@@ -168,18 +179,22 @@ struct GemmCfg {
 //   void finish();
 // Per-row state lives in the two warps ("halves") that own the row; epilogues combine the halves themselves
 // (separate partial slots, or through ctx.smem + named_bar_sync(kEpiBarrierId, kEpiThreads)).
-template <int BN, int NX, int STAGES, class Epi, int CL, int MC>
+template <int BN, int NX, int STAGES, class Epi, int CL, int MC, bool XRES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, const typename Epi::Params ep) {
   constexpr bool kPair = MC == MC_PAIR;
-  using Cfg = GemmCfg<BN, NX, STAGES, kPair>;
+  using Cfg = GemmCfg<BN, NX, STAGES, kPair, XRES>;
+  static_assert(!XRES || MC == MC_NONE || MC == MC_PAIR, "resident X is implemented for one-CTA and pair schedules");
   static_assert(CL == 1 || CL == 2 || CL == 4, "cluster size");
   static_assert(!kPair || CL == 2, "a CTA pair is a cluster of two");
   static_assert((CL == 1) == (MC == MC_NONE), "clusters exist to share operands");
   static_assert(MC != MC_X || (kTileM / CL) % 8 == 0, "X slice must be whole swizzle atoms");
   static_assert(MC != MC_Y || (BN / CL) % 8 == 0, "Y slice must be whole swizzle atoms");
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_x = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // resident X region (XRES): operand x, chunk j at smem_x + (x * k_res + j) * 16 KB; the ring follows it
+  const int k_res = XRES ? (int)(((long long)sched.k_chunks + sched.k_splits - 1) / sched.k_splits) : 0;
+  uint8_t* smem = smem_x + (size_t)NX * k_res * kXTileBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
@@ -230,19 +245,32 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
         for (int kc = work.kc0; kc < work.kc1; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * Cfg::kStageBytes;
+          // XRES: the X chunks travel with the first tile's stages and land in the resident region
+          const bool load_x = !XRES || it == 0;
+          const uint32_t stage_tx = (uint32_t)Cfg::kStageBytes + (XRES && it == 0 ? NX * kXTileBytes : 0);
+          uint8_t* xdst = XRES ? smem_x + (size_t)(kc - work.kc0) * kXTileBytes : st;
+          const size_t xstep = XRES ? (size_t)k_res * kXTileBytes : (size_t)kXTileBytes;
           if (kPair) {
             // both CTAs' bytes are posted on the leader's barrier, which the leader arms for the two of them
-            if (work.rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            if (work.rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_tx);
             const uint32_t lead_bar = mapa_u32(&full_bar[stage], 0);
+            if (load_x) {
 #pragma unroll
-            for (int x = 0; x < NX; ++x)
-              tma_load_2d_pair(st + x * kXTileBytes, &maps.x[x], kc * kChunkK, work.x_row, lead_bar);
-            tma_load_2d_pair(st + NX * kXTileBytes, &maps.y, kc * kChunkK, nt * BN + work.rank * (BN / 2), lead_bar);
+              for (int x = 0; x < NX; ++x)
+                tma_load_2d_pair(xdst + x * xstep, &maps.x[x], kc * kChunkK, work.x_row, lead_bar);
+            }
+            tma_load_2d_pair(st + Cfg::kYOffset, &maps.y, kc * kChunkK, nt * BN + work.rank * (BN / 2), lead_bar);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          if (MC == MC_X) {
+          mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+          if (XRES) {
+            if (load_x) {
+#pragma unroll
+              for (int x = 0; x < NX; ++x)
+                tma_load_2d(xdst + x * xstep, &maps.x[x], kc * kChunkK, work.x_row, &full_bar[stage]);
+            }
+          } else if (MC == MC_X) {
             constexpr int kRows = kTileM / CL;
 #pragma unroll
             for (int x = 0; x < NX; ++x)
@@ -255,10 +283,10 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
           }
           if (MC == MC_Y) {
             constexpr int kRows = BN / CL;
-            tma_load_2d_mc(st + NX * kXTileBytes + work.rank * kRows * 128, &maps.y, kc * kChunkK,
+            tma_load_2d_mc(st + Cfg::kYOffset + work.rank * kRows * 128, &maps.y, kc * kChunkK,
                            nt * BN + work.rank * kRows, &full_bar[stage], kClusterMask);
           } else {
-            tma_load_2d(st + NX * kXTileBytes, &maps.y, kc * kChunkK, nt * BN, &full_bar[stage]);
+            tma_load_2d(st + Cfg::kYOffset, &maps.y, kc * kChunkK, nt * BN, &full_bar[stage]);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -277,10 +305,12 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t st = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint64_t b_desc = make_kmajor_sw128_desc(st + NX * kXTileBytes);
+          const uint64_t b_desc = make_kmajor_sw128_desc(st + Cfg::kYOffset);
+          const uint32_t xbase = XRES ? smem_u32(smem_x) + (uint32_t)(kc - work.kc0) * kXTileBytes : st;
+          const uint32_t xstep = XRES ? (uint32_t)k_res * kXTileBytes : (uint32_t)kXTileBytes;
 #pragma unroll
           for (int x = 0; x < NX; ++x) {
-            const uint64_t a_desc = make_kmajor_sw128_desc(st + x * kXTileBytes);
+            const uint64_t a_desc = make_kmajor_sw128_desc(xbase + x * xstep);
             const uint32_t d = tmem_base + (uint32_t)(as * Cfg::kAccCols + x * BN);
 #pragma unroll
             for (int k = 0; k < kChunkK / kUmmaK; ++k) {
@@ -388,16 +418,27 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
   }
 }
 
-template <int BN, int NX, int STAGES, class Epi, int CL = 1, int MC = MC_NONE>
+constexpr int kMaxDynSmem = 227 * 1024;  // sm_100: 232448 B of dynamic shared memory per CTA
+
+// shared memory a resident-X launch needs; callers fall back to the streaming kernel when it exceeds kMaxDynSmem
+template <int BN, int NX, int STAGES, class Epi, int MC>
+constexpr int resident_smem_bytes(int k_chunks_per_split) {
+  return GemmCfg<BN, NX, STAGES, MC == MC_PAIR, true>::smem_bytes(Epi::kSmemBytes, k_chunks_per_split);
+}
+
+template <int BN, int NX, int STAGES, class Epi, int CL = 1, int MC = MC_NONE, bool XRES = false>
 int launch_stream_gemm(const GemmMaps& maps, const Sched& sched, const typename Epi::Params& ep, cudaStream_t stream,
                        const char* name) {
-  using Cfg = GemmCfg<BN, NX, STAGES, MC == MC_PAIR>;
-  auto kern = stream_gemm_kernel<BN, NX, STAGES, Epi, CL, MC>;
-  const int smem = Cfg::smem_bytes(Epi::kSmemBytes);
+  using Cfg = GemmCfg<BN, NX, STAGES, MC == MC_PAIR, XRES>;
+  auto kern = stream_gemm_kernel<BN, NX, STAGES, Epi, CL, MC, XRES>;
+  const int k_res = XRES ? (sched.k_chunks + sched.k_splits - 1) / sched.k_splits : 0;
+  const int smem = Cfg::smem_bytes(Epi::kSmemBytes, k_res);
+  if (smem > kMaxDynSmem) return fail(SCP_ERR_UNSUPPORTED, "%s: %d B of shared memory needed (K too large for a resident X tile)", name, smem);
   static thread_local bool configured = false;  // per instantiation
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return fail(SCP_ERR_CUDA, "%s: cudaFuncSetAttribute(%d B): %s", name, smem, cudaGetErrorString(e));
+    const int attr_smem = XRES ? kMaxDynSmem : smem;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, attr_smem);
+    if (e != cudaSuccess) return fail(SCP_ERR_CUDA, "%s: cudaFuncSetAttribute(%d B): %s", name, attr_smem, cudaGetErrorString(e));
     configured = true;
   }
   const int grid = sched_grid<CL, MC>(sched);

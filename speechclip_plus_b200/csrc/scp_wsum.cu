@@ -10,6 +10,11 @@
 //     torch's layer_norm), next layer's row prefetched while the current one is reduced.
 //   * backward: d_l = <g_y, xhat_l> accumulated per lane/warp, per-block partials, deterministic finalize kernel that also
 //     applies the softmax Jacobian  d_weights = w * (d - <w,d>).
+//   * S1' (caller tail of FairseqSpeechEncoder_Hubert.forward, speech_encoder_plus.py:572-592) -- the per-layer rescale
+//     the reference applies in a Python loop before the sum is fused as two more normalisation modes:
+//       SCP_NORM_L2_FRAME ("method1"): x / (||x||_2 + 1e-8) per frame      -> the warp<->row kernel with an L2 statistic
+//       SCP_NORM_UTT_MEAN ("method2"): x / mean_t ||x_t||_2 per utterance  -> a statistics pre-pass (scp_wsum_utt_scale)
+//                                      writes 1/mean per (layer, utterance); the plain kernels fold it into the weight.
 #include "scp_common.cuh"
 
 namespace scp {
@@ -60,7 +65,8 @@ __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* dst, const 
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(kWsumThreads)
 wsum_fwd_plain4_kernel(LayerPtrs lp, int L, int64_t n_vec, int vec_per_row, int64_t T, int64_t stride_b,
-                       int64_t stride_t, const float* __restrict__ weights, TOut* __restrict__ y) {
+                       int64_t stride_t, const float* __restrict__ weights, const float* __restrict__ utt_scale,
+                       int64_t B, TOut* __restrict__ y) {
   // plain forward: thread <-> one 16 B input vector of one row, all L loads issued before the first FMA;
   // output written in groups of 4 elements (any in/out dtype pair)
   constexpr int NE = Vec16<TIn>::NE;
@@ -85,7 +91,8 @@ wsum_fwd_plain4_kernel(LayerPtrs lp, int L, int64_t n_vec, int vec_per_row, int6
       if (l0 + j < L) {
         float f[NE];
         Vec16<TIn>::unpack(raw[j], f);
-        const float w = sw[l0 + j];
+        float w = sw[l0 + j];
+        if (utt_scale) w *= __ldg(utt_scale + (int64_t)(l0 + j) * B + b);  // method2: 1 / mean_t ||x_{l,b,t}||
 #pragma unroll
         for (int e = 0; e < NE; ++e) acc[e] = fmaf(w, f[e], acc[e]);
       }
@@ -131,7 +138,21 @@ __device__ __forceinline__ void row_stats(const float (&x)[NV][NE], int lane, in
   rstd = 1.0f / sqrtf(var + eps);
 }
 
-template <typename TIn, typename TOut, int NV>
+// L2 norm of the row held as x[NV][NE] (invalid vectors are zero)
+template <int NV, int NE>
+__device__ __forceinline__ float row_l2(const float (&x)[NV][NE]) {
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+#pragma unroll
+    for (int e = 0; e < NE; ++e) q = fmaf(x[j][e], x[j][e], q);
+  return sqrtf(warp_sum(q));
+}
+
+constexpr float kL2FrameEps = 1e-8f;  // speech_encoder_plus.py:582
+
+// MODE = SCP_NORM_LAYERNORM: xhat = (x - mean) * rstd ; MODE = SCP_NORM_L2_FRAME: xhat = x / (||x|| + 1e-8)
+template <typename TIn, typename TOut, int NV, int MODE>
 __global__ void __launch_bounds__(kWsumThreads)
 wsum_fwd_ln_kernel(LayerPtrs lp, int L, int64_t n_rows, int vec_per_row, int D, int64_t T, int64_t stride_b,
                    int64_t stride_t, const float* __restrict__ weights, float eps, TOut* __restrict__ y) {
@@ -156,8 +177,9 @@ wsum_fwd_ln_kernel(LayerPtrs lp, int L, int64_t n_rows, int vec_per_row, int D, 
       float x[NV][NE];
 #pragma unroll
       for (int j = 0; j < NV; ++j) Vec16<TIn>::unpack(cur[j], x[j]);
-      float mean, rstd;
-      row_stats<NV, NE>(x, lane, vec_per_row, D, eps, mean, rstd);
+      float mean = 0.f, rstd;
+      if (MODE == SCP_NORM_LAYERNORM) row_stats<NV, NE>(x, lane, vec_per_row, D, eps, mean, rstd);
+      else rstd = 1.0f / (row_l2<NV, NE>(x) + kL2FrameEps);
       const float a = sw[l] * rstd;
 #pragma unroll
       for (int j = 0; j < NV; ++j)
@@ -193,8 +215,9 @@ __device__ __forceinline__ void load_grad_vec(const TG* p, float* g) {
 template <typename TIn, typename TG>
 __global__ void __launch_bounds__(kWsumThreads)
 wsum_bwd_plain_kernel(LayerPtrs lp, int L, int64_t n_vec, int vec_per_row, int64_t T, int64_t stride_b,
-                      int64_t stride_t, const float* __restrict__ weights, const TG* __restrict__ g_y,
-                      float* __restrict__ partials, LayerOutPtrs gl, int write_gl) {
+                      int64_t stride_t, const float* __restrict__ weights, const float* __restrict__ utt_scale,
+                      int64_t B, const TG* __restrict__ g_y, float* __restrict__ partials, LayerOutPtrs gl,
+                      int write_gl) {
   constexpr int NE = Vec16<TIn>::NE;  // elements handled per thread-iteration
   __shared__ float sw[SCP_MAX_LAYERS];
   __shared__ float sred[kWsumThreads / 32][SCP_MAX_LAYERS];
@@ -226,6 +249,7 @@ wsum_bwd_plain_kernel(LayerPtrs lp, int L, int64_t n_vec, int vec_per_row, int64
             float s = 0.f;
 #pragma unroll
             for (int e = 0; e < NE; ++e) s = fmaf(g[e], f[e], s);
+            if (utt_scale) s *= __ldg(utt_scale + (int64_t)(l0 + j) * B + b);  // d_l = <g, x_l / mean-norm>
             acc[l0 + j] += s;
             if (write_gl) {
               const float w = sw[l0 + j];
@@ -256,8 +280,8 @@ wsum_bwd_plain_kernel(LayerPtrs lp, int L, int64_t n_vec, int vec_per_row, int64
   }
 }
 
-// backward, LayerNorm: warp <-> row
-template <typename TIn, typename TG, int NV>
+// backward, LayerNorm / per-frame L2: warp <-> row
+template <typename TIn, typename TG, int NV, int MODE>
 __global__ void __launch_bounds__(kWsumThreads)
 wsum_bwd_ln_kernel(LayerPtrs lp, int L, int64_t n_rows, int vec_per_row, int D, int64_t T, int64_t stride_b,
                    int64_t stride_t, const float* __restrict__ weights, float eps, const TG* __restrict__ g_y,
@@ -294,8 +318,13 @@ wsum_bwd_ln_kernel(LayerPtrs lp, int L, int64_t n_rows, int vec_per_row, int D, 
       float x[NV][NE];
 #pragma unroll
       for (int j = 0; j < NV; ++j) Vec16<TIn>::unpack(cur[j], x[j]);
-      float mean, rstd;
-      row_stats<NV, NE>(x, lane, vec_per_row, D, eps, mean, rstd);
+      float mean = 0.f, rstd, l2 = 0.f;
+      if (MODE == SCP_NORM_LAYERNORM) {
+        row_stats<NV, NE>(x, lane, vec_per_row, D, eps, mean, rstd);
+      } else {
+        l2 = row_l2<NV, NE>(x);
+        rstd = 1.0f / (l2 + kL2FrameEps);
+      }
       float dot = 0.f;  // sum_d g * xhat
 #pragma unroll
       for (int j = 0; j < NV; ++j)
@@ -310,7 +339,11 @@ wsum_bwd_ln_kernel(LayerPtrs lp, int L, int64_t n_rows, int vec_per_row, int D, 
       if (lane == 0) sred[warp][l] += dot;
       if (write_gl) {
         // LayerNorm backward with upstream gradient w_l*g:  dx = rstd*w_l*(g - mean(g) - xhat*mean(g*xhat))
-        const float a = rstd * sw[l], mg = gsum / (float)D, mgx = dot / (float)D;
+        // per-frame L2 (y = x/(n+eps)):                       dx = w_l/(n+eps)*(g - xhat*<g,xhat>*(n+eps)/n), n = 0 -> no 2nd term
+        const float a = rstd * sw[l];
+        const float mg = MODE == SCP_NORM_LAYERNORM ? gsum / (float)D : 0.f;
+        const float mgx = MODE == SCP_NORM_LAYERNORM ? dot / (float)D
+                                                      : (l2 > 0.f ? dot * (l2 + kL2FrameEps) / l2 : 0.f);
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
           const int v = lane + 32 * j;
@@ -334,6 +367,40 @@ wsum_bwd_ln_kernel(LayerPtrs lp, int L, int64_t n_rows, int vec_per_row, int D, 
 #pragma unroll
     for (int w = 0; w < kWsumThreads / 32; ++w) s += sred[w][threadIdx.x];
     partials[(int64_t)blockIdx.x * SCP_MAX_LAYERS + threadIdx.x] = s;
+  }
+}
+
+// method2 statistics: utt_scale[l*B + b] = 1 / mean_t ||x_l[b,t,:]||_2   (speech_encoder_plus.py:584-590)
+// grid (B, L); warp <-> frame (strided over t), fixed-order block reduction -> deterministic
+template <typename TIn>
+__global__ void __launch_bounds__(kWsumThreads)
+wsum_utt_scale_kernel(LayerPtrs lp, int64_t B, int64_t T, int vec_per_row, int64_t stride_b, int64_t stride_t,
+                      float* __restrict__ utt_scale) {
+  constexpr int NE = Vec16<TIn>::NE;
+  __shared__ float sred[kWsumThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = blockIdx.x;
+  const int l = blockIdx.y;
+  const TIn* base = reinterpret_cast<const TIn*>(lp.p[l]) + b * stride_b;
+  float tot = 0.f;
+  for (int64_t t = warp; t < T; t += kWsumThreads / 32) {
+    const TIn* row = base + t * stride_t;
+    float q = 0.f;
+    for (int v = lane; v < vec_per_row; v += 32) {
+      float f[NE];
+      Vec16<TIn>::unpack(ld_stream16(row + (int64_t)v * NE), f);
+#pragma unroll
+      for (int e = 0; e < NE; ++e) q = fmaf(f[e], f[e], q);
+    }
+    tot += sqrtf(warp_sum(q));
+  }
+  if (lane == 0) sred[warp] = tot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWsumThreads / 32; ++w) s += sred[w];
+    utt_scale[(int64_t)l * B + b] = (float)T / s;  // no epsilon in the reference: an all-zero utterance gives inf
   }
 }
 
@@ -361,15 +428,17 @@ __global__ void wsum_bwd_finalize_kernel(const float* __restrict__ partials, int
 // ------------------------------------------------------------------------------------------------------------
 template <typename TIn, typename TOut>
 static int launch_fwd(const LayerPtrs& lp, int L, int64_t B, int64_t T, int64_t D, int64_t sb, int64_t st,
-                      const float* weights, int layer_norm, float eps, void* y, cudaStream_t stream) {
+                      const float* weights, int norm_mode, float eps, const float* utt_scale, void* y,
+                      cudaStream_t stream) {
   constexpr int NE = Vec16<TIn>::NE;
   const int vec_per_row = (int)(D / NE);
   const int64_t n_rows = B * T;
-  if (!layer_norm) {
+  if (norm_mode == SCP_NORM_NONE || norm_mode == SCP_NORM_UTT_MEAN) {
     const int64_t n_vec = n_rows * vec_per_row;
     const int64_t blocks = ceil_div(n_vec, kWsumThreads);
     wsum_fwd_plain4_kernel<TIn, TOut><<<(unsigned)blocks, kWsumThreads, 0, stream>>>(
-        lp, L, n_vec, vec_per_row, T, sb, st, weights, reinterpret_cast<TOut*>(y));
+        lp, L, n_vec, vec_per_row, T, sb, st, weights, norm_mode == SCP_NORM_UTT_MEAN ? utt_scale : nullptr, B,
+        reinterpret_cast<TOut*>(y));
     SCP_CUDA_LAUNCH_CHECK("wsum_fwd_plain");
     return SCP_OK;
   }
@@ -377,14 +446,18 @@ static int launch_fwd(const LayerPtrs& lp, int L, int64_t B, int64_t T, int64_t 
   const int64_t blocks = std::min<int64_t>(ceil_div(n_rows, kWsumThreads / 32), (int64_t)kNumSMs * 8);
 #define SCP_LN_CASE(NVV)                                                                                         \
   case NVV:                                                                                                      \
-    wsum_fwd_ln_kernel<TIn, TOut, NVV><<<(unsigned)blocks, kWsumThreads, 0, stream>>>(                           \
-        lp, L, n_rows, vec_per_row, (int)D, T, sb, st, weights, eps, reinterpret_cast<TOut*>(y));                \
+    if (norm_mode == SCP_NORM_LAYERNORM)                                                                         \
+      wsum_fwd_ln_kernel<TIn, TOut, NVV, SCP_NORM_LAYERNORM><<<(unsigned)blocks, kWsumThreads, 0, stream>>>(     \
+          lp, L, n_rows, vec_per_row, (int)D, T, sb, st, weights, eps, reinterpret_cast<TOut*>(y));              \
+    else                                                                                                         \
+      wsum_fwd_ln_kernel<TIn, TOut, NVV, SCP_NORM_L2_FRAME><<<(unsigned)blocks, kWsumThreads, 0, stream>>>(      \
+          lp, L, n_rows, vec_per_row, (int)D, T, sb, st, weights, eps, reinterpret_cast<TOut*>(y));              \
     break;
   switch (nv) {
     SCP_LN_CASE(1) SCP_LN_CASE(2) SCP_LN_CASE(3) SCP_LN_CASE(4) SCP_LN_CASE(5) SCP_LN_CASE(6) SCP_LN_CASE(7)
     SCP_LN_CASE(8)
     default:
-      return fail(SCP_ERR_UNSUPPORTED, "wsum LayerNorm path supports D <= %d for this dtype (got %lld)",
+      return fail(SCP_ERR_UNSUPPORTED, "wsum per-frame normalisation supports D <= %d for this dtype (got %lld)",
                   8 * 32 * NE, (long long)D);
   }
 #undef SCP_LN_CASE
@@ -394,32 +467,38 @@ static int launch_fwd(const LayerPtrs& lp, int L, int64_t B, int64_t T, int64_t 
 
 template <typename TIn, typename TG>
 static int launch_bwd(const LayerPtrs& lp, int L, int64_t B, int64_t T, int64_t D, int64_t sb, int64_t st,
-                      const float* weights, int layer_norm, float eps, const void* g_y, float* d_weights,
-                      const LayerOutPtrs& gl, int write_gl, float* partials, cudaStream_t stream) {
+                      const float* weights, int norm_mode, float eps, const float* utt_scale, const void* g_y,
+                      float* d_weights, const LayerOutPtrs& gl, int write_gl, float* partials, cudaStream_t stream) {
   constexpr int NE = Vec16<TIn>::NE;
   const int vec_per_row = (int)(D / NE);
   const int64_t n_rows = B * T;
   int blocks;
-  if (!layer_norm) {
+  if (norm_mode == SCP_NORM_NONE || norm_mode == SCP_NORM_UTT_MEAN) {
     const int64_t n_vec = n_rows * vec_per_row;
     blocks = (int)std::min<int64_t>(ceil_div(n_vec, kWsumThreads), kWsumBwdBlocks);
     wsum_bwd_plain_kernel<TIn, TG><<<blocks, kWsumThreads, 0, stream>>>(
-        lp, L, n_vec, vec_per_row, T, sb, st, weights, reinterpret_cast<const TG*>(g_y), partials, gl, write_gl);
+        lp, L, n_vec, vec_per_row, T, sb, st, weights, norm_mode == SCP_NORM_UTT_MEAN ? utt_scale : nullptr, B,
+        reinterpret_cast<const TG*>(g_y), partials, gl, write_gl);
     SCP_CUDA_LAUNCH_CHECK("wsum_bwd_plain");
   } else {
     const int nv = (int)ceil_div(vec_per_row, 32);
     blocks = (int)std::min<int64_t>(ceil_div(n_rows, kWsumThreads / 32), kWsumBwdBlocks);
 #define SCP_LN_CASE(NVV)                                                                                     \
   case NVV:                                                                                                  \
-    wsum_bwd_ln_kernel<TIn, TG, NVV><<<blocks, kWsumThreads, 0, stream>>>(                                   \
-        lp, L, n_rows, vec_per_row, (int)D, T, sb, st, weights, eps, reinterpret_cast<const TG*>(g_y),       \
-        partials, gl, write_gl);                                                                             \
+    if (norm_mode == SCP_NORM_LAYERNORM)                                                                     \
+      wsum_bwd_ln_kernel<TIn, TG, NVV, SCP_NORM_LAYERNORM><<<blocks, kWsumThreads, 0, stream>>>(             \
+          lp, L, n_rows, vec_per_row, (int)D, T, sb, st, weights, eps, reinterpret_cast<const TG*>(g_y),     \
+          partials, gl, write_gl);                                                                           \
+    else                                                                                                     \
+      wsum_bwd_ln_kernel<TIn, TG, NVV, SCP_NORM_L2_FRAME><<<blocks, kWsumThreads, 0, stream>>>(              \
+          lp, L, n_rows, vec_per_row, (int)D, T, sb, st, weights, eps, reinterpret_cast<const TG*>(g_y),     \
+          partials, gl, write_gl);                                                                           \
     break;
     switch (nv) {
       SCP_LN_CASE(1) SCP_LN_CASE(2) SCP_LN_CASE(3) SCP_LN_CASE(4) SCP_LN_CASE(5) SCP_LN_CASE(6) SCP_LN_CASE(7)
       SCP_LN_CASE(8)
       default:
-        return fail(SCP_ERR_UNSUPPORTED, "wsum LayerNorm path supports D <= %d for this dtype (got %lld)",
+        return fail(SCP_ERR_UNSUPPORTED, "wsum per-frame normalisation supports D <= %d for this dtype (got %lld)",
                     8 * 32 * NE, (long long)D);
     }
 #undef SCP_LN_CASE
@@ -451,16 +530,45 @@ static int check_wsum_args(const void* const* layer_ptrs, int L, int64_t B, int6
 
 using namespace scp;
 
+static int check_norm_mode(int norm_mode, const float* utt_scale) {
+  SCP_CHECK_ARG(norm_mode >= SCP_NORM_NONE && norm_mode <= SCP_NORM_UTT_MEAN, "wsum: bad norm_mode %d", norm_mode);
+  SCP_CHECK_ARG(norm_mode != SCP_NORM_UTT_MEAN || utt_scale, "wsum: SCP_NORM_UTT_MEAN needs utt_scale (scp_wsum_utt_scale)");
+  return SCP_OK;
+}
+
+extern "C" int scp_wsum_utt_scale(const void* const* layer_ptrs, int L, int64_t B, int64_t T, int64_t D,
+                                  int64_t stride_b, int64_t stride_t, int dtype_in, float* utt_scale,
+                                  scp_stream_t stream) {
+  int rc = check_wsum_args(layer_ptrs, L, B, T, D, stride_b, stride_t, dtype_in, utt_scale);
+  if (rc) return rc;
+  SCP_CHECK_ARG(B <= 2147483647ll, "wsum_utt_scale: B too large");
+  LayerPtrs lp{};
+  for (int l = 0; l < L; ++l) lp.p[l] = layer_ptrs[l];
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const dim3 grid((unsigned)B, (unsigned)L);
+  const int ne = dtype_in == SCP_F32 ? 4 : 8;
+  if (dtype_in == SCP_F32)
+    wsum_utt_scale_kernel<float><<<grid, kWsumThreads, 0, s>>>(lp, B, T, (int)(D / ne), stride_b, stride_t, utt_scale);
+  else if (dtype_in == SCP_F16)
+    wsum_utt_scale_kernel<__half><<<grid, kWsumThreads, 0, s>>>(lp, B, T, (int)(D / ne), stride_b, stride_t, utt_scale);
+  else
+    wsum_utt_scale_kernel<__nv_bfloat16><<<grid, kWsumThreads, 0, s>>>(lp, B, T, (int)(D / ne), stride_b, stride_t, utt_scale);
+  SCP_CUDA_LAUNCH_CHECK("wsum_utt_scale");
+  return SCP_OK;
+}
+
 extern "C" int scp_wsum_fwd(const void* const* layer_ptrs, int L, int64_t B, int64_t T, int64_t D, int64_t stride_b,
-                            int64_t stride_t, int dtype_in, const float* weights, int layer_norm, float eps,
-                            void* y, int dtype_out, scp_stream_t stream) {
+                            int64_t stride_t, int dtype_in, const float* weights, int norm_mode, float eps,
+                            const float* utt_scale, void* y, int dtype_out, scp_stream_t stream) {
   int rc = check_wsum_args(layer_ptrs, L, B, T, D, stride_b, stride_t, dtype_in, weights);
   if (rc) return rc;
+  if ((rc = check_norm_mode(norm_mode, utt_scale))) return rc;
   SCP_CHECK_ARG(y && !(reinterpret_cast<uintptr_t>(y) & 15), "wsum_fwd: y null or misaligned");
   LayerPtrs lp{};
   for (int l = 0; l < L; ++l) lp.p[l] = layer_ptrs[l];
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-#define SCP_DISPATCH(TI, TO) return launch_fwd<TI, TO>(lp, L, B, T, D, stride_b, stride_t, weights, layer_norm, eps, y, s)
+#define SCP_DISPATCH(TI, TO) \
+  return launch_fwd<TI, TO>(lp, L, B, T, D, stride_b, stride_t, weights, norm_mode, eps, utt_scale, y, s)
   if (dtype_in == SCP_F32 && dtype_out == SCP_F32) SCP_DISPATCH(float, float);
   if (dtype_in == SCP_F16 && dtype_out == SCP_F32) SCP_DISPATCH(__half, float);
   if (dtype_in == SCP_BF16 && dtype_out == SCP_F32) SCP_DISPATCH(__nv_bfloat16, float);
@@ -475,11 +583,15 @@ extern "C" size_t scp_wsum_bwd_workspace_bytes(int, int64_t, int64_t, int64_t) {
 }
 
 extern "C" int scp_wsum_bwd(const void* const* layer_ptrs, int L, int64_t B, int64_t T, int64_t D, int64_t stride_b,
-                            int64_t stride_t, int dtype_in, const float* weights, int layer_norm, float eps,
-                            const void* g_y, int dtype_g, float* d_weights, void* const* g_layers, void* workspace,
-                            size_t workspace_bytes, scp_stream_t stream) {
+                            int64_t stride_t, int dtype_in, const float* weights, int norm_mode, float eps,
+                            const float* utt_scale, const void* g_y, int dtype_g, float* d_weights,
+                            void* const* g_layers, void* workspace, size_t workspace_bytes, scp_stream_t stream) {
   int rc = check_wsum_args(layer_ptrs, L, B, T, D, stride_b, stride_t, dtype_in, weights);
   if (rc) return rc;
+  if ((rc = check_norm_mode(norm_mode, utt_scale))) return rc;
+  if (norm_mode == SCP_NORM_UTT_MEAN && g_layers)
+    return fail(SCP_ERR_UNSUPPORTED, "wsum_bwd: layer gradients through the per-utterance mean-norm (method2) are not "
+                                     "implemented (no shipped recipe trains HuBERT with normalize_type=method2)");
   SCP_CHECK_ARG(g_y && d_weights && workspace, "wsum_bwd: null pointer");
   SCP_CHECK_ARG(!(reinterpret_cast<uintptr_t>(g_y) & 15), "wsum_bwd: g_y misaligned");
   if (workspace_bytes < scp_wsum_bwd_workspace_bytes(L, B, T, D))
@@ -496,8 +608,8 @@ extern "C" int scp_wsum_bwd(const void* const* layer_ptrs, int L, int64_t B, int
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   float* partials = reinterpret_cast<float*>(workspace);
 #define SCP_DISPATCH(TI, TG)                                                                                   \
-  return launch_bwd<TI, TG>(lp, L, B, T, D, stride_b, stride_t, weights, layer_norm, eps, g_y, d_weights, gl,  \
-                            g_layers != nullptr, partials, s)
+  return launch_bwd<TI, TG>(lp, L, B, T, D, stride_b, stride_t, weights, norm_mode, eps, utt_scale, g_y,      \
+                            d_weights, gl, g_layers != nullptr, partials, s)
   if (dtype_in == SCP_F32 && dtype_g == SCP_F32) SCP_DISPATCH(float, float);
   if (dtype_in == SCP_F16 && dtype_g == SCP_F32) SCP_DISPATCH(__half, float);
   if (dtype_in == SCP_BF16 && dtype_g == SCP_F32) SCP_DISPATCH(__nv_bfloat16, float);

@@ -3,6 +3,11 @@
 Same constructor, parameter name (``weights``, zeros-initialised, shape ``(n_weights,)``), ``state_dict`` key and
 ``forward(x: List[Tensor]) -> Tensor`` contract; the arithmetic runs in the sm_100a kernels of csrc/scp_wsum.cu
 (one pass over the L layer tensors, no ``torch.stack`` copy, no broadcast temporaries).
+
+Extension (keyword-only, default = reference behaviour): ``normalize_type`` selects which per-layer normalisation is
+fused into the sum -- ``"s3prl"`` (LayerNorm, weighted_sum.py:41-42) or the two rescales the reference's HuBERT wrapper
+applies in a Python loop before calling the layer (speech_encoder_plus.py:572-592): ``"method1"`` (per-frame L2) and
+``"method2"`` (per-utterance mean frame norm).  See ``speech_encoder_plus.fuse_upstream_features``.
 """
 from __future__ import annotations
 
@@ -18,6 +23,8 @@ from .. import _lib
 logger = logging.getLogger(__name__)
 
 LN_EPS = 1e-5  # F.layer_norm default, weighted_sum.py:42
+NORM_MODES = {None: _lib.SCP_NORM_NONE, "s3prl": _lib.SCP_NORM_LAYERNORM, "method1": _lib.SCP_NORM_L2_FRAME,
+              "method2": _lib.SCP_NORM_UTT_MEAN}
 
 
 def _uniform_views(layers: Sequence[torch.Tensor]):
@@ -36,7 +43,7 @@ def _uniform_views(layers: Sequence[torch.Tensor]):
 
 class _WeightedSumFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, weights: torch.Tensor, normalize: bool, *layers: torch.Tensor):
+    def forward(ctx, weights: torch.Tensor, norm_mode: int, *layers: torch.Tensor):
         lib = _lib.load()
         x0 = layers[0]
         _lib.require_cuda(x0, "WeightedSumLayer")
@@ -50,12 +57,19 @@ class _WeightedSumFn(torch.autograd.Function):
         w = weights.detach().float().contiguous()
         y = torch.empty((B, T, D), dtype=torch.float32, device=v0.device)
         ptrs = _lib.ptr_array(views)
+        utt_scale = None
         with torch.cuda.device(v0.device):
+            if norm_mode == _lib.SCP_NORM_UTT_MEAN:  # statistics pre-pass: 1 / mean_t ||x_{l,b,t}||
+                utt_scale = torch.empty((len(views), B), dtype=torch.float32, device=v0.device)
+                st = lib.scp_wsum_utt_scale(ptrs, len(views), B, T, D, v0.stride(0), v0.stride(1),
+                                            _lib.dtype_code(v0.dtype), _lib.ptr(utt_scale), _lib.stream_ptr(v0.device))
+                _lib.check(st, "scp_wsum_utt_scale")
             st = lib.scp_wsum_fwd(ptrs, len(views), B, T, D, v0.stride(0), v0.stride(1), _lib.dtype_code(v0.dtype),
-                                  _lib.ptr(w), int(normalize), LN_EPS, _lib.ptr(y), _lib.SCP_F32,
+                                  _lib.ptr(w), int(norm_mode), LN_EPS, _lib.ptr(utt_scale), _lib.ptr(y), _lib.SCP_F32,
                                   _lib.stream_ptr(v0.device))
         _lib.check(st, "scp_wsum_fwd")
-        ctx.normalize = bool(normalize)
+        ctx.norm_mode = int(norm_mode)
+        ctx.utt_scale = utt_scale
         ctx.save_for_backward(w, *views)
         ctx.lead_shape = lead_shape
         ctx.in_shapes = [l.shape for l in layers]
@@ -80,8 +94,8 @@ class _WeightedSumFn(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=v0.device)
         with torch.cuda.device(v0.device):
             st = lib.scp_wsum_bwd(_lib.ptr_array(views), L, B, T, D, v0.stride(0), v0.stride(1),
-                                  _lib.dtype_code(v0.dtype), _lib.ptr(w), int(ctx.normalize), LN_EPS,
-                                  _lib.ptr(g), _lib.SCP_F32, _lib.ptr(d_w),
+                                  _lib.dtype_code(v0.dtype), _lib.ptr(w), ctx.norm_mode, LN_EPS,
+                                  _lib.ptr(ctx.utt_scale), _lib.ptr(g), _lib.SCP_F32, _lib.ptr(d_w),
                                   g_ptrs if g_ptrs is not None else ctypes.cast(None, ctypes.POINTER(ctypes.c_void_p)),
                                   _lib.ptr(ws), ws_bytes, _lib.stream_ptr(v0.device))
         _lib.check(st, "scp_wsum_bwd")
@@ -94,9 +108,12 @@ class _WeightedSumFn(torch.autograd.Function):
 
 
 class WeightedSumLayer(nn.Module):
-    def __init__(self, n_weights: int, normalize_features: bool = False):
+    def __init__(self, n_weights: int, normalize_features: bool = False, *, normalize_type: str = "s3prl"):
         """Softmax-weighted sum of ``n_weights`` hidden representations (weighted_sum.py:11-24)."""
         super().__init__()
+        if normalize_type not in ("s3prl", "method1", "method2"):  # speech_encoder_plus.py:377
+            raise AssertionError(normalize_type)
+        self.normalize_type = normalize_type
         if n_weights > _lib.SCP_MAX_LAYERS:
             raise _lib.ScpError(f"n_weights={n_weights} > {_lib.SCP_MAX_LAYERS}")
         self.n_weights = n_weights
@@ -107,4 +124,5 @@ class WeightedSumLayer(nn.Module):
 
     def forward(self, x: List[torch.Tensor]) -> torch.Tensor:
         assert len(x) == self.n_weights, len(x)  # weighted_sum.py:36
-        return _WeightedSumFn.apply(self.weights, self.normalize_features, *x)
+        mode = NORM_MODES[self.normalize_type] if self.normalize_features else _lib.SCP_NORM_NONE
+        return _WeightedSumFn.apply(self.weights, mode, *x)

@@ -8,6 +8,8 @@ Each fixture stores the inputs and what the reference classes returned (outputs 
 gradients).  The fixtures are committed; the GPU box replays them without the reference.
 Reference entry points exercised (paths relative to /root/reference):
   * avssl/module/weighted_sum.py            WeightedSumLayer.forward                      (S1)
+  * avssl/module/speech_encoder_plus.py:518-622  FairseqSpeechEncoder_Hubert.forward with a stand-in upstream
+                                            model: per-layer rescale, feat_len, weighted sum   (S1')
   * avssl/model/kw_branches.py:158-197      GeneralBranch.get_keyword_cosine_score,
                                             GeneralBranch.vq_audio_features (identity projection)  (V1, V4)
   * avssl/module/speechclip_c_modules/my_vector_quantizer.py  SimpleVectorQuantizer.forward   (V3)
@@ -72,6 +74,56 @@ def golden_wsum():
         grads = torch.autograd.grad(y, [layer.weights] + layers, grad_outputs=gy)
         save(name, layers_tbd=torch.stack(storage), weights=layer.weights, normalize=np.array(norm),
              y=y, grad_y=gy, grad_weights=grads[0], grad_layers=torch.stack([x for x in grads[1:]]))
+
+
+# ----------------------------------------------------------------------------------------------
+def golden_s1_tail():
+    """Runs the reference's FairseqSpeechEncoder_Hubert.forward (speech_encoder_plus.py:518-622) around a stand-in
+    upstream model that returns fixed layer_results: exercises the method1 / method2 rescale loop (:572-592), the
+    feat_len arithmetic (:600-611) and the weighted-sum call (:619-622) exactly as shipped."""
+    ref.import_avssl()
+    import avssl.module.speech_encoder_plus as sep
+    cases = [
+        # name, L, B, T, D, normalize_hiddenstates, normalize_type, wav lengths
+        ("s1tail_method1", 13, 3, 5, 384, True, "method1", [1600, 1120, 801]),   # 1120/320 = 3.5 -> 4 (half to even)
+        ("s1tail_method2", 5, 3, 9, 256, True, "method2", [2880, 2400, 1761]),  # 2400/320 = 7.5 -> 8
+        ("s1tail_method2_large", 25, 2, 3, 1024, True, "method2", [960, 800]),    # 800/320 = 2.5 -> 2
+        ("s1tail_s3prl", 4, 3, 7, 192, True, "s3prl", [2240, 2239, 160]),
+        ("s1tail_plain", 4, 2, 5, 64, False, "s3prl", [1600, 4000]),  # 4000/320 = 12.5 -> clamped to T
+    ]
+    for i, (name, L, B, T, D, norm, ntype, wav_lens) in enumerate(cases):
+        g = _gen(500 + i)
+        storage = [torch.randn(T, B, D, generator=g) * (1.0 + 0.3 * l) + 0.1 * l for l in range(L)]
+        if name == "s1tail_method1":
+            storage[3][2, 1] = 0.0  # an all-zero frame: x / (0 + 1e-8) = 0, gradient g / 1e-8
+        layers = [s.transpose(0, 1).requires_grad_(True) for s in storage]
+
+        class FakeUpstream(torch.nn.Module):
+            def customHubertForward(self, wav, padding_mask=None, mask=None):
+                return {"layer_results": list(layers)}
+
+        enc = sep.FairseqSpeechEncoder_Hubert.__new__(sep.FairseqSpeechEncoder_Hubert)
+        torch.nn.Module.__init__(enc)
+        enc.encoder = FakeUpstream()
+        enc.encoder_task = types.SimpleNamespace(cfg=types.SimpleNamespace(normalize=False))
+        enc.trainable = True  # keeps the autograd graph through the rescale (else the upstream call is under no_grad)
+        enc.normalize_hiddenstates = norm
+        enc.normalize_type = ntype
+        enc.downsample_rate = 320
+        enc.max_audio_len = 102400
+        enc.feat_select_idx = "weighted_sum"
+        enc.weightedsum_layer = sep.WeightedSumLayer(n_weights=L, normalize_features=norm and ntype == "s3prl")
+        with torch.no_grad():
+            enc.weightedsum_layer.weights.copy_(torch.randn(L, generator=g) * 0.5)
+        enc.eval()  # no random crop
+        wav = [torch.randn(n, generator=g) for n in wav_lens]
+        y, feat_len = enc(wav)
+        gy = torch.randn(B, T, D, generator=g)
+        grads = torch.autograd.grad(y, [enc.weightedsum_layer.weights] + layers, grad_outputs=gy)
+        save(name, layers_tbd=torch.stack(storage), weights=enc.weightedsum_layer.weights,
+             normalize_hiddenstates=np.array(norm), normalize_type=np.array(ntype), wav_len=np.array(wav_lens),
+             y=y, feat_len=feat_len, grad_y=gy, grad_weights=grads[0],
+             grad_layers=torch.stack([x for x in grads[1:]]))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -211,6 +263,7 @@ if __name__ == "__main__":
     assert ref.reference_available(), "needs /root/reference"
     torch.set_num_threads(max(os.cpu_count() or 1, 1))
     golden_wsum()
+    golden_s1_tail()
     golden_vq()
     golden_nce()
     golden_hybrid_loss()

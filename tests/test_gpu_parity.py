@@ -52,6 +52,58 @@ def test_wsum_golden(scp, name):
     assert norm_err(torch.stack(grads[1:]), g["grad_layers"]) < TOL
 
 
+@pytest.mark.parametrize("name", golden_names("s1tail_"))
+def test_upstream_tail_golden(scp, name):
+    """S1' through fuse_upstream_features vs what the reference's HuBERT wrapper forward returned."""
+    from speechclip_plus_b200.module.speech_encoder_plus import fuse_upstream_features
+    g = load_golden(name)
+    L = g["layers_tbd"].shape[0]
+    norm, ntype = g["normalize_hiddenstates"], g["normalize_type"]
+    layer = scp.WeightedSumLayer(L, normalize_features=norm and ntype == "s3prl").cuda()  # speech_encoder_plus.py:472-476
+    with torch.no_grad():
+        layer.weights.copy_(g["weights"])
+    trainable_upstream = ntype != "method2"  # layer gradients through method2 are not implemented (documented)
+    layers = [t.cuda().transpose(0, 1).requires_grad_(trainable_upstream) for t in g["layers_tbd"]]
+    y, feat_len = fuse_upstream_features(layers, layer, norm, ntype, g["wav_len"].tolist(), 320)
+    assert torch.equal(feat_len.cpu(), g["feat_len"]) and feat_len.dtype == torch.int64 and feat_len.is_cuda
+    assert rel_err(y, g["y"]) < TOL
+    if trainable_upstream:
+        grads = torch.autograd.grad(y, [layer.weights] + layers, grad_outputs=g["grad_y"].cuda())
+        assert norm_err(torch.stack(grads[1:]), g["grad_layers"]) < TOL
+    else:
+        grads = torch.autograd.grad(y, [layer.weights], grad_outputs=g["grad_y"].cuda())
+        with pytest.raises(scp.ScpError):  # method2 with a trainable upstream: loud, not silent
+            xs = [t.cuda().transpose(0, 1).requires_grad_(True) for t in g["layers_tbd"]]
+            y2, _ = fuse_upstream_features(xs, layer, norm, ntype)
+            torch.autograd.grad(y2, xs[:1], grad_outputs=g["grad_y"].cuda())
+    assert rel_err(grads[0], g["grad_weights"]) < TOL
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("ntype", ["method1", "method2"])
+@pytest.mark.parametrize("shape", [(13, 8, 249, 768), (25, 3, 61, 1024)])
+def test_upstream_tail_vs_oracle(scp, shape, ntype, dtype):
+    from speechclip_plus_b200.module.speech_encoder_plus import fuse_upstream_features
+    L, B, T, D = shape
+    gen = torch.Generator().manual_seed(L * 100 + T)
+    storage = [(torch.randn(T, B, D, generator=gen) * (1 + 0.2 * l) + 0.05 * l).to(dtype) for l in range(L)]
+    w = torch.randn(L, generator=gen) * 0.5
+    gy = torch.randn(B, T, D, generator=gen)
+    layer = scp.WeightedSumLayer(L).cuda()
+    with torch.no_grad():
+        layer.weights.copy_(w)
+    wav_len = [320 * T - 37 * b for b in range(B)]
+    y, feat_len = fuse_upstream_features([s.cuda().transpose(0, 1) for s in storage], layer, True, ntype, wav_len)
+    (dw,) = torch.autograd.grad(y, [layer.weights], grad_outputs=gy.cuda())
+    ref_layers = [s.double().transpose(0, 1) for s in storage]
+    w_ref = w.double().requires_grad_(True)
+    y_ref, len_ref = oracle.upstream_tail(ref_layers, w_ref, True, ntype, wav_len)
+    (dw_ref,) = torch.autograd.grad(y_ref, [w_ref], grad_outputs=gy.double())
+    assert torch.equal(feat_len.cpu(), len_ref)
+    assert rel_err(y, y_ref) < TOL
+    assert rel_err(dw, dw_ref) < TOL
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("norm", [False, True])
 @pytest.mark.parametrize("shape", [(13, 8, 249, 768), (25, 3, 61, 1024), (5, 2, 7, 64)])

@@ -23,6 +23,23 @@ def test_weighted_sum_layer_contract():
         scp.WeightedSumLayer(n_weights=64)
 
 
+def test_upstream_tail_host_logic():
+    from speechclip_plus_b200.module.speech_encoder_plus import fuse_upstream_features, upstream_feat_len
+    # feat_len: Python round (half to even) then clamp to T (speech_encoder_plus.py:604-611)
+    fl = upstream_feat_len([800, 1120, 2400, 160, 99999], 320, 9)
+    assert fl.dtype == torch.int64 and fl.tolist() == [2, 4, 8, 0, 9]
+    assert scp.WeightedSumLayer(4, True, normalize_type="method1").normalize_type == "method1"
+    with pytest.raises(AssertionError):
+        scp.WeightedSumLayer(4, True, normalize_type="zscore")               # speech_encoder_plus.py:377
+    ln_layer = scp.WeightedSumLayer(3, normalize_features=True)
+    with pytest.raises(scp.ScpError):                                          # method* excludes the LN flag (:472-476)
+        fuse_upstream_features([torch.zeros(1, 2, 4)] * 3, ln_layer, True, "method2")
+    with pytest.raises(AssertionError):
+        fuse_upstream_features([torch.zeros(1, 2, 4)] * 2, ln_layer, False, "s3prl")
+    with pytest.raises(scp.ScpError):                                          # CPU tensors: no fallback
+        fuse_upstream_features([torch.zeros(1, 2, 4)] * 3, scp.WeightedSumLayer(3), True, "method1")
+
+
 def test_vector_quantizer_constructor_semantics():
     fixed = scp.SimpleVectorQuantizer("fixed=0.1")
     assert fixed.temp_type == "fixed" and "curr_temp" in dict(fixed.named_buffers())
