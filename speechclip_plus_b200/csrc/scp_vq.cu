@@ -46,6 +46,14 @@ __device__ __forceinline__ bool is_masked(const MaskedCols& mc, int c) {
   for (int i = 0; i < SCP_MAX_MASKED; ++i) m |= (i < mc.n && mc.col[i] == c);
   return m;
 }
+// bit i set <=> column col0 + i is masked or beyond the vocabulary (rare path: kept small, not unrolled over columns)
+__device__ __forceinline__ uint32_t chunk_mask_bits(const MaskedCols& mc, int col0, int V) {
+  uint32_t bits = col0 + 32 > V ? (col0 >= V ? 0xffffffffu : ~((1u << (V - col0)) - 1u)) : 0u;
+#pragma unroll
+  for (int i = 0; i < SCP_MAX_MASKED; ++i)
+    if (i < mc.n && (mc.col[i] >> 5) == (col0 >> 5)) bits |= 1u << (mc.col[i] & 31);
+  return bits;
+}
 __device__ __forceinline__ bool chunk_has_mask(const MaskedCols& mc, int col0) {
   bool m = false;
 #pragma unroll
@@ -140,16 +148,16 @@ __global__ void vq_prep_kw_kernel(const float* __restrict__ kw, int64_t M, int64
 // =====================================================================================================================
 // sweep 1: per-row statistics of S = khat * Ehat^T
 // =====================================================================================================================
-// x^N by repeated squaring, N known at compile time (no branches in the epilogue's inner loop)
+// x^N by repeated squaring on a packed pair, N known at compile time (no branches in the epilogue's inner loop)
 template <int N>
-__device__ __forceinline__ float ipow(float x) {
+__device__ __forceinline__ tc::f32x2 ipow2(tc::f32x2 x) {
   if constexpr (N == 1) {
     return x;
   } else if constexpr (N % 2 == 0) {
-    const float t = ipow<N / 2>(x);
-    return t * t;
+    const tc::f32x2 t = ipow2<N / 2>(x);
+    return tc::mul2(t, t);
   } else {
-    return x * ipow<N - 1>(x);
+    return tc::mul2(x, ipow2<N - 1>(x));
   }
 }
 
@@ -167,75 +175,85 @@ struct Sweep1Epi {
   const Params& p;
   int64_t row;
   int slot;
-  int n_pow;    // 1/tau when it is one of the integers {2,4,5,8,10,16,20} (every shipped recipe: tau = 0.1 -> 10), else 0
+  bool pow10;   // 1/tau == 10 (every shipped recipe: "fixed=0.1"): e^{c/tau} = (e^c)^10 by repeated squaring
   float k_tau;  // log2(e)/tau
-  float sum_e1, sum_ce1, run_max, sum_et;
+  // running sums as packed pairs (even / odd columns), two independent sets to shorten the dependency chains:
+  // sum e^c, sum c e^c, sum e^{(c - run_max)/tau}
+  tc::f32x2 acc_e[2], acc_ce[2], acc_et[2];
+  float run_max;
 
   __device__ __forceinline__ Sweep1Epi(const Params& p_, const WorkInfo& w, const tc::EpiCtx& ctx)
       : p(p_), row((int64_t)w.m_tile * tc::kTileM + ctx.row_in_tile), slot(w.n_group * 2 + ctx.half) {
     const float inv_tau = 1.0f / __ldg(p.tau);
     k_tau = kLog2e * inv_tau;
-    const float n = rintf(inv_tau);
-    const int ni = (int)n;
-    const bool supported = ni == 2 || ni == 4 || ni == 5 || ni == 8 || ni == 10 || ni == 16 || ni == 20;
-    n_pow = (supported && fabsf(inv_tau - n) <= 1e-5f * n) ? ni : 0;
-    sum_e1 = 0.f; sum_ce1 = 0.f; run_max = kNegBig; sum_et = 0.f;
+    pow10 = fabsf(inv_tau - 10.0f) <= 1e-4f;
+    const tc::f32x2 z = tc::pack2(0.f, 0.f);
+    acc_e[0] = acc_e[1] = acc_ce[0] = acc_ce[1] = acc_et[0] = acc_et[1] = z;
+    run_max = kNegBig;
   }
   __device__ __forceinline__ void tile_begin(int) {}
   __device__ __forceinline__ void tile_end(int) {}
   template <int N>
   __device__ __forceinline__ void pow_chunk(const float (&c)[32]) {
+    const tc::f32x2 kl = tc::pack2(kLog2e, kLog2e);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float e1 = tc::fast_ex2(c[i] * kLog2e);
-      sum_e1 += e1;
-      sum_ce1 = fmaf(c[i], e1, sum_ce1);
-      sum_et += ipow<N>(e1);
+    for (int i = 0; i < 32; i += 2) {
+      const int a = (i >> 1) & 1;
+      const tc::f32x2 cc = tc::pack2(c[i], c[i + 1]);
+      const tc::f32x2 e1 = tc::ex2_2(tc::mul2(cc, kl));
+      acc_e[a] = tc::add2(acc_e[a], e1);
+      acc_ce[a] = tc::fma2(cc, e1, acc_ce[a]);
+      acc_et[a] = tc::add2(acc_et[a], ipow2<N>(e1));
     }
   }
   __device__ __forceinline__ void chunk(int col0, float (&v)[1][32]) {
     float(&c)[32] = v[0];
     if (col0 + 32 > p.V || chunk_has_mask(p.mc, col0)) {
+      const uint32_t bits = chunk_mask_bits(p.mc, col0, p.V);
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        if (col0 + i >= p.V || is_masked(p.mc, col0 + i)) c[i] = kNegBig;
+        if ((bits >> i) & 1u) c[i] = kNegBig;
     }
-    float cmax = c[0];
+    // 3-input max tree (FMNMX3): 16 instructions for 32 values
+    float m8[11];
 #pragma unroll
-    for (int i = 1; i < 32; ++i) cmax = fmaxf(cmax, c[i]);
+    for (int i = 0; i < 10; ++i) m8[i] = tc::fmax3(c[3 * i], c[3 * i + 1], c[3 * i + 2]);
+    m8[10] = fmaxf(c[30], c[31]);
+    const float m3a = tc::fmax3(m8[0], m8[1], m8[2]), m3b = tc::fmax3(m8[3], m8[4], m8[5]);
+    const float m3c = tc::fmax3(m8[6], m8[7], m8[8]), m3d = fmaxf(m8[9], m8[10]);
+    const float cmax = fmaxf(tc::fmax3(m3a, m3b, m3c), m3d);
     p.chunk_max[row * p.n_chunks + (col0 >> 5)] = cmax;
     if (cmax <= kNegBig) return;  // fully masked / padding chunk: contributes nothing (and has no finite maximum)
-    if (n_pow) {
-      // |c| <= 1 and 1/tau = n <= 20: e^{c/tau} = (e^c)^n cannot overflow, so no running maximum is needed and the
-      // second exponential becomes a few multiplies (repeated squaring) -- ONE SFU op per logit instead of two
-      // (the SFU does only 4 lanes/clk per sub-partition and bounds this epilogue otherwise)
+    if (pow10) {
+      // |c| <= 1 and 1/tau = 10: e^{c/tau} = (e^c)^10 cannot overflow, so no running maximum is needed and the
+      // second exponential becomes four packed multiplies -- ONE SFU op per logit instead of two.  Only this one
+      // specialisation is compiled: every extra variant is another unrolled copy of the loop in the instruction cache.
       run_max = 0.f;  // the partial sum is relative to a shift of 0
-      switch (n_pow) {
-        case 2: pow_chunk<2>(c); break;
-        case 4: pow_chunk<4>(c); break;
-        case 5: pow_chunk<5>(c); break;
-        case 8: pow_chunk<8>(c); break;
-        case 10: pow_chunk<10>(c); break;
-        case 16: pow_chunk<16>(c); break;
-        default: pow_chunk<20>(c); break;
-      }
+      pow_chunk<10>(c);
       return;
     }
     if (cmax > run_max) {  // rescale the temperature-tau sum to the new running maximum
-      sum_et *= tc::fast_ex2((run_max - cmax) * k_tau);
+      const float f = tc::fast_ex2((run_max - cmax) * k_tau);
+      const tc::f32x2 ff = tc::pack2(f, f);
+      acc_et[0] = tc::mul2(acc_et[0], ff);
+      acc_et[1] = tc::mul2(acc_et[1], ff);
       run_max = cmax;
     }
-    const float shift = run_max * k_tau;
+    const float shift = -run_max * k_tau;
+    const tc::f32x2 kl = tc::pack2(kLog2e, kLog2e), kt = tc::pack2(k_tau, k_tau), sh = tc::pack2(shift, shift);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float e1 = tc::fast_ex2(c[i] * kLog2e);  // |c| <= 1: no shift needed at temperature 1
-      sum_e1 += e1;
-      sum_ce1 = fmaf(c[i], e1, sum_ce1);
-      sum_et += tc::fast_ex2(fmaf(c[i], k_tau, -shift));
+    for (int i = 0; i < 32; i += 2) {
+      const int a = (i >> 1) & 1;
+      const tc::f32x2 cc = tc::pack2(c[i], c[i + 1]);
+      const tc::f32x2 e1 = tc::ex2_2(tc::mul2(cc, kl));  // |c| <= 1: no shift needed at temperature 1
+      acc_e[a] = tc::add2(acc_e[a], e1);
+      acc_ce[a] = tc::fma2(cc, e1, acc_ce[a]);
+      acc_et[a] = tc::add2(acc_et[a], tc::ex2_2(tc::fma2(cc, kt, sh)));
     }
   }
   __device__ __forceinline__ void finish() {
-    float4 o = make_float4(sum_e1, sum_ce1, run_max, sum_et);
+    float4 o = make_float4(tc::hsum2(tc::add2(acc_e[0], acc_e[1])), tc::hsum2(tc::add2(acc_ce[0], acc_ce[1])), run_max,
+                           tc::hsum2(tc::add2(acc_et[0], acc_et[1])));
     *reinterpret_cast<float4*>(p.partials + (row * (2 * p.n_groups) + slot) * 4) = o;
   }
 };
@@ -432,40 +450,59 @@ vq_select_kernel(const float* __restrict__ kw, const float* __restrict__ table, 
 __global__ void vq_lse_to_log2_kernel(const float* __restrict__ row_stats, int64_t M, int64_t Mp2,
                                       float* __restrict__ lse1_l2) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m < Mp2) lse1_l2[m] = m < M ? row_stats[m * 4] * kLog2e : 1.0e30f;  // padding columns contribute exp2(-1e30) = 0
+  // stored NEGATED (the epilogue adds it with one packed FMA); padding columns contribute exp2(-1e30) = 0
+  if (m < Mp2) lse1_l2[m] = m < M ? -row_stats[m * 4] * kLog2e : -1.0e30f;
 }
 
 struct Sweep2Epi {
   struct Params {
-    const float* lse1_l2;  // (Mp2,) lse at temperature 1 times log2(e); +1e30 for padding
+    const float* lse1_l2;  // (Mp2,) MINUS lse at temperature 1 times log2(e); -1e30 for padding
     float* avg_probs;      // (Vp,)
     float inv_m;
     int V;
     MaskedCols mc;
   };
-  static constexpr int kSmemBytes = tc::kTileM * 4;
+  // [128 floats: half-1 partial sums][per warp: the 128 normalisers of the columns it consumes in the current tile]
+  static constexpr int kWarpVec = 128 * 4;
+  static constexpr int kSmemBytes = tc::kTileM * 4 + tc::kEpiWarps * kWarpVec;
   const Params& p;
-  int v, half, row_in_tile;
-  float acc;
+  int v, half, row_in_tile, lane, nt_stride, nt_end;
+  tc::f32x2 acc2[2];
   float* s_acc;
+  uint32_t wsm;  // shared address of this warp's normaliser vector
+  float4 pre;    // normalisers of the NEXT tile, fetched one tile ahead (a per-chunk __ldg sat on the critical path:
+                 // ncu attributed 18 % of all stall samples to its long-scoreboard wait)
+  __device__ __forceinline__ const float4* vec_src(int nt) const {
+    return reinterpret_cast<const float4*>(p.lse1_l2 + (int64_t)nt * 256 + half * 128) + lane;
+  }
   __device__ __forceinline__ Sweep2Epi(const Params& p_, const WorkInfo& w, const tc::EpiCtx& ctx)
-      : p(p_), v(w.m_tile * tc::kTileM + ctx.row_in_tile), half(ctx.half), row_in_tile(ctx.row_in_tile), acc(0.f),
-        s_acc(reinterpret_cast<float*>(ctx.smem)) {}
-  __device__ __forceinline__ void tile_begin(int) {}
+      : p(p_), v(w.m_tile * tc::kTileM + ctx.row_in_tile), half(ctx.half), row_in_tile(ctx.row_in_tile),
+        lane(ctx.tid & 31), nt_stride(w.nt_stride), nt_end(w.nt_end), s_acc(reinterpret_cast<float*>(ctx.smem)) {
+    acc2[0] = acc2[1] = tc::pack2(0.f, 0.f);
+    wsm = tc::smem_u32(ctx.smem + tc::kTileM * 4 + (ctx.tid >> 5) * kWarpVec);
+    pre = w.nt_first < w.nt_end ? __ldg(vec_src(w.nt_first)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __device__ __forceinline__ void tile_begin(int nt) {
+    __syncwarp();  // the previous tile's reads of the vector are complete
+    tc::sts128f(wsm + lane * 16, pre);
+    __syncwarp();
+    const int next = nt + nt_stride;
+    if (next < nt_end) pre = __ldg(vec_src(next));
+  }
   __device__ __forceinline__ void tile_end(int) {}
   __device__ __forceinline__ void chunk(int col0, float (&c)[1][32]) {
-    const float4* l4 = reinterpret_cast<const float4*>(p.lse1_l2 + col0);
+    const uint32_t src = wsm + (uint32_t)(col0 & 127) * 4;  // NEGATED lse * log2(e) of the 32 columns (broadcast reads)
+    const tc::f32x2 kl = tc::pack2(kLog2e, kLog2e);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float4 l = __ldg(l4 + i);
-      acc += tc::fast_ex2(fmaf(c[0][4 * i + 0], kLog2e, -l.x));
-      acc += tc::fast_ex2(fmaf(c[0][4 * i + 1], kLog2e, -l.y));
-      acc += tc::fast_ex2(fmaf(c[0][4 * i + 2], kLog2e, -l.z));
-      acc += tc::fast_ex2(fmaf(c[0][4 * i + 3], kLog2e, -l.w));
+      const float4 l = tc::lds128f(src + i * 16);
+      acc2[0] = tc::add2(acc2[0], tc::ex2_2(tc::fma2(tc::pack2(c[0][4 * i + 0], c[0][4 * i + 1]), kl, tc::pack2(l.x, l.y))));
+      acc2[1] = tc::add2(acc2[1], tc::ex2_2(tc::fma2(tc::pack2(c[0][4 * i + 2], c[0][4 * i + 3]), kl, tc::pack2(l.z, l.w))));
     }
   }
   __device__ __forceinline__ void finish() {
     // the two warps that own a row add their halves in a fixed order
+    const float acc = tc::hsum2(tc::add2(acc2[0], acc2[1]));
     if (half == 1) s_acc[row_in_tile] = acc;
     tc::named_bar_sync(tc::kEpiBarrierId, tc::kEpiThreads);
     if (half == 0) p.avg_probs[v] = (v < p.V && !is_masked(p.mc, v)) ? (acc + s_acc[row_in_tile]) * p.inv_m : 0.f;
@@ -572,81 +609,101 @@ struct Sweep3Epi {
     const float* table_mean;  // [D] = norm_ref
     const float* tau;
     __half* pq;               // (2*Mp, Vp): rows [0,Mp) = Q~, rows [Mp,2Mp) = P~
-    float* partials;          // (Mp, 2*n_groups, 4): sum Q, sum P, sum Q c, sum P c
+    float* partials;          // (Mp, 2*n_groups, 4): sum Q~, sum P~, sum Q~ c, sum P~ c   (all carry the 2^14 scale)
     int64_t M, Mp, Vp;
     int n_groups, V, D;
+    int want_tau;             // accumulate the two c-weighted sums (only the learnable-temperature gradient needs them)
     MaskedCols mc;
   };
   // Each warp owns a private 4 KB staging area (32 rows x 32 columns of Q~ and of P~): the accumulator layout gives
   // every lane one ROW, but a store instruction in which 32 lanes touch 32 different rows costs 32 LSU transactions;
   // transposing through shared memory turns it into 64-byte row segments (8 rows per instruction, full sectors).
   static constexpr int kWarpStage = 2 * 32 * 64;
-  static constexpr int kSmemBytes = tc::kEpiWarps * kWarpStage;
+  static constexpr int kWarpVec = 64 * 4;  // table norms of the 64 columns a warp consumes per tile
+  static constexpr int kSmemBytes = tc::kEpiWarps * (kWarpStage + kWarpVec);
   const Params& p;
   int64_t row, row0;
-  int slot, lane;
-  uint8_t* stage;
-  float k_tau, lse_l2, s0, inv_norm_ref;
-  float sq, sp, sqc, spc;
+  int slot, lane, half, nt_stride, nt_end;
+  uint32_t stage;  // shared address of this warp's staging area
+  uint32_t wsm;    // shared address of this warp's column-norm vector
+  float4 pre;      // column norms of the NEXT tile, fetched one tile ahead (see Sweep2Epi)
+  float k_tau, bias, s0, inv_norm_ref;  // bias = log2(kPScale) - lse_tau*log2(e): P~ = 2^(c*k_tau + bias)
+  tc::f32x2 acc_q, acc_p, acc_qc, acc_pc;
+  __device__ __forceinline__ const float4* vec_src(int nt) const {
+    return reinterpret_cast<const float4*>(p.table_norm + (int64_t)nt * 128 + half * 64) + (lane & 15);
+  }
   __device__ __forceinline__ Sweep3Epi(const Params& p_, const WorkInfo& w, const tc::EpiCtx& ctx)
-      : p(p_), row((int64_t)w.m_tile * tc::kTileM + ctx.row_in_tile), slot(w.n_group * 2 + ctx.half) {
+      : p(p_), row((int64_t)w.m_tile * tc::kTileM + ctx.row_in_tile), slot(w.n_group * 2 + ctx.half),
+        half(ctx.half), nt_stride(w.nt_stride), nt_end(w.nt_end) {
     lane = ctx.tid & 31;
     row0 = row - lane;
-    stage = ctx.smem + (ctx.tid >> 5) * kWarpStage;
+    stage = tc::smem_u32(ctx.smem + (ctx.tid >> 5) * kWarpStage);
+    wsm = tc::smem_u32(ctx.smem + tc::kEpiWarps * kWarpStage + (ctx.tid >> 5) * kWarpVec);
+    pre = w.nt_first < w.nt_end ? __ldg(vec_src(w.nt_first)) : make_float4(0.f, 0.f, 0.f, 0.f);
     k_tau = kLog2e / __ldg(p.tau);
     const bool valid = row < p.M;
-    lse_l2 = valid ? p.row_stats[row * 4 + 1] * kLog2e : 1.0e30f;  // padding rows: P = 0
+    bias = valid ? 14.0f - p.row_stats[row * 4 + 1] * kLog2e : -1.0e30f;  // 2^14 = kPScale; padding rows: P = 0
     s0 = p.g_aux[row * 2 + 1];
     inv_norm_ref = 1.0f / p.table_mean[p.D];
-    sq = sp = sqc = spc = 0.f;
+    acc_q = acc_p = acc_qc = acc_pc = tc::pack2(0.f, 0.f);
   }
-  __device__ __forceinline__ void tile_begin(int) {}
+  __device__ __forceinline__ void tile_begin(int nt) {
+    __syncwarp();  // the previous tile's reads of the vector are complete
+    // staged as r_v = ||e_v|| / norm_ref, so that T' = (ghat . ehat_v) * r_v - s0 is one FMA per logit
+    if (lane < 16)
+      tc::sts128f(wsm + lane * 16, make_float4(pre.x * inv_norm_ref, pre.y * inv_norm_ref, pre.z * inv_norm_ref,
+                                               pre.w * inv_norm_ref));
+    __syncwarp();
+    const int next = nt + nt_stride;
+    if (next < nt_end) pre = __ldg(vec_src(next));
+  }
   __device__ __forceinline__ void tile_end(int) {}
   __device__ __forceinline__ void chunk(int col0, float (&v)[2][32]) {
     float(&c)[32] = v[0];
     float(&t)[32] = v[1];
     if (col0 + 32 > p.V || chunk_has_mask(p.mc, col0)) {
+      const uint32_t bits = chunk_mask_bits(p.mc, col0, p.V);
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        if (col0 + i >= p.V || is_masked(p.mc, col0 + i)) c[i] = kNegBig;
+        if ((bits >> i) & 1u) c[i] = kNegBig;
     }
-    const float4* n4 = reinterpret_cast<const float4*>(p.table_norm + col0);
+    const uint32_t n_src = wsm + (uint32_t)(col0 & 63) * 4;  // ||e_v|| of the 32 columns (broadcast reads)
     // staging layout: row r at r*64 B, its four 16-byte units XOR-swizzled with (r >> 1) & 3 (conflict-free both ways)
-    uint8_t* qs = stage + lane * 64;
-    uint8_t* ps = stage + 32 * 64 + lane * 64;
+    const uint32_t qs = stage + lane * 64;
+    const uint32_t ps = stage + 32 * 64 + lane * 64;
     const int sw = (lane >> 1) & 3;
+    const tc::f32x2 kt2 = tc::pack2(k_tau, k_tau), b2 = tc::pack2(bias, bias), ns0 = tc::pack2(-s0, -s0);
     __syncwarp();  // the previous chunk's read-out of the staging area is complete
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       uint32_t pk_q[4], pk_p[4];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const float4 nv = __ldg(n4 + 2 * i + h);
-        const float nn[4] = {nv.x, nv.y, nv.z, nv.w};
-        float pv[4], qv[4];
+        const float4 rv = tc::lds128f(n_src + (2 * i + h) * 16);
+        const tc::f32x2 rr[2] = {tc::pack2(rv.x, rv.y), tc::pack2(rv.z, rv.w)};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int e = 8 * i + 4 * h + j;
-          const float cc = c[e];
-          const float pj = tc::fast_ex2(fmaf(cc, k_tau, -lse_l2));        // softmax_tau
-          const float tj = fmaf(t[e] * nn[j], inv_norm_ref, -s0);          // (g . e_v)/(|g| norm_ref) - s0
-          const float qj = pj * tj;
-          sp += pj;
-          sq += qj;
-          const float cf = cc > -2.f ? cc : 0.f;
-          spc = fmaf(pj, cf, spc);
-          sqc = fmaf(qj, cf, sqc);
-          pv[j] = pj * kPScale;
-          qv[j] = qj * kPScale;
+        for (int j = 0; j < 2; ++j) {  // packed pairs of adjacent columns
+          const int e = 8 * i + 4 * h + 2 * j;
+          const tc::f32x2 cc = tc::pack2(c[e], c[e + 1]);
+          const tc::f32x2 pj = tc::ex2_2(tc::fma2(cc, kt2, b2));               // P~ = 2^14 softmax_tau
+          const tc::f32x2 tj = tc::fma2(tc::pack2(t[e], t[e + 1]), rr[j], ns0);  // (g . e_v)/(|g| norm_ref) - s0
+          const tc::f32x2 qj = tc::mul2(pj, tj);
+          acc_p = tc::add2(acc_p, pj);
+          acc_q = tc::add2(acc_q, qj);
+          if (p.want_tau) {  // masked columns: P~ = 0 exactly and c = -1e30 is finite, so the products vanish
+            acc_pc = tc::fma2(pj, cc, acc_pc);
+            acc_qc = tc::fma2(qj, cc, acc_qc);
+          }
+          float a, b;
+          __half2 hh;
+          tc::unpack2(qj, a, b);
+          hh = __floats2half2_rn(a, b); pk_q[2 * h + j] = *reinterpret_cast<uint32_t*>(&hh);
+          tc::unpack2(pj, a, b);
+          hh = __floats2half2_rn(a, b); pk_p[2 * h + j] = *reinterpret_cast<uint32_t*>(&hh);
         }
-        __half2 hh;
-        hh = __floats2half2_rn(qv[0], qv[1]); pk_q[2 * h] = *reinterpret_cast<uint32_t*>(&hh);
-        hh = __floats2half2_rn(qv[2], qv[3]); pk_q[2 * h + 1] = *reinterpret_cast<uint32_t*>(&hh);
-        hh = __floats2half2_rn(pv[0], pv[1]); pk_p[2 * h] = *reinterpret_cast<uint32_t*>(&hh);
-        hh = __floats2half2_rn(pv[2], pv[3]); pk_p[2 * h + 1] = *reinterpret_cast<uint32_t*>(&hh);
       }
-      *reinterpret_cast<uint4*>(qs + ((i ^ sw) << 4)) = make_uint4(pk_q[0], pk_q[1], pk_q[2], pk_q[3]);
-      *reinterpret_cast<uint4*>(ps + ((i ^ sw) << 4)) = make_uint4(pk_p[0], pk_p[1], pk_p[2], pk_p[3]);
+      tc::sts128(qs + ((i ^ sw) << 4), make_uint4(pk_q[0], pk_q[1], pk_q[2], pk_q[3]));
+      tc::sts128(ps + ((i ^ sw) << 4), make_uint4(pk_p[0], pk_p[1], pk_p[2], pk_p[3]));
     }
     __syncwarp();
     // read-out: instruction k covers rows 8k..8k+7, four lanes per row -> 64-byte contiguous global segments
@@ -655,15 +712,16 @@ struct Sweep3Epi {
       const int r = 8 * k + (lane >> 2);
       const int u = lane & 3;
       const int off = r * 64 + ((u ^ ((r >> 1) & 3)) << 4);
-      const uint4 q4 = *reinterpret_cast<const uint4*>(stage + off);
-      const uint4 p4 = *reinterpret_cast<const uint4*>(stage + 32 * 64 + off);
+      const uint4 q4 = tc::lds128(stage + off);
+      const uint4 p4 = tc::lds128(stage + 32 * 64 + off);
       const int64_t grow = row0 + r;
       *reinterpret_cast<uint4*>(p.pq + grow * p.Vp + col0 + u * 8) = q4;
       *reinterpret_cast<uint4*>(p.pq + (p.Mp + grow) * p.Vp + col0 + u * 8) = p4;
     }
   }
   __device__ __forceinline__ void finish() {
-    *reinterpret_cast<float4*>(p.partials + (row * (2 * p.n_groups) + slot) * 4) = make_float4(sq, sp, sqc, spc);
+    *reinterpret_cast<float4*>(p.partials + (row * (2 * p.n_groups) + slot) * 4) =
+        make_float4(tc::hsum2(acc_q), tc::hsum2(acc_p), tc::hsum2(acc_qc), tc::hsum2(acc_pc));
   }
 };
 
@@ -740,7 +798,7 @@ __global__ void vq_bwd_finalize_kernel(const float* __restrict__ uw /* (k_splits
   }
   if (g_tau && lane == 0) {
     // d/dtau = -(1/tau^2) sum_v P (T - s) c      (T in true units = T' * |g| * norm_ref)
-    const float contrib = -(g_aux[m * 2] * table_mean[D]) * (sqc - s_adj * spc) / (tau * tau);
+    const float contrib = -(g_aux[m * 2] * table_mean[D]) * (sqc - s_adj * spc) / (kPScale * tau * tau);
     atomicAdd(g_tau, contrib);
   }
 }
@@ -893,6 +951,12 @@ struct VqFwdWs {
 static bool vq_use_pair(int m_tiles) { return m_tiles >= 2; }
 static int vq_m_ctas(int m_tiles) { return vq_use_pair(m_tiles) ? 2 * (int)ceil_div(m_tiles, 2) : m_tiles; }
 
+// bring-up switch: SCP_VQ_RESIDENT=0 selects the streaming-X kernels (A/B measurement of the resident-X mode)
+static bool vq_resident_enabled() {
+  static const bool on = [] { const char* e = getenv("SCP_VQ_RESIDENT"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 static int vq_sweep1_groups(int64_t Mp, int64_t Vp) {
   const int m_tiles = (int)(Mp / tc::kTileM);
   const int n_tiles = (int)(Vp / kVqBN);
@@ -1043,7 +1107,11 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
     ep.n_groups = ws.n_groups;
     ep.V = (int)V;
     ep.mc = mc;
-    if (pair) rc = tc::launch_stream_gemm<kVqBN, 1, 6, Sweep1Epi, 2, tc::MC_PAIR>(maps, sc, ep, s, "vq_sweep1");
+    // resident keyword tile (128 x D fp16) when it fits next to a 6-stage ring of table half-tiles (D <= 512)
+    const bool xres = pair && vq_resident_enabled() &&
+                      tc::resident_smem_bytes<kVqBN, 1, 6, Sweep1Epi, tc::MC_PAIR>(sc.k_chunks) <= tc::kMaxDynSmem;
+    if (xres) rc = tc::launch_stream_gemm<kVqBN, 1, 6, Sweep1Epi, 2, tc::MC_PAIR, true>(maps, sc, ep, s, "vq_sweep1");
+    else if (pair) rc = tc::launch_stream_gemm<kVqBN, 1, 6, Sweep1Epi, 2, tc::MC_PAIR>(maps, sc, ep, s, "vq_sweep1");
     else rc = tc::launch_stream_gemm<kVqBN, 1, 4, Sweep1Epi>(maps, sc, ep, s, "vq_sweep1");
     if (rc) return rc;
   }
@@ -1083,7 +1151,11 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
     ep.inv_m = 1.0f / (float)M;
     ep.V = (int)V;
     ep.mc = mc;
-    if ((rc = tc::launch_stream_gemm<256, 1, 6, Sweep2Epi, 2, tc::MC_PAIR>(maps, sc, ep, s, "vq_sweep2"))) return rc;
+    const bool xres = vq_resident_enabled() &&
+                      tc::resident_smem_bytes<256, 1, 5, Sweep2Epi, tc::MC_PAIR>(sc.k_chunks) <= tc::kMaxDynSmem;
+    if (xres) rc = tc::launch_stream_gemm<256, 1, 5, Sweep2Epi, 2, tc::MC_PAIR, true>(maps, sc, ep, s, "vq_sweep2");
+    else rc = tc::launch_stream_gemm<256, 1, 6, Sweep2Epi, 2, tc::MC_PAIR>(maps, sc, ep, s, "vq_sweep2");
+    if (rc) return rc;
   }
   vq_metrics_partial_kernel<<<kMetricBlocks, 256, 0, s>>>(code_hist, avg_probs, M, (int)V, ws.metric_part);
   SCP_CUDA_LAUNCH_CHECK("vq_metrics_partial");
@@ -1152,6 +1224,7 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
     ep.n_groups = ws.n_groups;
     ep.V = (int)V;
     ep.D = (int)D;
+    ep.want_tau = g_tau != nullptr;
     ep.mc = mc;
     if (pair) rc = tc::launch_stream_gemm<128, 2, 4, Sweep3Epi, 2, tc::MC_PAIR>(maps, sc, ep, s, "vq_sweep3");
     else rc = tc::launch_stream_gemm<128, 2, 3, Sweep3Epi>(maps, sc, ep, s, "vq_sweep3");
