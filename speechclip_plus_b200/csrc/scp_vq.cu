@@ -122,10 +122,18 @@ __global__ void vq_table_mean_kernel(const float* __restrict__ table, int64_t V,
   atomicAdd(&mean[d], s / (float)V);
 }
 
-// warp <-> keyword row: unit-normalise into fp16 (zero rows for m >= M), 1/max(||kw||,1e-8) -> row_stats[m][3]
+// warp <-> keyword row: unit-normalise into fp16 (zero rows for m >= M), 1/max(||kw||,1e-8) -> row_stats[m][3].
+// Also clears the code histogram and presets the padding entries of the sweep-2 normaliser vector (two memsets /
+// helper launches folded into this one: the forward is a chain of short kernels and every launch costs ~3 us).
 __global__ void vq_prep_kw_kernel(const float* __restrict__ kw, int64_t M, int64_t Mp, int D,
-                                  __half* __restrict__ kw_hat, float* __restrict__ row_stats) {
+                                  __half* __restrict__ kw_hat, float* __restrict__ row_stats,
+                                  float* __restrict__ code_hist, int64_t Vp, float* __restrict__ lse1_l2, int64_t Mp2,
+                                  unsigned int* __restrict__ ticket) {
   const int lane = threadIdx.x & 31;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+  if (gtid == 0) *ticket = 0u;  // the metrics kernel's last-block ticket
+  for (int64_t v = gtid; v < Vp; v += gsz) code_hist[v] = 0.f;
+  for (int64_t i = M + gtid; i < Mp2; i += gsz) lse1_l2[i] = -1.0e30f;  // padding columns contribute exp2(-1e30) = 0
   const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= Mp) return;
   __half* dst = kw_hat + m * D;
@@ -352,7 +360,8 @@ __global__ void __launch_bounds__(128)
 vq_select_kernel(const float* __restrict__ kw, const float* __restrict__ table, const float* __restrict__ table_norm,
                  int64_t M, int V, int D, const float* __restrict__ chunk_max, int n_chunks, const float* __restrict__ partials, int n_groups,
                  const float* __restrict__ tau_ptr, MaskedCols mc, int64_t* __restrict__ idx_out,
-                 float* __restrict__ keywords, float* __restrict__ row_stats, float* __restrict__ code_hist) {
+                 float* __restrict__ keywords, float* __restrict__ row_stats, float* __restrict__ code_hist,
+                 float* __restrict__ lse1_l2) {
   __shared__ float s_red[4];
   __shared__ Best s_best[4];
   __shared__ int s_cand[kSelMaxCand];
@@ -437,6 +446,7 @@ vq_select_kernel(const float* __restrict__ kw, const float* __restrict__ table, 
     rs[0] = lse1;
     rs[1] = gmax / tau + logf(zt);
     rs[2] = ent;
+    lse1_l2[m] = -lse1 * kLog2e;  // sweep 2 adds it with one packed FMA
   }
   // keywords = E[k]   (value of subword_prob @ E, kw_branches.py:195)
   const float4* src = reinterpret_cast<const float4*>(table + (int64_t)k * D);
@@ -447,13 +457,6 @@ vq_select_kernel(const float* __restrict__ kw, const float* __restrict__ table, 
 // =====================================================================================================================
 // sweep 2: avg_probs[v] = (1/M) sum_m exp(c[m,v] - lse1[m])       X = Ehat (rows v), Y = khat (rows m)
 // =====================================================================================================================
-__global__ void vq_lse_to_log2_kernel(const float* __restrict__ row_stats, int64_t M, int64_t Mp2,
-                                      float* __restrict__ lse1_l2) {
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  // stored NEGATED (the epilogue adds it with one packed FMA); padding columns contribute exp2(-1e30) = 0
-  if (m < Mp2) lse1_l2[m] = m < M ? -row_stats[m * 4] * kLog2e : -1.0e30f;
-}
-
 struct Sweep2Epi {
   struct Params {
     const float* lse1_l2;  // (Mp2,) MINUS lse at temperature 1 times log2(e); -1e30 for padding
@@ -514,11 +517,16 @@ struct Sweep2Epi {
 // =====================================================================================================================
 constexpr int kMetricBlocks = 64;
 
-// stage 1: per-block partial sums of h log(h + 1e-7) over the code histogram and the average softmax
+// Stage 1 (all blocks): per-block partial sums of h log(h + 1e-7) over the code histogram and the average softmax.
+// Stage 2 (the block that draws the last ticket): fixed-order sum of the partials, perplexities, diversity loss,
+// ent_per_t.  `ticket` must be zero on entry (vq_prep_kw / a memset clears it) and is left at zero.
 __global__ void __launch_bounds__(256)
-vq_metrics_partial_kernel(const float* __restrict__ code_hist, const float* __restrict__ avg_probs, int64_t M, int V,
-                          float* __restrict__ partial /* (kMetricBlocks, 2) */) {
+vq_metrics_kernel(const float* __restrict__ code_hist, const float* __restrict__ avg_probs,
+                  const float* __restrict__ row_stats, int64_t M, int K, int V,
+                  float* __restrict__ partial /* (kMetricBlocks, 2) */, unsigned int* __restrict__ ticket,
+                  float* __restrict__ metrics) {
   __shared__ float s_red[2][8];
+  __shared__ bool s_last;
   const float inv_m = 1.0f / (float)M;
   float hc = 0.f, hp = 0.f;
   for (int v = blockIdx.x * 256 + threadIdx.x; v < V; v += kMetricBlocks * 256) {
@@ -537,33 +545,34 @@ vq_metrics_partial_kernel(const float* __restrict__ code_hist, const float* __re
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += s_red[threadIdx.x][i];
-    partial[blockIdx.x * 2 + threadIdx.x] = t;
+    __stcg(&partial[blockIdx.x * 2 + threadIdx.x], t);
   }
-}
-
-// stage 2 (one block): fixed-order sum of the partials, perplexities, diversity loss, ent_per_t
-__global__ void __launch_bounds__(256)
-vq_metrics_kernel(const float* __restrict__ partial, int has_avg, const float* __restrict__ row_stats, int64_t M,
-                  int K, int V, float* __restrict__ metrics) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == (unsigned)kMetricBlocks - 1u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
   if (threadIdx.x < 32) {
-    float hc = 0.f, hp = 0.f;
-    for (int i = threadIdx.x; i < kMetricBlocks; i += 32) { hc += partial[2 * i]; hp += partial[2 * i + 1]; }
-    hc = warp_sum(hc);
-    hp = warp_sum(hp);
+    float hc2 = 0.f, hp2 = 0.f;
+    for (int i = threadIdx.x; i < kMetricBlocks; i += 32) { hc2 += __ldcg(&partial[2 * i]); hp2 += __ldcg(&partial[2 * i + 1]); }
+    hc2 = warp_sum(hc2);
+    hp2 = warp_sum(hp2);
     if (threadIdx.x == 0) {
-      metrics[0] = expf(-hc);
-      const float pp = has_avg ? expf(-hp) : nanf("");
+      metrics[0] = expf(-hc2);
+      const float pp = avg_probs ? expf(-hp2) : nanf("");
       metrics[1] = pp;
       metrics[2] = ((float)V - pp) / (float)V;  // diversity_loss, :155-158
+      *ticket = 0u;
     }
   }
   // ent_per_t[i] = mean_b entropy[b*K + i]     (:104-116)
   const int64_t Bsz = M / K;
   for (int i = threadIdx.x >> 5; i < K; i += (blockDim.x >> 5)) {
-    float s = 0.f;
-    for (int64_t b = threadIdx.x & 31; b < Bsz; b += 32) s += row_stats[(b * K + i) * 4 + 2];
-    s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) metrics[3 + i] = s / (float)Bsz;
+    float sum = 0.f;
+    for (int64_t b = threadIdx.x & 31; b < Bsz; b += 32) sum += row_stats[(b * K + i) * 4 + 2];
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) metrics[3 + i] = sum / (float)Bsz;
   }
 }
 
@@ -979,7 +988,7 @@ static VqFwdWs vq_fwd_ws(void* base, int64_t M, int64_t V) {
   w.chunk_max = static_cast<float*>(take((size_t)Mp * w.n_chunks * 4));
   w.partials = static_cast<float*>(take((size_t)Mp * w.n_groups * 2 * 16));
   w.lse1_l2 = static_cast<float*>(take((size_t)round_up(M, 256) * 4));
-  w.metric_part = static_cast<float*>(take((size_t)kMetricBlocks * 2 * 4));
+  w.metric_part = static_cast<float*>(take((size_t)(kMetricBlocks * 2 + 1) * 4));  // + the ticket counter
   w.total = off;
   return w;
 }
@@ -1080,9 +1089,9 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
   const MaskedCols mc = make_masked(masked_cols, n_masked);
 
   vq_prep_kw_kernel<<<(unsigned)ceil_div(Mp, 8), 256, 0, s>>>(kw, M, Mp, (int)D, reinterpret_cast<__half*>(kw_hat),
-                                                              row_stats);
+                                                              row_stats, code_hist, Vp, ws.lse1_l2, round_up(M, 256),
+                                                              reinterpret_cast<unsigned int*>(ws.metric_part + kMetricBlocks * 2));
   SCP_CUDA_LAUNCH_CHECK("vq_prep_kw");
-  if (cudaMemsetAsync(code_hist, 0, (size_t)Vp * 4, s) != cudaSuccess) return fail(SCP_ERR_CUDA, "memset code_hist");
 
   // ---- sweep 1
   {
@@ -1119,7 +1128,7 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
 #define SCP_SELECT(NVV)                                                                                              \
   vq_select_kernel<NVV><<<(unsigned)M, 128, 0, s>>>(kw, table, table_norm, M, (int)V, (int)D, ws.chunk_max, ws.n_chunks, \
                                                     ws.partials, 2 * ws.n_groups, tau, mc, idx, keywords, row_stats, \
-                                                    code_hist)
+                                                    code_hist, ws.lse1_l2)
   if (D <= 128) SCP_SELECT(1);
   else if (D <= 256) SCP_SELECT(2);
   else if (D <= 512) SCP_SELECT(4);
@@ -1131,8 +1140,6 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
   // ---- sweep 2 (column sums) -- skipped when the caller does not want prob_perplexity
   if (avg_probs) {
     const int64_t Mp2 = round_up(M, 256);
-    vq_lse_to_log2_kernel<<<(unsigned)ceil_div(Mp2, 256), 256, 0, s>>>(row_stats, M, Mp2, ws.lse1_l2);
-    SCP_CUDA_LAUNCH_CHECK("vq_lse_to_log2");
     GemmMaps maps{};
     if ((rc = tc::make_tmap_f16(&maps.x[0], table_hat, Vp, D, D, tc::kTileM))) return rc;
     maps.x[1] = maps.x[0];
@@ -1157,9 +1164,9 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
     else rc = tc::launch_stream_gemm<256, 1, 6, Sweep2Epi, 2, tc::MC_PAIR>(maps, sc, ep, s, "vq_sweep2");
     if (rc) return rc;
   }
-  vq_metrics_partial_kernel<<<kMetricBlocks, 256, 0, s>>>(code_hist, avg_probs, M, (int)V, ws.metric_part);
-  SCP_CUDA_LAUNCH_CHECK("vq_metrics_partial");
-  vq_metrics_kernel<<<1, 256, 0, s>>>(ws.metric_part, avg_probs != nullptr, row_stats, M, (int)K, (int)V, metrics);
+  vq_metrics_kernel<<<kMetricBlocks, 256, 0, s>>>(code_hist, avg_probs, row_stats, M, (int)K, (int)V, ws.metric_part,
+                                                  reinterpret_cast<unsigned int*>(ws.metric_part + kMetricBlocks * 2),
+                                                  metrics);
   SCP_CUDA_LAUNCH_CHECK("vq_metrics");
   return SCP_OK;
 }
@@ -1262,7 +1269,7 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
   return SCP_OK;
 }
 
-extern "C" size_t scp_vq_dense_workspace_bytes(int64_t, int64_t) { return (size_t)kMetricBlocks * 2 * 4; }
+extern "C" size_t scp_vq_dense_workspace_bytes(int64_t, int64_t) { return (size_t)(kMetricBlocks * 2 + 1) * 4; }
 
 extern "C" int scp_vq_dense_fwd(float* x, int64_t M, int64_t K, int64_t V, int64_t ldx, const int32_t* masked_cols,
                                 int n_masked, const float* tau, int training, int64_t* idx, float* row_stats,
@@ -1285,9 +1292,9 @@ extern "C" int scp_vq_dense_fwd(float* x, int64_t M, int64_t K, int64_t V, int64
     SCP_CUDA_LAUNCH_CHECK("vq_dense_colsum");
   }
   float* part = reinterpret_cast<float*>(workspace);
-  vq_metrics_partial_kernel<<<kMetricBlocks, 256, 0, s>>>(code_hist, avg_probs, M, (int)V, part);
-  SCP_CUDA_LAUNCH_CHECK("vq_metrics_partial");
-  vq_metrics_kernel<<<1, 256, 0, s>>>(part, avg_probs != nullptr, row_stats, M, (int)K, (int)V, metrics);
+  if (cudaMemsetAsync(part + kMetricBlocks * 2, 0, 4, s) != cudaSuccess) return fail(SCP_ERR_CUDA, "memset ticket");
+  vq_metrics_kernel<<<kMetricBlocks, 256, 0, s>>>(code_hist, avg_probs, row_stats, M, (int)K, (int)V, part,
+                                                  reinterpret_cast<unsigned int*>(part + kMetricBlocks * 2), metrics);
   SCP_CUDA_LAUNCH_CHECK("vq_metrics");
   return SCP_OK;
 }
