@@ -84,6 +84,30 @@ int scp_wsum_bwd(const void* const* layer_ptrs, int L, int64_t B, int64_t T, int
                  const void* g_y, int dtype_g, float* d_weights, void* const* g_layers,
                  void* workspace, size_t workspace_bytes, scp_stream_t stream);
 
+/* ---- N1: keyword batch-norm prologue -- replaces Kw_BatchNorm.forward / Kw_BatchNorm_dynamic.forward
+ *      (avssl/module/speechclip_c_modules/kw_bn.py:97-164, :216-228), the step between the keyword projection and the VQ
+ *      (GeneralBranch.project_feats_to_CLIPspace, avssl/model/kw_branches.py:143-156) ------------------------------- */
+/* x, y, g_y, g_x: (M,D) f32 row-major, rows m = b*K + k.  Row m belongs to statistics group m % n_groups:
+ *   n_groups = 1  batchnorm_type "same" and Kw_BatchNorm_dynamic (one BatchNorm1d(D) over all keyword rows),
+ *   n_groups = K  batchnorm_type "eachKw" (one set of statistics per keyword slot).
+ * gamma / beta / running_mean / running_var are addressed IN PLACE as p[g*gstride + d*dstride]:
+ *   BatchNorm1d(D): (0,1);  BatchNorm1d(D*K) of the `parallel` variant (kw_bn.py:119-127): (1,K);  K stacked layers: (D,1).
+ * row_valid: nullable (M,) bytes; rows with 0 are excluded from the statistics and passed through unchanged (the
+ * seq_lens branch, kw_bn.py:137-159).  training != 0: batch statistics (biased variance), running statistics updated
+ * with `momentum` (unbiased variance) like torch.nn.BatchNorm1d; training == 0: running statistics are used.
+ * save_mean / save_rstd: (n_groups, D) f32 contiguous, kept for the backward pass. */
+size_t scp_kwbn_workspace_bytes(int64_t M, int64_t D, int n_groups);
+int scp_kwbn_fwd(const float* x, int64_t M, int64_t D, int n_groups, int64_t gstride, int64_t dstride,
+                 const uint8_t* row_valid, const float* gamma, const float* beta,
+                 float* running_mean, float* running_var, int training, float momentum, float eps,
+                 float* y, float* save_mean, float* save_rstd,
+                 void* workspace, size_t workspace_bytes, scp_stream_t stream);
+/* g_gamma / g_beta (nullable) are written with the parameter addressing above. */
+int scp_kwbn_bwd(const float* g_y, const float* x, int64_t M, int64_t D, int n_groups, int64_t gstride, int64_t dstride,
+                 const uint8_t* row_valid, const float* gamma, const float* save_mean, const float* save_rstd,
+                 int training, float* g_x, float* g_gamma, float* g_beta,
+                 void* workspace, size_t workspace_bytes, scp_stream_t stream);
+
 /* ---- S2: keyword vector quantiser -- replaces GeneralBranch.get_keyword_cosine_score + SimpleVectorQuantizer.forward
  *      + the lookup matmul (avssl/model/kw_branches.py:158-197, avssl/module/speechclip_c_modules/my_vector_quantizer.py:64-165) -- */
 

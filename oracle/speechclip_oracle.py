@@ -32,6 +32,7 @@ __all__ = [
     "normalize_hidden_states",
     "upstream_feat_len",
     "upstream_tail",
+    "kw_batchnorm",
     "cosine_scores_loop",
     "cosine_scores",
     "vq_forward",
@@ -122,6 +123,61 @@ def upstream_tail(layers: Sequence[torch.Tensor], weights: torch.Tensor, normali
     feat_len = upstream_feat_len(wav_len, downsample_rate, layers[0].shape[1])
     y = wsum_forward(layers, weights, normalize_features=normalize_hiddenstates and normalize_type == "s3prl")
     return y, feat_len
+
+
+# ----------------------------------------------------------------------------------------
+# N1  keyword batch-norm prologue         avssl/module/speechclip_c_modules/kw_bn.py:97-164, :216-228
+# ----------------------------------------------------------------------------------------
+def kw_batchnorm(keywords: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, running_mean: torch.Tensor,
+                 running_var: torch.Tensor, batchnorm_type: str = "same", parallel: bool = False,
+                 training: bool = True, seq_lens: Optional[Sequence[int]] = None, momentum: float = 0.1,
+                 eps: float = 1e-5) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Kw_BatchNorm.forward / Kw_BatchNorm_dynamic.forward written out as explicit statistics.
+
+    keywords (B,K,D).  Parameter / running-statistic layouts follow the reference modules:
+      "same" (and the dynamic layer, kw_bn.py:216-228): (D,)  -- one BatchNorm1d(D) over all B*K rows (:141-143), or
+          over the first seq_lens[b] rows of every utterance with the other rows left untouched (:144-159);
+      "eachKw", parallel=True: (D*K,) with feature index d*K + k -- BatchNorm1d(D*K) on the (B, D*K) view of the
+          (B,D,K) permutation (:119-127);
+      "eachKw", parallel=False: (K,D) -- K independent BatchNorm1d(D) layers, one per keyword slot (:128-140).
+    Training uses the biased batch variance for the normalisation and updates the running statistics with the
+    unbiased one (torch.nn.BatchNorm1d); eval uses the running statistics.  Returns (y, running_mean', running_var').
+    """
+    B, K, D = keywords.shape
+    if batchnorm_type == "eachKw":
+        if parallel:
+            w, b = weight.view(D, K).t(), bias.view(D, K).t()            # (K,D) views of index d*K + k
+            rm, rv = running_mean.view(D, K).t(), running_var.view(D, K).t()
+        else:
+            w, b, rm, rv = weight, bias, running_mean, running_var        # (K,D)
+        x = keywords                                                       # statistics over the batch axis
+        if training:
+            mean = x.mean(dim=0)
+            var = x.var(dim=0, unbiased=False)
+            new_rm = (1 - momentum) * rm + momentum * mean.detach()
+            new_rv = (1 - momentum) * rv + momentum * x.var(dim=0, unbiased=True).detach()
+        else:
+            mean, var, new_rm, new_rv = rm, rv, rm, rv
+        y = (x - mean) / torch.sqrt(var + eps) * w + b
+        if parallel:
+            new_rm, new_rv = new_rm.t().reshape(-1), new_rv.t().reshape(-1)
+        return y, new_rm, new_rv
+    assert batchnorm_type == "same", batchnorm_type
+    if seq_lens is None:
+        valid = torch.ones(B, K, dtype=torch.bool)
+    else:
+        valid = torch.arange(K)[None, :] < torch.as_tensor(list(seq_lens))[:, None]
+    rows = keywords[valid]                                                 # (n_valid, D)
+    if training:
+        mean = rows.mean(dim=0)
+        var = rows.var(dim=0, unbiased=False)
+        new_rm = (1 - momentum) * running_mean + momentum * mean.detach()
+        new_rv = (1 - momentum) * running_var + momentum * rows.var(dim=0, unbiased=True).detach()
+    else:
+        mean, var, new_rm, new_rv = running_mean, running_var, running_mean, running_var
+    normed = (keywords - mean) / torch.sqrt(var + eps) * weight + bias
+    y = torch.where(valid[..., None], normed, keywords)
+    return y, new_rm, new_rv
 
 
 # ----------------------------------------------------------------------------------------

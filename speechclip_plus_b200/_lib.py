@@ -40,6 +40,12 @@ SIGNATURES = {
     "scp_wsum_bwd": (c_int, [POINTER(c_void_p), c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int,
                              c_void_p, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, POINTER(c_void_p),
                              c_void_p, c_size_t, c_void_p]),
+    "scp_kwbn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "scp_kwbn_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                             c_void_p]),
+    "scp_kwbn_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "scp_vq_padded_vocab": (c_int64, [c_int64]),
     "scp_vq_prepare_table": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "scp_vq_fwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),

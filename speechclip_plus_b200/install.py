@@ -5,6 +5,7 @@ The reference resolves the three hot-path classes by name on Python modules:
   * ``getattr(vector_quantizers, vq.type)``                       avssl/model/kw_branches.py:75-91
   * ``WeightedSumLayer(...)`` imported by name                    avssl/module/speech_encoder_plus.py:24, :218-220, :472-476
   * the cosine + lookup glue is a method of ``GeneralBranch``     avssl/model/kw_branches.py:158-197
+  * ``Kw_BatchNorm`` / ``Kw_BatchNorm_dynamic`` imported by name  avssl/model/kw_branches.py:19, :95, :629
 
 ``install()`` must run after ``import avssl`` and before the model is constructed.
 """
@@ -19,6 +20,7 @@ def install(avssl_package: str = "avssl", strict: bool = False) -> dict:
     from .module.losses import MaskedContrastiveLoss
     from .module.vector_quantizers import SimpleVectorQuantizer, fused_vq_audio_features
     from .module.weighted_sum import WeightedSumLayer
+    from .module.kw_bn import Kw_BatchNorm, Kw_BatchNorm_dynamic
 
     done = {}
 
@@ -42,6 +44,9 @@ def install(avssl_package: str = "avssl", strict: bool = False) -> dict:
     patch(f"{p}.module", "WeightedSumLayer", WeightedSumLayer)
     patch(f"{p}.module.speechclip_c_modules.my_vector_quantizer", "SimpleVectorQuantizer", SimpleVectorQuantizer)
     patch(f"{p}.module.speechclip_c_modules.vector_quantizers", "SimpleVectorQuantizer", SimpleVectorQuantizer)
+    for name, cls in (("Kw_BatchNorm", Kw_BatchNorm), ("Kw_BatchNorm_dynamic", Kw_BatchNorm_dynamic)):
+        patch(f"{p}.module.speechclip_c_modules.kw_bn", name, cls)
+        patch(f"{p}.model.kw_branches", name, cls)  # imported by name there (kw_branches.py:19)
     # the fused cosine + quantise + lookup replaces the method body on the shared base class of all branches
     try:
         kb = sys.modules.get(f"{p}.model.kw_branches") or importlib.import_module(f"{p}.model.kw_branches")

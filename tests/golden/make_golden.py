@@ -10,6 +10,7 @@ Reference entry points exercised (paths relative to /root/reference):
   * avssl/module/weighted_sum.py            WeightedSumLayer.forward                      (S1)
   * avssl/module/speech_encoder_plus.py:518-622  FairseqSpeechEncoder_Hubert.forward with a stand-in upstream
                                             model: per-layer rescale, feat_len, weighted sum   (S1')
+  * avssl/module/speechclip_c_modules/kw_bn.py  Kw_BatchNorm / Kw_BatchNorm_dynamic .forward   (N1)
   * avssl/model/kw_branches.py:158-197      GeneralBranch.get_keyword_cosine_score,
                                             GeneralBranch.vq_audio_features (identity projection)  (V1, V4)
   * avssl/module/speechclip_c_modules/my_vector_quantizer.py  SimpleVectorQuantizer.forward   (V3)
@@ -124,6 +125,58 @@ def golden_s1_tail():
              normalize_hiddenstates=np.array(norm), normalize_type=np.array(ntype), wav_len=np.array(wav_lens),
              y=y, feat_len=feat_len, grad_y=gy, grad_weights=grads[0],
              grad_layers=torch.stack([x for x in grads[1:]]))
+
+
+# ----------------------------------------------------------------------------------------------
+def golden_kwbn():
+    """The reference's keyword batch-norm layers (kw_bn.py) in every configuration the branches can build: eachKw
+    parallel (the shipped fixed-K recipes), eachKw with K separate layers, same, same with seq_lens, the dynamic layer
+    of the "+" branches, plus an eval-mode case that normalises with (non-trivial) running statistics."""
+    kb = ref.load_leaf("avssl/module/speechclip_c_modules/kw_bn.py", "ref_kw_bn")
+    cases = [
+        # name, B, K, D, type, parallel, training, seq_lens
+        ("kwbn_eachkw_parallel", 6, 8, 64, "eachKw", True, True, None),
+        ("kwbn_eachkw_layers", 5, 3, 32, "eachKw", False, True, None),
+        ("kwbn_same", 4, 8, 64, "same", False, True, None),
+        ("kwbn_same_seqlens", 4, 6, 32, "same", False, True, [6, 2, 4, 1]),
+        ("kwbn_dynamic", 3, 11, 64, "dynamic", False, True, None),
+        ("kwbn_eachkw_parallel_eval", 6, 8, 64, "eachKw", True, False, None),
+    ]
+    for i, (name, B, K, D, btype, parallel, training, seq_lens) in enumerate(cases):
+        g = _gen(600 + i)
+        table = torch.randn(300, D, generator=g) * 0.02 + 0.003 * torch.randn(1, D, generator=g)
+        init_bias, init_scale = table.mean(0), table.std(0)   # kw_branches.py:99-100
+        if btype == "dynamic":
+            layer = kb.Kw_BatchNorm_dynamic(kw_dim=D, init_bias=init_bias, init_scale=init_scale, std_scale=1.0)
+        else:
+            layer = kb.Kw_BatchNorm(kw_num=K, kw_dim=D, batchnorm_type=btype, init_bias=init_bias,
+                                    init_scale=init_scale, std_scale=1.0, learnable=True, parallel=parallel)
+        bns = list(layer.bn_layers) if hasattr(layer, "bn_layers") else [layer.bn_layer]
+        for bn in bns:  # non-trivial running statistics
+            with torch.no_grad():
+                bn.running_mean.copy_(torch.randn(bn.running_mean.shape, generator=g) * 0.1)
+                bn.running_var.copy_(torch.rand(bn.running_var.shape, generator=g) + 0.5)
+        rm0 = torch.stack([bn.running_mean.clone() for bn in bns])
+        rv0 = torch.stack([bn.running_var.clone() for bn in bns])
+        layer.train(training)
+        x = (torch.randn(B, K, D, generator=g) * 0.7 + 0.3 * torch.randn(1, 1, D, generator=g)).requires_grad_(True)
+        x_in = x.clone()  # the seq_lens branch writes into its input (kw_bn.py:157)
+        if seq_lens is not None:
+            y = layer(x_in, torch.tensor(seq_lens))
+        else:
+            y = layer(x_in)
+        gy = torch.randn(B, K, D, generator=g)
+        params = [p for bn in bns for p in (bn.weight, bn.bias)]
+        grads = torch.autograd.grad(y, [x] + params, grad_outputs=gy)
+        save(name, x=x, batchnorm_type=np.array(btype), parallel=np.array(parallel), training=np.array(training),
+             seq_lens=np.array(seq_lens if seq_lens is not None else [], dtype=np.int64),
+             weight=torch.stack([bn.weight for bn in bns]), bias=torch.stack([bn.bias for bn in bns]),
+             running_mean_in=rm0, running_var_in=rv0,
+             running_mean_out=torch.stack([bn.running_mean for bn in bns]),
+             running_var_out=torch.stack([bn.running_var for bn in bns]),
+             num_batches_tracked=torch.stack([bn.num_batches_tracked for bn in bns]),
+             y=y, grad_y=gy, grad_x=grads[0], grad_weight=torch.stack(list(grads[1::2])),
+             grad_bias=torch.stack(list(grads[2::2])))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -264,6 +317,7 @@ if __name__ == "__main__":
     torch.set_num_threads(max(os.cpu_count() or 1, 1))
     golden_wsum()
     golden_s1_tail()
+    golden_kwbn()
     golden_vq()
     golden_nce()
     golden_hybrid_loss()

@@ -171,6 +171,98 @@ def test_wsum_full_size_properties(scp):
 
 
 # =====================================================================================================================
+# N1 keyword batch-norm prologue
+# =====================================================================================================================
+def _build_kwbn(g, D, K):
+    from speechclip_plus_b200.module.kw_bn import Kw_BatchNorm, Kw_BatchNorm_dynamic
+    btype = g["batchnorm_type"]
+    zeros, ones = torch.zeros(D), torch.ones(D)
+    if btype == "dynamic":
+        layer = Kw_BatchNorm_dynamic(kw_dim=D, init_bias=zeros, init_scale=ones)
+    else:
+        layer = Kw_BatchNorm(kw_num=K, kw_dim=D, batchnorm_type=btype, init_bias=zeros, init_scale=ones,
+                             parallel=g["parallel"])
+    bns = list(layer.bn_layers) if hasattr(layer, "bn_layers") else [layer.bn_layer]
+    with torch.no_grad():
+        for i, bn in enumerate(bns):
+            bn.weight.copy_(g["weight"][i]); bn.bias.copy_(g["bias"][i])
+            bn.running_mean.copy_(g["running_mean_in"][i]); bn.running_var.copy_(g["running_var_in"][i])
+    layer.cuda().train(g["training"])
+    return layer, bns
+
+
+@pytest.mark.parametrize("name", golden_names("kwbn_"))
+def test_kw_batchnorm_golden(scp, name):
+    g = load_golden(name)
+    B, K, D = g["x"].shape
+    layer, bns = _build_kwbn(g, D, K)
+    x = g["x"].cuda().requires_grad_(True)
+    seq_lens = g["seq_lens"]
+    y = layer(x, seq_lens.cuda()) if seq_lens.numel() else layer(x)
+    assert y.shape == g["y"].shape
+    assert rel_err(y, g["y"]) < TOL
+    params = [p for bn in bns for p in (bn.weight, bn.bias)]
+    grads = torch.autograd.grad(y, [x] + params, grad_outputs=g["grad_y"].cuda())
+    assert norm_err(grads[0], g["grad_x"]) < TOL
+    assert rel_err(torch.stack(list(grads[1::2])), g["grad_weight"]) < TOL
+    assert rel_err(torch.stack(list(grads[2::2])), g["grad_bias"]) < TOL
+    # running statistics and the batch counter follow torch.nn.BatchNorm1d
+    assert rel_err(torch.stack([bn.running_mean for bn in bns]), g["running_mean_out"]) < TOL
+    assert rel_err(torch.stack([bn.running_var for bn in bns]), g["running_var_out"]) < TOL
+    assert torch.equal(torch.stack([bn.num_batches_tracked for bn in bns]).cpu(), g["num_batches_tracked"])
+
+
+@pytest.mark.parametrize("cfg", [("eachKw", True, 256, 8, 512), ("same", False, 256, 8, 512), ("same", False, 64, 12, 768),
+                                 ("eachKw", True, 3, 5, 64)])
+def test_kw_batchnorm_vs_oracle(scp, cfg):
+    from speechclip_plus_b200.module.kw_bn import Kw_BatchNorm
+    btype, parallel, B, K, D = cfg
+    gen = torch.Generator().manual_seed(B * 7 + K)
+    x = (torch.randn(B, K, D, generator=gen) * 0.6 + 3.0 * torch.randn(1, 1, D, generator=gen))  # |mean| >> std
+    init_bias, init_scale = torch.randn(D, generator=gen) * 0.01, torch.rand(D, generator=gen) * 0.02 + 0.01
+    layer = Kw_BatchNorm(K, D, btype, init_bias, init_scale, parallel=parallel).cuda().train()
+    bn = layer.bn_layer
+    xd = x.cuda().requires_grad_(True)
+    y = layer(xd)
+    gy = torch.randn(B, K, D, generator=gen)
+    gx, gw, gb = torch.autograd.grad(y, [xd, bn.weight, bn.bias], grad_outputs=gy.cuda())
+    xr = x.double().requires_grad_(True)
+    w_r = bn.weight.detach().double().cpu().requires_grad_(True)
+    b_r = bn.bias.detach().double().cpu().requires_grad_(True)
+    n_feat = w_r.numel()
+    y_r, rm_r, rv_r = oracle.kw_batchnorm(xr, w_r, b_r, torch.zeros(n_feat, dtype=torch.float64),
+                                          torch.ones(n_feat, dtype=torch.float64), btype, parallel, True)
+    gx_r, gw_r, gb_r = torch.autograd.grad(y_r, [xr, w_r, b_r], grad_outputs=gy.double())
+    assert rel_err(y, y_r) < TOL
+    assert norm_err(gx, gx_r) < TOL and rel_err(gw, gw_r) < TOL and rel_err(gb, gb_r) < TOL
+    assert rel_err(bn.running_mean, rm_r) < TOL and rel_err(bn.running_var, rv_r) < TOL
+    # determinism: the slice partials are combined in a fixed order
+    layer2 = Kw_BatchNorm(K, D, btype, init_bias, init_scale, parallel=parallel).cuda().train()
+    assert torch.equal(layer2(x.cuda()), y)
+
+
+def test_kw_batchnorm_state_dict_and_errors(scp):
+    from speechclip_plus_b200.module.kw_bn import Kw_BatchNorm, Kw_BatchNorm_dynamic
+    D, K = 64, 4
+    par = Kw_BatchNorm(K, D, "eachKw", torch.zeros(D), torch.ones(D), parallel=True)
+    assert sorted(par.state_dict()) == ["bn_layer.bias", "bn_layer.num_batches_tracked", "bn_layer.running_mean",
+                                        "bn_layer.running_var", "bn_layer.weight"]
+    assert par.bn_layer.weight.shape == (D * K,)                                 # kw_bn.py:46
+    lay = Kw_BatchNorm(K, D, "eachKw", torch.zeros(D), torch.ones(D), parallel=False)
+    assert "bn_layers.3.running_var" in lay.state_dict()                         # kw_bn.py:48-50
+    dyn = Kw_BatchNorm_dynamic(D, torch.zeros(D), torch.ones(D), std_scale=2.0, learnable=False).cuda()
+    assert not dyn.bn_layer.weight.requires_grad and float(dyn.bn_layer.weight[0]) == 2.0
+    with pytest.raises(NotImplementedError):
+        Kw_BatchNorm(K, D, "perRow", torch.zeros(D), torch.ones(D))
+    with pytest.raises(AssertionError):
+        par.cuda()(torch.zeros(2, K + 1, D, device="cuda"))                      # kw_bn.py:112
+    with pytest.raises(ValueError):
+        par.train()(torch.zeros(1, K, D, device="cuda"))                         # one value per channel in training
+    with pytest.raises(scp.ScpError):
+        dyn(torch.zeros(2, 3, D))                                                # CPU tensor: no fallback
+
+
+# =====================================================================================================================
 # S2 vector quantiser
 # =====================================================================================================================
 def _make_vq(scp, spec, training):
@@ -462,7 +554,8 @@ def test_install_patches_reference_namespaces(scp):
     for name in [pkg, f"{pkg}.module", f"{pkg}.module.losses", f"{pkg}.module.weighted_sum",
                  f"{pkg}.module.speech_encoder_plus", f"{pkg}.module.speechclip_c_modules",
                  f"{pkg}.module.speechclip_c_modules.my_vector_quantizer",
-                 f"{pkg}.module.speechclip_c_modules.vector_quantizers", f"{pkg}.model", f"{pkg}.model.kw_branches"]:
+                 f"{pkg}.module.speechclip_c_modules.vector_quantizers", f"{pkg}.module.speechclip_c_modules.kw_bn",
+                 f"{pkg}.model", f"{pkg}.model.kw_branches"]:
         mods[name] = types.ModuleType(name)
         sys.modules[name] = mods[name]
 
@@ -474,6 +567,8 @@ def test_install_patches_reference_namespaces(scp):
         done = scp.install(pkg, strict=True)
         assert all(done.values())
         assert mods[f"{pkg}.module.losses"].MaskedContrastiveLoss is scp.MaskedContrastiveLoss
+        assert mods[f"{pkg}.model.kw_branches"].Kw_BatchNorm is scp.Kw_BatchNorm
+        assert mods[f"{pkg}.module.speechclip_c_modules.kw_bn"].Kw_BatchNorm_dynamic is scp.Kw_BatchNorm_dynamic
         assert getattr(mods[f"{pkg}.module.speechclip_c_modules.vector_quantizers"], "SimpleVectorQuantizer") \
             is scp.SimpleVectorQuantizer
         # the patched method runs the fused path on a duck-typed branch (projection = identity)
