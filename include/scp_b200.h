@@ -167,6 +167,24 @@ int scp_vq_dense_fwd(float* x, int64_t M, int64_t K, int64_t V, int64_t ldx,
 int scp_vq_dense_bwd(const float* x_masked, const float* g_p, int64_t M, int64_t V, int64_t ldx, int64_t ldg,
                      const float* row_stats, const float* tau, float* g_x, float* g_tau, scp_stream_t stream);
 
+/* ---- N3: text-transformer input splice -- replaces the prologue of ClipModel.encode_keywords
+ *      (avssl/module/clip_official.py:240-267: id tensor, token-embedding lookup, the per-sample Python splice loop
+ *      :261-265, positional embedding) and get_keypadding_mask (avssl/util/data_utils.py:6-22) --------------------- */
+/* x[b,l,:] = src(b,l) + pos_emb[l,:],  src = E[sot] (l = 0) | keywords[b,l-1] (1 <= l <= n_b) | E[eot] (l = n_b+1) |
+ * E[0] (else);  n_b = kw_num[b] (device int64, nullable) or fixed_num, clamped to [0, min(Kmax, L-2)].
+ * keywords (B,Kmax,D) f32; table (V,D), pos_emb (L,D) and x (B,L,D) share `dtype` (keywords are rounded to it first,
+ * as the reference's slice-assignment does).  eot_index (nullable, (B,) int64) = n_b + 1 (clip_official.py:274-277). */
+int scp_kw_splice_fwd(const float* keywords, const int64_t* kw_num, int64_t fixed_num,
+                      const void* table, const void* pos_emb, int dtype,
+                      int64_t B, int64_t Kmax, int64_t D, int64_t L, int64_t sot_id, int64_t eot_id,
+                      void* x, int64_t* eot_index, scp_stream_t stream);
+/* g_keywords[b,j,:] = g_x[b,1+j,:] for j < n_b, 0 otherwise (token table and positional embedding are frozen:
+ * clip_official.py:110-123). */
+int scp_kw_splice_bwd(const void* g_x, int dtype, const int64_t* kw_num, int64_t fixed_num,
+                      int64_t B, int64_t Kmax, int64_t D, int64_t L, float* g_keywords, scp_stream_t stream);
+/* mask[b,j] = (j >= lens[b]) as bytes (True = padding). */
+int scp_keypadding_mask(const int64_t* lens, int64_t B, int64_t max_len, uint8_t* mask, scp_stream_t stream);
+
 /* ---- N0 + G0: L2-normalise the loss features and pack them into the all-gather send buffer
  *      (avssl/model/kwClip.py:857, :905-907, :913-915; gather point kwClip.py:149-169) -------------------- */
 /* packed layout per rank: n_feats blocks of (n,D) f32 followed by n int64 ids.  feats: HOST array of device ptrs.

@@ -33,6 +33,8 @@ __all__ = [
     "upstream_feat_len",
     "upstream_tail",
     "kw_batchnorm",
+    "splice_keywords",
+    "keypadding_mask",
     "cosine_scores_loop",
     "cosine_scores",
     "vq_forward",
@@ -324,6 +326,38 @@ def vq_keyword_grad(keywords_in: torch.Tensor, table: torch.Tensor, curr_temp, g
 def l2_normalise(feat: torch.Tensor) -> torch.Tensor:
     """f / ||f||_2 over the last dim, no epsilon (kwClip.py:857)."""
     return feat / feat.norm(dim=-1, keepdim=True)
+
+
+# ----------------------------------------------------------------------------------------
+# N3  text-transformer input splice       avssl/module/clip_official.py:240-267, avssl/util/data_utils.py:6-22
+# ----------------------------------------------------------------------------------------
+def splice_keywords(keywords: torch.Tensor, keyword_num, table: torch.Tensor, pos_emb: torch.Tensor,
+                    sot_token: int, eot_token: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The prologue of ClipModel.encode_keywords: a zero-initialised (B,77) id tensor with SOT at 0 (:240-249) and EOT at
+    keyword_num + 1 (:251-258), the token-embedding lookup (:260), the keywords written over positions 1..n (:262-267)
+    and the positional-embedding add (:269).  Returns (x (B,L,D), eot positions (B,))."""
+    B = keywords.shape[0]
+    L = pos_emb.shape[0]
+    text = torch.zeros(B, L, dtype=torch.long)
+    text[:, 0] = sot_token
+    if torch.is_tensor(keyword_num):
+        index = keyword_num.long() + 1
+        text = text.scatter(1, index.unsqueeze(1), eot_token)
+    else:
+        index = torch.full((B,), int(keyword_num) + 1, dtype=torch.long)
+        text[:, keyword_num + 1] = eot_token
+    x = table[text]
+    rows = []
+    for i in range(B):  # out-of-place form of the slice assignment so that autograd reaches `keywords`
+        n = int(index[i]) - 1
+        rows.append(torch.cat([x[i, :1], keywords[i, :n].to(x.dtype), x[i, n + 1:]], dim=0))
+    x = torch.stack(rows) + pos_emb
+    return x, index
+
+
+def keypadding_mask(max_length: int, data_lens: torch.Tensor) -> torch.Tensor:
+    """True marks padding (data_utils.py:17-20)."""
+    return torch.arange(max_length)[None, :] >= data_lens.long()[:, None]
 
 
 # ----------------------------------------------------------------------------------------

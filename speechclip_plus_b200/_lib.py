@@ -62,6 +62,11 @@ SIGNATURES = {
                                  c_void_p, c_size_t, c_void_p]),
     "scp_vq_dense_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
+    "scp_kw_splice_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64,
+                                  c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "scp_kw_splice_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p,
+                                  c_void_p]),
+    "scp_keypadding_mask": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "scp_pack_bytes": (c_size_t, [c_int, c_int64, c_int64]),
     "scp_l2norm_pack": (c_int, [POINTER(c_void_p), c_int, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),

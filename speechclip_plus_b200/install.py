@@ -47,6 +47,18 @@ def install(avssl_package: str = "avssl", strict: bool = False) -> dict:
     for name, cls in (("Kw_BatchNorm", Kw_BatchNorm), ("Kw_BatchNorm_dynamic", Kw_BatchNorm_dynamic)):
         patch(f"{p}.module.speechclip_c_modules.kw_bn", name, cls)
         patch(f"{p}.model.kw_branches", name, cls)  # imported by name there (kw_branches.py:19)
+    # N3: the text-transformer input splice replaces the body of ClipModel.encode_keywords; get_keypadding_mask by name
+    try:
+        from .module.clip_glue import encode_keywords, get_keypadding_mask
+        co = sys.modules.get(f"{p}.module.clip_official") or importlib.import_module(f"{p}.module.clip_official")
+        co.ClipModel.encode_keywords = encode_keywords
+        done[f"{p}.module.clip_official.ClipModel.encode_keywords"] = True
+        patch(f"{p}.util.data_utils", "get_keypadding_mask", get_keypadding_mask)
+        patch(f"{p}.model.kw_branches", "get_keypadding_mask", get_keypadding_mask)
+    except Exception:
+        if strict:
+            raise
+        done[f"{p}.module.clip_official.ClipModel.encode_keywords"] = False
     # the fused cosine + quantise + lookup replaces the method body on the shared base class of all branches
     try:
         kb = sys.modules.get(f"{p}.model.kw_branches") or importlib.import_module(f"{p}.model.kw_branches")

@@ -14,6 +14,8 @@ Reference entry points exercised (paths relative to /root/reference):
   * avssl/model/kw_branches.py:158-197      GeneralBranch.get_keyword_cosine_score,
                                             GeneralBranch.vq_audio_features (identity projection)  (V1, V4)
   * avssl/module/speechclip_c_modules/my_vector_quantizer.py  SimpleVectorQuantizer.forward   (V3)
+  * avssl/module/clip_official.py:222-279   ClipModel.encode_keywords around a stand-in text tower;
+    avssl/util/data_utils.py:6-22           get_keypadding_mask                            (N3)
   * avssl/module/losses.py:129-245          MaskedContrastiveLoss                          (S3)
   * avssl/model/kwClip.py:999-1040          KWClip_GeneralTransformer.compute_loss         (C0)
 """
@@ -180,6 +182,62 @@ def golden_kwbn():
 
 
 # ----------------------------------------------------------------------------------------------
+def golden_splice():
+    """ClipModel.encode_keywords (clip_official.py:222-279) run unbound on a duck-typed CLIP whose "transformer" records
+    its input: pins the spliced (B,77,D) tensor, the EOT gather and the gradient that reaches the keywords."""
+    ref.import_avssl()
+    import avssl.module.clip_official as co
+    import avssl.util.data_utils as du
+    cases = [
+        # name, B, Kmax, D, V, keyword_num (int or per-utterance list), reduced vocabulary
+        ("splice_fixed8", 3, 8, 64, 120, 8, False),
+        ("splice_dynamic", 4, 12, 64, 120, [12, 3, 7, 1], False),
+        ("splice_dynamic_reduced", 3, 6, 32, 90, [2, 6, 4], True),
+    ]
+    for i, (name, B, Kmax, D, V, num, reduced) in enumerate(cases):
+        g = _gen(700 + i)
+        L = 77
+        emb = torch.nn.Embedding(V, D)
+        with torch.no_grad():
+            emb.weight.copy_(torch.randn(V, D, generator=g) * 0.02)
+        emb.weight.requires_grad_(False)
+        captured = {}
+
+        class Tower(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.mix = torch.nn.Linear(D, D)
+
+            def forward(self, x):  # (L, N, D)
+                captured["x"] = x.permute(1, 0, 2)
+                return torch.tanh(self.mix(x))
+
+        torch.manual_seed(SEED + 700 + i)
+        model = types.SimpleNamespace(token_embedding=emb, positional_embedding=torch.randn(L, D, generator=g) * 0.01,
+                                      transformer=Tower(), ln_final=torch.nn.LayerNorm(D),
+                                      text_projection=torch.randn(D, 16, generator=g) * 0.1)
+        sot, eot = V - 2, V - 1
+        clip = types.SimpleNamespace(model=model, device=torch.device("cpu"),
+                                     tokenizer=types.SimpleNamespace(encoder={"<|startoftext|>": sot, "<|endoftext|>": eot}),
+                                     selected_text_emb_ids=None)
+        if reduced:  # ids come from the reduced-vocabulary attributes instead of the tokenizer (:246-247)
+            clip.selected_text_emb_ids = np.arange(V)
+            clip.startOfTxt_reduced, clip.endOfTxt_reduced = 5, 7
+            sot, eot = 5, 7
+        kw = (torch.randn(B, Kmax, D, generator=g) * 0.02).requires_grad_(True)
+        keyword_num = torch.tensor(num) if isinstance(num, list) else num
+        out = co.ClipModel.encode_keywords(clip, kw, keyword_num)
+        g_out = torch.randn(out.shape, generator=g)
+        (g_kw,) = torch.autograd.grad(out, [kw], grad_outputs=g_out)
+        lens = torch.tensor(num) if isinstance(num, list) else torch.full((B,), num)
+        mask = du.get_keypadding_mask(Kmax, lens)
+        save(name, keywords=kw, keyword_num=np.array(num), table=emb.weight, pos_emb=model.positional_embedding,
+             sot=np.array(sot), eot=np.array(eot), x=captured["x"], mix_w=model.transformer.mix.weight,
+             mix_b=model.transformer.mix.bias, text_projection=model.text_projection, out=out, grad_out=g_out,
+             grad_keywords=g_kw, keypadding_mask=mask)
+
+
+# ----------------------------------------------------------------------------------------------
 def _fake_branch(kb, vq_mod, table: torch.Tensor, temp_spec: str, training: bool):
     """A GeneralBranch whose projection is the identity, so that vq_audio_features (kw_branches.py:181-197)
     runs V1 + V3 + V4 of the reference on the given keyword vectors."""
@@ -318,6 +376,7 @@ if __name__ == "__main__":
     golden_wsum()
     golden_s1_tail()
     golden_kwbn()
+    golden_splice()
     golden_vq()
     golden_nce()
     golden_hybrid_loss()

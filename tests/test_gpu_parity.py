@@ -263,6 +263,83 @@ def test_kw_batchnorm_state_dict_and_errors(scp):
 
 
 # =====================================================================================================================
+# N3 text-transformer input splice
+# =====================================================================================================================
+def _fake_clip(g, dtype=torch.float32):
+    import types
+    V, D = g["table"].shape
+    emb = torch.nn.Embedding(V, D)
+    emb.weight.data.copy_(g["table"])
+    emb.weight.requires_grad_(False)
+    emb = emb.cuda().to(dtype)
+    captured = {}
+
+    class Tower(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.mix = torch.nn.Linear(D, D)
+            self.mix.weight.data.copy_(g["mix_w"]); self.mix.bias.data.copy_(g["mix_b"])
+
+        def forward(self, x):
+            captured["x"] = x.permute(1, 0, 2)
+            return torch.tanh(self.mix(x))
+
+    model = types.SimpleNamespace(token_embedding=emb, positional_embedding=g["pos_emb"].cuda().to(dtype),
+                                  transformer=Tower().cuda().to(dtype), ln_final=torch.nn.LayerNorm(D).cuda().to(dtype),
+                                  text_projection=g["text_projection"].cuda().to(dtype))
+    sot, eot = int(g["sot"]), int(g["eot"])
+    clip = types.SimpleNamespace(model=model, device=torch.device("cuda"), selected_text_emb_ids=None,
+                                 tokenizer=types.SimpleNamespace(encoder={"<|startoftext|>": sot, "<|endoftext|>": eot}))
+    return clip, captured
+
+
+@pytest.mark.parametrize("name", golden_names("splice_"))
+def test_keyword_splice_golden(scp, name):
+    from speechclip_plus_b200.module.clip_glue import encode_keywords, get_keypadding_mask
+    g = load_golden(name)
+    clip, captured = _fake_clip(g)
+    if name.endswith("reduced"):  # token ids taken from the reduced-vocabulary attributes (clip_official.py:246-247)
+        clip.selected_text_emb_ids = list(range(g["table"].shape[0]))
+        clip.startOfTxt_reduced, clip.endOfTxt_reduced = int(g["sot"]), int(g["eot"])
+        clip.tokenizer.encoder = {"<|startoftext|>": 0, "<|endoftext|>": 1}
+    kw = g["keywords"].cuda().requires_grad_(True)
+    num = g["keyword_num"]
+    keyword_num = num.cuda() if num.dim() else int(num)
+    out = encode_keywords(clip, kw, keyword_num)
+    assert torch.equal(captured["x"].cpu(), g["x"])        # bit-exact: data movement + one fp32 add
+    assert rel_err(out, g["out"]) < TOL
+    (g_kw,) = torch.autograd.grad(out, [kw], grad_outputs=g["grad_out"].cuda())
+    assert norm_err(g_kw, g["grad_keywords"]) < TOL
+    lens = num if num.dim() else torch.full((kw.shape[0],), int(num))
+    mask = get_keypadding_mask(kw.shape[1], lens.cuda())
+    assert mask.dtype == torch.bool and torch.equal(mask.cpu(), g["keypadding_mask"])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_keyword_splice_full_size(scp, dtype):
+    """B=256, 77 x 512 CLIP text width (BASELINE config 3), dynamic keyword counts up to the CIF cap."""
+    from speechclip_plus_b200.module.clip_glue import splice_keywords
+    B, Kmax, D, V, L = 256, 75, 512, 49408, 77
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    table = (torch.randn(V, D, device="cuda", generator=gen) * 0.02).to(dtype)
+    pos = (torch.randn(L, D, device="cuda", generator=gen) * 0.01).to(dtype)
+    kw = (torch.randn(B, Kmax, D, device="cuda", generator=gen) * 0.02).requires_grad_(True)
+    num = torch.randint(0, Kmax + 1, (B,), device="cuda", generator=gen)
+    x, idx = splice_keywords(kw, num, table, pos, V - 2, V - 1)
+    x_ref, idx_ref = oracle.splice_keywords(kw.detach().cpu(), num.cpu(), table.cpu(), pos.cpu(), V - 2, V - 1)
+    assert x.dtype == dtype and torch.equal(idx.cpu(), idx_ref)
+    assert torch.equal(x.cpu(), x_ref)
+    gx = torch.randn(B, L, D, device="cuda", generator=gen).to(dtype)
+    (g_kw,) = torch.autograd.grad(x, [kw], grad_outputs=gx)
+    valid = (torch.arange(Kmax, device="cuda")[None, :] < num[:, None])[..., None]
+    assert torch.equal(g_kw, torch.where(valid, gx[:, 1:1 + Kmax].float(), torch.zeros((), device="cuda")))
+    with pytest.raises(RuntimeError):
+        splice_keywords(kw, 8, table, pos, V - 2, V - 1)              # int keyword_num must equal keywords.shape[1]
+    with pytest.raises(scp.ScpError):
+        splice_keywords(kw, num, table.clone().requires_grad_(True), pos, V - 2, V - 1)
+
+
+# =====================================================================================================================
 # S2 vector quantiser
 # =====================================================================================================================
 def _make_vq(scp, spec, training):
@@ -555,6 +632,7 @@ def test_install_patches_reference_namespaces(scp):
                  f"{pkg}.module.speech_encoder_plus", f"{pkg}.module.speechclip_c_modules",
                  f"{pkg}.module.speechclip_c_modules.my_vector_quantizer",
                  f"{pkg}.module.speechclip_c_modules.vector_quantizers", f"{pkg}.module.speechclip_c_modules.kw_bn",
+                 f"{pkg}.module.clip_official", f"{pkg}.util", f"{pkg}.util.data_utils",
                  f"{pkg}.model", f"{pkg}.model.kw_branches"]:
         mods[name] = types.ModuleType(name)
         sys.modules[name] = mods[name]
@@ -563,11 +641,15 @@ def test_install_patches_reference_namespaces(scp):
         pass
 
     mods[f"{pkg}.model.kw_branches"].GeneralBranch = GeneralBranch
+    mods[f"{pkg}.module.clip_official"].ClipModel = type("ClipModel", (), {})
     try:
         done = scp.install(pkg, strict=True)
         assert all(done.values())
         assert mods[f"{pkg}.module.losses"].MaskedContrastiveLoss is scp.MaskedContrastiveLoss
         assert mods[f"{pkg}.model.kw_branches"].Kw_BatchNorm is scp.Kw_BatchNorm
+        from speechclip_plus_b200.module import clip_glue
+        assert mods[f"{pkg}.module.clip_official"].ClipModel.encode_keywords is clip_glue.encode_keywords
+        assert mods[f"{pkg}.model.kw_branches"].get_keypadding_mask is clip_glue.get_keypadding_mask
         assert mods[f"{pkg}.module.speechclip_c_modules.kw_bn"].Kw_BatchNorm_dynamic is scp.Kw_BatchNorm_dynamic
         assert getattr(mods[f"{pkg}.module.speechclip_c_modules.vector_quantizers"], "SimpleVectorQuantizer") \
             is scp.SimpleVectorQuantizer
