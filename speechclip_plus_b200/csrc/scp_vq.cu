@@ -171,7 +171,8 @@ __device__ __forceinline__ tc::f32x2 ipow2(tc::f32x2 x) {
 
 struct Sweep1Epi {
   struct Params {
-    float* chunk_max;   // (Mp, n_chunks)
+    float* chunk_max;   // (Mp, n_chunks): maximum of every 32-column chunk (scanned by the arg-max kernel)
+    float* group_max;   // (Mp, n_chunks, 4): maximum of every 8-column group (read for candidate chunks only)
     float* partials;    // (Mp, n_slots, 4): sum e^c, sum c e^c, running max, sum e^{(c-max)/tau};  n_slots = 2*n_groups
     const float* tau;   // device scalar
     int n_chunks;
@@ -222,15 +223,16 @@ struct Sweep1Epi {
       for (int i = 0; i < 32; ++i)
         if ((bits >> i) & 1u) c[i] = kNegBig;
     }
-    // 3-input max tree (FMNMX3): 16 instructions for 32 values
-    float m8[11];
+    // maxima of the four 8-column groups (3-input max, FMNMX3: 4 instructions per group), one 16-byte store; the
+    // exact arg-max kernel re-scores only the groups that can hide the true maximum
+    float gm[4];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) m8[i] = tc::fmax3(c[3 * i], c[3 * i + 1], c[3 * i + 2]);
-    m8[10] = fmaxf(c[30], c[31]);
-    const float m3a = tc::fmax3(m8[0], m8[1], m8[2]), m3b = tc::fmax3(m8[3], m8[4], m8[5]);
-    const float m3c = tc::fmax3(m8[6], m8[7], m8[8]), m3d = fmaxf(m8[9], m8[10]);
-    const float cmax = fmaxf(tc::fmax3(m3a, m3b, m3c), m3d);
+    for (int g = 0; g < 4; ++g)
+      gm[g] = tc::fmax3(tc::fmax3(c[8 * g], c[8 * g + 1], c[8 * g + 2]), tc::fmax3(c[8 * g + 3], c[8 * g + 4], c[8 * g + 5]),
+                        fmaxf(c[8 * g + 6], c[8 * g + 7]));
+    const float cmax = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
     p.chunk_max[row * p.n_chunks + (col0 >> 5)] = cmax;
+    *reinterpret_cast<float4*>(p.group_max + (row * p.n_chunks + (col0 >> 5)) * 4) = make_float4(gm[0], gm[1], gm[2], gm[3]);
     if (cmax <= kNegBig) return;  // fully masked / padding chunk: contributes nothing (and has no finite maximum)
     if (pow10) {
       // |c| <= 1 and 1/tau = 10: e^{c/tau} = (e^c)^10 cannot overflow, so no running maximum is needed and the
@@ -281,59 +283,103 @@ __device__ __forceinline__ Best better(const Best& a, const Best& b) {
   return a;
 }
 
-constexpr int kSelMaxCand = 64;  // candidate chunks buffered per pass (more candidates -> more passes)
 
-// Exact re-scoring of one 32-column chunk by a 128-thread block: warp w scores columns [8w, 8w+8); the 32 lanes of a
-// warp split the D axis (coalesced 16-byte loads of the fp32 table row, all loads of the batch in flight together).
-// Two precision levels keep the fp64 pipe almost idle:
-//   1. fp32 scores of the 8 columns (16 products per lane + butterfly: error <= ~1.3e-6 * ||kw||),
-//   2. only the columns within 4e-6 * ||kw|| of the best fp32 score of the group (normally exactly one) are evaluated
-//      in fp64 (exact products of fp32 numbers, fp64 accumulation) -- the group's true maximum is always among them.
-// kreg holds this lane's slice of the keyword row.
+// Exact re-scoring of one 8-column group by a warp: the 32 lanes split the D axis (coalesced 16-byte loads, the loads
+// of all eight columns in flight together).
+// Three precision levels keep both HBM and the fp64 pipe almost idle:
+//   0. fp16-operand scores of the 8 columns from the UNIT fp16 table (the rows sweep 1 has just streamed: L2 hits, half
+//      the bytes of the fp32 table).  They carry the same <= 2^-10 bound as the tensor-core logits, so only columns
+//      within kRescueMargin of the row maximum (normally exactly one per row) can be the exact arg-max;
+//   1. fp32 scores of those columns from the fp32 table (16 products per lane + butterfly: error <= ~1.3e-6 * ||kw||);
+//   2. only the columns within 4e-6 * ||kw|| of the best fp32 score of the group are evaluated in fp64 (exact products
+//      of fp32 numbers, fp64 accumulation) -- the group's true maximum is always among them.
+// Before level 0 existed every candidate chunk cost 32 fp32 rows (64 KB) of mostly-cold HBM reads: 200 MB per call.
+// kreg / khreg hold this lane's slice of the keyword row (fp32) and of its unit fp16 copy.
 template <int NV>  // float4 vectors per lane: D <= 128*NV
 __device__ __forceinline__ Best rescore_chunk(const float* __restrict__ table, const float* __restrict__ table_norm,
-                                              int V, int D, int chunk, const float (&kreg)[NV][4], float margin2,
-                                              const MaskedCols& mc, int warp, int lane) {
+                                              const __half* __restrict__ table_hat, int V, int D, int group8,
+                                              const float (&kreg)[NV][4], const uint4 (&khreg)[(NV + 1) / 2],
+                                              float margin2, float thr16, const MaskedCols& mc, int lane) {
   Best best{0.0, -1};
   const int nvec = D >> 2;
-  constexpr int CB = NV <= 2 ? 8 : 4;  // columns whose loads are in flight together (register budget)
+  constexpr int NH = (NV + 1) / 2;  // uint4 (8 halfs) per lane
+  const int nvech = D >> 3;
+  // ---- level 0: fp16-operand scores, all 8 columns' loads in flight together
+  uint4 h[8][NH];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int v = group8 * 8 + c;  // < Vp: padding rows of the unit table are zero
+    const uint4* e = reinterpret_cast<const uint4*>(table_hat + (int64_t)v * D);
+#pragma unroll
+    for (int j = 0; j < NH; ++j) {
+      const int q = lane + 32 * j;
+      h[c][j] = q < nvech ? __ldg(e + q) : make_uint4(0, 0, 0, 0);
+    }
+  }
+  unsigned cand = 0;  // bit c: column c of this warp survives level 0 (warp-uniform)
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int v = group8 * 8 + c;
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < NH; ++j) {
+      const uint32_t a[4] = {h[c][j].x, h[c][j].y, h[c][j].z, h[c][j].w};
+      const uint32_t b[4] = {khreg[j].x, khreg[j].y, khreg[j].z, khreg[j].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 x = __half22float2(*reinterpret_cast<const __half2*>(&a[i]));
+        const float2 y = __half22float2(*reinterpret_cast<const __half2*>(&b[i]));
+        dot = fmaf(x.x, y.x, dot);
+        dot = fmaf(x.y, y.y, dot);
+      }
+    }
+    dot = warp_sum(dot);
+    if (v < V && !is_masked(mc, v) && dot >= thr16) cand |= 1u << c;
+  }
+  if (cand == 0) return best;
+  // ---- level 1: fp32 scores of the surviving columns
+  // (levels 1 and 2 visit one or two columns: rolled loops keep the kernel small enough for the instruction cache)
   float sc[8];
   float gmax = -INFINITY;
 #pragma unroll
-  for (int cb = 0; cb < 8; cb += CB) {
-    float4 x[CB][NV];
-#pragma unroll
-    for (int c = 0; c < CB; ++c) {
-      const int v = chunk * 32 + warp * 8 + cb + c;
-      const float4* e = reinterpret_cast<const float4*>(table + (int64_t)min(v, V - 1) * D);
+  for (int c = 0; c < 8; ++c) sc[c] = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {
+    if (cand & (1u << c)) {  // warp-uniform
+      const int v = group8 * 8 + c;
+      const float4* e = reinterpret_cast<const float4*>(table + (int64_t)v * D);
+      float4 x[NV];
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         const int q = lane + 32 * j;
-        x[c][j] = q < nvec ? __ldg(e + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[j] = q < nvec ? __ldg(e + q) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-    }
-#pragma unroll
-    for (int c = 0; c < CB; ++c) {
-      const int v = chunk * 32 + warp * 8 + cb + c;
       float dot = 0.f;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        dot = fmaf(kreg[j][0], x[c][j].x, dot);
-        dot = fmaf(kreg[j][1], x[c][j].y, dot);
-        dot = fmaf(kreg[j][2], x[c][j].z, dot);
-        dot = fmaf(kreg[j][3], x[c][j].w, dot);
+        dot = fmaf(kreg[j][0], x[j].x, dot);
+        dot = fmaf(kreg[j][1], x[j].y, dot);
+        dot = fmaf(kreg[j][2], x[j].z, dot);
+        dot = fmaf(kreg[j][3], x[j].w, dot);
       }
       dot = warp_sum(dot);
-      const bool ok = v < V && !is_masked(mc, v);
-      sc[cb + c] = ok ? dot / __ldg(table_norm + min(v, V - 1)) : -INFINITY;
-      gmax = fmaxf(gmax, sc[cb + c]);
+      const float sv = dot / __ldg(table_norm + v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i == c) sc[i] = sv;
+      gmax = fmaxf(gmax, sv);
     }
   }
+  // ---- level 2: fp64 for the near-ties of the group
   const float thr2 = gmax - margin2;
+  unsigned near = 0;
 #pragma unroll
+  for (int c = 0; c < 8; ++c)
+    if (sc[c] >= thr2 && sc[c] > -INFINITY) near |= 1u << c;
+#pragma unroll 1
   for (int c = 0; c < 8; ++c) {
-    if (sc[c] >= thr2 && sc[c] > -INFINITY) {  // warp-uniform; normally true for exactly one column
-      const int v = chunk * 32 + warp * 8 + c;
+    if (near & (1u << c)) {  // warp-uniform; normally true for exactly one column
+      const int v = group8 * 8 + c;
       const float4* e = reinterpret_cast<const float4*>(table + (int64_t)v * D);
       double dot = 0.0, nn = 0.0;
 #pragma unroll
@@ -355,20 +401,50 @@ __device__ __forceinline__ Best rescore_chunk(const float* __restrict__ table, c
   return best;  // identical in every lane of the warp
 }
 
+// warp <-> keyword row (four rows per 128-thread block).  A block-per-row version had a ~12 us serial critical path
+// per row (scan, barrier, candidate list, re-scoring, single-thread statistics) and only ~600 rows resident at a time:
+// 3.5 waves, 70 us.  One warp per row needs no block barriers or shared memory and keeps all M rows of the benchmark
+// shape resident in a single wave.
 template <int NV>
 __global__ void __launch_bounds__(128)
 vq_select_kernel(const float* __restrict__ kw, const float* __restrict__ table, const float* __restrict__ table_norm,
-                 int64_t M, int V, int D, const float* __restrict__ chunk_max, int n_chunks, const float* __restrict__ partials, int n_groups,
+                 const __half* __restrict__ table_hat, const __half* __restrict__ kw_hat, int64_t M, int V, int D,
+                 const float* __restrict__ chunk_max, const float* __restrict__ group_max, int n_chunks,
+                 const float* __restrict__ partials, int n_groups,
                  const float* __restrict__ tau_ptr, MaskedCols mc, int64_t* __restrict__ idx_out,
                  float* __restrict__ keywords, float* __restrict__ row_stats, float* __restrict__ code_hist,
                  float* __restrict__ lse1_l2) {
-  __shared__ float s_red[4];
-  __shared__ Best s_best[4];
-  __shared__ int s_cand[kSelMaxCand];
-  __shared__ int s_ncand;
-  const int64_t m = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // this lane's slice of the keyword row
+  const int lane = threadIdx.x & 31;
+  const int64_t m = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (m >= M) return;  // whole warp
+  // ---- statistics of the row: combine the per-group partials of sweep 1 (lane <-> group, fixed tree order)
+  {
+    const float tau = *tau_ptr;
+    float z1 = 0.f, c1 = 0.f, gmax = kNegBig;
+    for (int g = lane; g < n_groups; g += 32) {
+      const float4 q = *reinterpret_cast<const float4*>(partials + (m * n_groups + g) * 4);
+      z1 += q.x; c1 += q.y; gmax = fmaxf(gmax, q.z);
+    }
+    z1 = warp_sum(z1); c1 = warp_sum(c1); gmax = warp_max(gmax);
+    float zt = 0.f;
+    for (int g = lane; g < n_groups; g += 32) {
+      const float4 q = *reinterpret_cast<const float4*>(partials + (m * n_groups + g) * 4);
+      zt += q.w * expf((q.z - gmax) / tau);
+    }
+    zt = warp_sum(zt);
+    if (lane == 0) {
+      const float lse1 = logf(z1);
+      int n_valid = V;
+      for (int i = 0; i < mc.n; ++i) n_valid -= (mc.col[i] >= 0 && mc.col[i] < V);
+      // -sum p log(p + 1e-9) = H - n_valid*1e-9 + O(1e-8): at temperature 1 every p >= 1/(V e^2) >> 1e-9
+      float* rs = row_stats + m * 4;
+      rs[0] = lse1;
+      rs[1] = gmax / tau + logf(zt);
+      rs[2] = lse1 - c1 / z1 - (float)n_valid * 1e-9f;
+      lse1_l2[m] = -lse1 * kLog2e;  // sweep 2 adds it with one packed FMA
+    }
+  }
+  // ---- this lane's slice of the keyword row (fp32) and of its unit fp16 copy (the tensor-core operand of sweep 1)
   float kreg[NV][4];
   const int nvec = D >> 2;
   float kss = 0.f;
@@ -379,79 +455,67 @@ vq_select_kernel(const float* __restrict__ kw, const float* __restrict__ table, 
     kreg[j][0] = k4.x; kreg[j][1] = k4.y; kreg[j][2] = k4.z; kreg[j][3] = k4.w;
     kss += k4.x * k4.x + k4.y * k4.y + k4.z * k4.z + k4.w * k4.w;
   }
-  const float margin2 = 4e-6f * sqrtf(warp_sum(kss));  // 2 x the fp32 dot-product error bound, see rescore_chunk
-  // approximate (fp16-product) row maximum
-  const float* cm = chunk_max + m * n_chunks;
-  float mx = kNegBig;
-  for (int c = tid; c < n_chunks; c += 128) mx = fmaxf(mx, __ldg(cm + c));
-  mx = warp_max(mx);
-  if (lane == 0) s_red[warp] = mx;
-  if (tid == 0) s_ncand = 0;
-  __syncthreads();
-  mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
-  const float thr = mx - kRescueMargin;
-  // every chunk whose maximum could hide the true arg-max is re-scored exactly (usually one or two per row)
+  kss = warp_sum(kss);
+  const float margin2 = 4e-6f * sqrtf(kss);  // 2 x the fp32 dot-product error bound, see rescore_chunk
+  uint4 khreg[(NV + 1) / 2];
+#pragma unroll
+  for (int j = 0; j < (NV + 1) / 2; ++j) {
+    const int q = lane + 32 * j;
+    khreg[j] = q < (D >> 3) ? __ldg(reinterpret_cast<const uint4*>(kw_hat + m * D) + q) : make_uint4(0, 0, 0, 0);
+  }
   Best best{0.0, -1};
-  for (int base = 0; base < n_chunks; base += 128 * 8) {  // bounded passes keep the candidate buffer small
-    const int hi = min(n_chunks, base + 128 * 8);
-    for (int c0 = base; c0 < hi; c0 += 128) {
-      const int c = c0 + tid;
-      if (c < hi && __ldg(cm + c) >= thr) {
-        const int slot = atomicAdd(&s_ncand, 1);
-        if (slot < kSelMaxCand) s_cand[slot] = c;
+  if (kss > 0.f) {  // a zero keyword ties every cosine at 0: the first unmasked column wins (handled below)
+    // approximate (fp16-product) row maximum.  The row's chunk maxima are read ONCE from global memory with 16-byte
+    // loads and parked in this warp's slice of shared memory; the candidate pass then reads them back from there.
+    // (Two dependent passes of scalar global loads were the kernel's critical path; a fully unrolled register-resident
+    // scan instead inlined the re-scoring code 64 times and thrashed the instruction cache: 47 % stall_no_inst.)
+    extern __shared__ float s_scan[];
+    float* mine = s_scan + (size_t)(threadIdx.x >> 5) * n_chunks;
+    const float4* cm4 = reinterpret_cast<const float4*>(chunk_max + m * n_chunks);  // n_chunks % 8 == 0 (Vp % 256 == 0)
+    const int n4 = n_chunks >> 2;
+    float mx = kNegBig;
+#pragma unroll 4
+    for (int q = lane; q < n4; q += 32) {
+      const float4 t = __ldg(cm4 + q);
+      *reinterpret_cast<float4*>(mine + 4 * q) = t;
+      mx = fmaxf(mx, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
+    }
+    mx = warp_max(mx);  // (the shuffles also order the shared-memory writes before the reads below)
+    __syncwarp();
+    const float thr = mx - kRescueMargin;
+    // every chunk whose maximum could hide the true arg-max is re-scored exactly (usually one or two per row), and
+    // inside it only the 8-column groups whose own maximum qualifies
+#pragma unroll 1
+    for (int c0 = 0; c0 < n_chunks; c0 += 32) {
+      const float v = c0 + lane < n_chunks ? mine[c0 + lane] : kNegBig;
+      unsigned todo = __ballot_sync(0xffffffffu, v >= thr && v > kNegBig);
+#pragma unroll 1
+      while (todo) {
+        const int chunk = c0 + __ffs(todo) - 1;
+        todo &= todo - 1;
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(group_max + (m * n_chunks + chunk) * 4));
+        const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g)
+          if (gv[g] >= thr)
+            best = better(best, rescore_chunk<NV>(table, table_norm, table_hat, V, D, chunk * 4 + g, kreg, khreg,
+                                                  margin2, thr, mc, lane));
       }
     }
-    __syncthreads();
-    int ncand = s_ncand;
-    if (ncand > kSelMaxCand) {
-      // degenerate row (e.g. a zero keyword: every cosine ties): fall back to scoring every chunk of this pass
-      for (int c = base; c < hi; ++c) best = better(best, rescore_chunk<NV>(table, table_norm, V, D, c, kreg, margin2, mc, warp, lane));
-    } else {
-      for (int i = 0; i < ncand; ++i) best = better(best, rescore_chunk<NV>(table, table_norm, V, D, s_cand[i], kreg, margin2, mc, warp, lane));
-    }
-    __syncthreads();
-    if (tid == 0) s_ncand = 0;
-    __syncthreads();
   }
-  if (lane == 0) s_best[warp] = best;
-  __syncthreads();
-  best = better(better(s_best[0], s_best[1]), better(s_best[2], s_best[3]));
   int k = best.idx;
-  if (k < 0) {  // no finite candidate (all columns masked): first unmasked column, like argmax over equal values
+  if (k < 0) {  // no finite candidate (zero keyword / all columns masked): first unmasked column, like torch's argmax
     k = 0;
     while (k < V - 1 && is_masked(mc, k)) ++k;
   }
-  if (tid == 0) {
+  if (lane == 0) {
     idx_out[m] = k;
     atomicAdd(&code_hist[k], 1.0f);
-    // combine the per-group statistics
-    const float tau = *tau_ptr;
-    const float4* pp = reinterpret_cast<const float4*>(partials + m * n_groups * 4);
-    float z1 = 0.f, c1 = 0.f, gmax = kNegBig;
-    for (int g = 0; g < n_groups; ++g) {
-      const float4 q = pp[g];
-      z1 += q.x; c1 += q.y; gmax = fmaxf(gmax, q.z);
-    }
-    float zt = 0.f;
-    for (int g = 0; g < n_groups; ++g) {
-      const float4 q = pp[g];
-      zt += q.w * expf((q.z - gmax) / tau);
-    }
-    const float lse1 = logf(z1);
-    int n_valid = V;
-    for (int i = 0; i < mc.n; ++i) n_valid -= (mc.col[i] >= 0 && mc.col[i] < V);
-    // -sum p log(p + 1e-9) = H - n_valid*1e-9 + O(1e-8): at temperature 1 every p >= 1/(V e^2) >> 1e-9
-    const float ent = lse1 - c1 / z1 - (float)n_valid * 1e-9f;
-    float* rs = row_stats + m * 4;
-    rs[0] = lse1;
-    rs[1] = gmax / tau + logf(zt);
-    rs[2] = ent;
-    lse1_l2[m] = -lse1 * kLog2e;  // sweep 2 adds it with one packed FMA
   }
   // keywords = E[k]   (value of subword_prob @ E, kw_branches.py:195)
   const float4* src = reinterpret_cast<const float4*>(table + (int64_t)k * D);
   float4* dst = reinterpret_cast<float4*>(keywords + m * D);
-  for (int d4 = tid; d4 < D / 4; d4 += 128) dst[d4] = __ldg(src + d4);
+  for (int d4 = lane; d4 < D / 4; d4 += 32) dst[d4] = __ldg(src + d4);
 }
 
 // =====================================================================================================================
@@ -761,51 +825,48 @@ struct StoreEpi {
   __device__ __forceinline__ void finish() {}
 };
 
-// warp <-> row: g_khat = (U - s W) * scale / tau ; g_kw = (g_khat - <g_khat,khat> khat) / ||kw||
-__global__ void vq_bwd_finalize_kernel(const float* __restrict__ uw /* (k_splits, 2, Mp, D) */, int k_splits,
-                                       int64_t M, int64_t Mp, int D, const float* __restrict__ partials, int n_groups,
-                                       const float* __restrict__ g_aux, const float* __restrict__ kw,
-                                       const float* __restrict__ row_stats, const float* __restrict__ table_mean,
-                                       const float* __restrict__ tau_ptr, float* __restrict__ g_kw,
-                                       float* __restrict__ g_tau) {
-  const int lane = threadIdx.x & 31;
-  const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (m >= M) return;
+// block (D/4 threads) <-> row, thread <-> 4 channels:  g_khat = (U - s W) * scale / tau ;
+// g_kw = (g_khat - <g_khat,khat> khat) / ||kw||.  (A warp-per-row version left most of the 33 MB of split-K partials
+// to 256 resident warps and took 28 us; one block per row keeps every SM streaming.)
+__global__ void __launch_bounds__(256)
+vq_bwd_finalize_kernel(const float* __restrict__ uw /* (k_splits, 2, Mp, D) */, int k_splits, int64_t M, int64_t Mp,
+                       int D, const float* __restrict__ partials, int n_groups, const float* __restrict__ g_aux,
+                       const float* __restrict__ kw, const float* __restrict__ row_stats,
+                       const float* __restrict__ table_mean, const float* __restrict__ tau_ptr,
+                       float* __restrict__ g_kw, float* __restrict__ g_tau) {
+  __shared__ float s_red[8];
+  const int64_t m = blockIdx.x;
+  const int d0 = threadIdx.x * 4;
   const float tau = *tau_ptr;
   float sq = 0.f, sp = 0.f, sqc = 0.f, spc = 0.f;
-  for (int g = 0; g < n_groups; ++g) {
+  for (int g = 0; g < n_groups; ++g) {  // same address in every thread: broadcast loads
     const float4 q = *reinterpret_cast<const float4*>(partials + (m * n_groups + g) * 4);
     sq += q.x; sp += q.y; sqc += q.z; spc += q.w;
   }
   const float s_adj = sp > 0.f ? sq / sp : 0.f;
   const float scale = g_aux[m * 2] * table_mean[D] / (kPScale * tau);
   const float inv_norm = row_stats[m * 4 + 3];
-  float gk[32];  // D <= 1024 (checked on the host): this lane's slice of g_khat stays in registers
-  float proj = 0.f;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const int d = lane + 32 * j;
-    gk[j] = 0.f;
-    if (d < D) {
-      float u = 0.f, w = 0.f;
-      for (int ks = 0; ks < k_splits; ++ks) {
-        u += uw[(((int64_t)ks * 2 + 0) * Mp + m) * D + d];
-        w += uw[(((int64_t)ks * 2 + 1) * Mp + m) * D + d];
-      }
-      gk[j] = (u - s_adj * w) * scale;
-      proj = fmaf(gk[j], kw[m * D + d] * inv_norm, proj);
-    }
+  float4 u = make_float4(0.f, 0.f, 0.f, 0.f), w = u;
+  for (int ks = 0; ks < k_splits; ++ks) {
+    const float4 a = *reinterpret_cast<const float4*>(uw + (((int64_t)ks * 2 + 0) * Mp + m) * D + d0);
+    const float4 b = *reinterpret_cast<const float4*>(uw + (((int64_t)ks * 2 + 1) * Mp + m) * D + d0);
+    u.x += a.x; u.y += a.y; u.z += a.z; u.w += a.w;
+    w.x += b.x; w.y += b.y; w.z += b.z; w.w += b.w;
   }
+  const float4 k4 = *reinterpret_cast<const float4*>(kw + m * D + d0);
+  const float gk[4] = {(u.x - s_adj * w.x) * scale, (u.y - s_adj * w.y) * scale, (u.z - s_adj * w.z) * scale,
+                       (u.w - s_adj * w.w) * scale};
+  const float kh[4] = {k4.x * inv_norm, k4.y * inv_norm, k4.z * inv_norm, k4.w * inv_norm};
+  float proj = gk[0] * kh[0] + gk[1] * kh[1] + gk[2] * kh[2] + gk[3] * kh[3];
   proj = warp_sum(proj);
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const int d = lane + 32 * j;
-    if (d < D) {
-      const float kh = kw[m * D + d] * inv_norm;
-      g_kw[m * D + d] = (gk[j] - proj * kh) * inv_norm;
-    }
-  }
-  if (g_tau && lane == 0) {
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = proj;
+  __syncthreads();
+  proj = 0.f;
+  for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) proj += s_red[i];  // fixed order
+  *reinterpret_cast<float4*>(g_kw + m * D + d0) =
+      make_float4((gk[0] - proj * kh[0]) * inv_norm, (gk[1] - proj * kh[1]) * inv_norm,
+                  (gk[2] - proj * kh[2]) * inv_norm, (gk[3] - proj * kh[3]) * inv_norm);
+  if (g_tau && threadIdx.x == 0) {
     // d/dtau = -(1/tau^2) sum_v P (T - s) c      (T in true units = T' * |g| * norm_ref)
     const float contrib = -(g_aux[m * 2] * table_mean[D]) * (sqc - s_adj * spc) / (kPScale * tau * tau);
     atomicAdd(g_tau, contrib);
@@ -950,6 +1011,7 @@ static MaskedCols make_masked(const int32_t* cols, int n) {
 
 struct VqFwdWs {
   float* chunk_max;
+  float* group_max;
   float* partials;
   float* lse1_l2;
   float* metric_part;
@@ -986,6 +1048,7 @@ static VqFwdWs vq_fwd_ws(void* base, int64_t M, int64_t V) {
     return p;
   };
   w.chunk_max = static_cast<float*>(take((size_t)Mp * w.n_chunks * 4));
+  w.group_max = static_cast<float*>(take((size_t)Mp * w.n_chunks * 4 * 4));  // four 8-column group maxima per chunk
   w.partials = static_cast<float*>(take((size_t)Mp * w.n_groups * 2 * 16));
   w.lse1_l2 = static_cast<float*>(take((size_t)round_up(M, 256) * 4));
   w.metric_part = static_cast<float*>(take((size_t)(kMetricBlocks * 2 + 1) * 4));  // + the ticket counter
@@ -1110,6 +1173,7 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
     sc.n_upper_off = 0;
     Sweep1Epi::Params ep{};
     ep.chunk_max = ws.chunk_max;
+    ep.group_max = ws.group_max;
     ep.partials = ws.partials;
     ep.tau = tau;
     ep.n_chunks = ws.n_chunks;
@@ -1125,8 +1189,13 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
     if (rc) return rc;
   }
   // ---- exact arg-max, statistics, gather
+  const size_t sel_smem = (size_t)4 * ws.n_chunks * sizeof(float);  // one row of chunk maxima per warp
+  if (sel_smem > 48 * 1024)
+    return fail(SCP_ERR_UNSUPPORTED, "vq_fwd: V=%lld exceeds the arg-max kernel's shared-memory scan (V <= 98304)", (long long)V);
 #define SCP_SELECT(NVV)                                                                                              \
-  vq_select_kernel<NVV><<<(unsigned)M, 128, 0, s>>>(kw, table, table_norm, M, (int)V, (int)D, ws.chunk_max, ws.n_chunks, \
+  vq_select_kernel<NVV><<<(unsigned)ceil_div(M, 4), 128, sel_smem, s>>>(kw, table, table_norm, reinterpret_cast<const __half*>(table_hat),   \
+                                                    reinterpret_cast<const __half*>(kw_hat), M, (int)V, (int)D,           \
+                                                    ws.chunk_max, ws.group_max, ws.n_chunks,                              \
                                                     ws.partials, 2 * ws.n_groups, tau, mc, idx, keywords, row_stats, \
                                                     code_hist, ws.lse1_l2)
   if (D <= 128) SCP_SELECT(1);
@@ -1262,7 +1331,7 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
     if (rc) return rc;
   }
   if (g_tau && cudaMemsetAsync(g_tau, 0, 4, s) != cudaSuccess) return fail(SCP_ERR_CUDA, "memset g_tau");
-  vq_bwd_finalize_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, s>>>(ws.uw, ws.k_splits, M, Mp, (int)D, ws.partials,
+  vq_bwd_finalize_kernel<<<(unsigned)M, (unsigned)(D / 4), 0, s>>>(ws.uw, ws.k_splits, M, Mp, (int)D, ws.partials,
                                                                   2 * ws.n_groups, ws.g_aux, kw, row_stats, table_mean,
                                                                   tau, g_kw, g_tau);
   SCP_CUDA_LAUNCH_CHECK("vq_bwd_finalize");
