@@ -416,14 +416,15 @@ def _tie_tolerant_index_check(idx, kw, table, prob_msk=(0, 2, 3)):
     return len(bad)
 
 
-@pytest.mark.parametrize("shape", [(32, 8, 8112, 512), (16, 12, 19787, 768), (7, 5, 1000, 64), (1, 1, 300, 64)])
-def test_vq_fused_vs_oracle(scp, shape):
+@pytest.mark.parametrize("tau", [0.1, 0.07])  # 0.1: the (e^c)^10 fast path of sweep 1; 0.07: the online-max path
+@pytest.mark.parametrize("shape", [(32, 8, 8112, 512), (16, 12, 19787, 768), (7, 5, 1000, 64), (1, 1, 300, 64),
+                                   (5, 3, 2000, 1024), (40, 8, 4096, 256), (33, 1, 600, 128), (3, 7, 12000, 384)])
+def test_vq_fused_vs_oracle(scp, shape, tau):
     B, K, V, D = shape
     gen = torch.Generator().manual_seed(V + B)
     table = torch.randn(V, D, generator=gen) * 0.02 + 0.003 * torch.randn(1, D, generator=gen)
     kw = torch.randn(B, K, D, generator=gen) * table.std(0) + table.mean(0)
     gout = torch.randn(B, K, D, generator=gen)
-    tau = 0.1
     vq = _make_vq(scp, f"fixed={tau}", True)
     kwd = kw.cuda().requires_grad_(True)
     res, out = vq.quantize_keywords(kwd, table.cuda())
