@@ -15,7 +15,45 @@ import torch
 
 from .. import _lib
 
-__all__ = ["splice_keywords", "encode_keywords", "get_keypadding_mask"]
+__all__ = ["splice_keywords", "encode_keywords", "get_keypadding_mask", "ReducedVocab", "reduce_subword_embedding"]
+
+
+class ReducedVocab:
+    """N2 -- the vocabulary-reduction state ``ClipModel.__init__`` builds from a ``text_clip_vocab_usage_byfreq.npy``
+    file (avssl/module/clip_official.py:63-108; file format: (V',2) int64 rows ``[original_token_id, count]`` sorted by
+    frequency, avssl/data/{flickr,coco}_stat/).  Attribute names follow the reference so that code written against
+    ``ClipModel`` (``selected_text_emb_ids``, ``original2Reduced``, ``startOfTxt_reduced`` ...) reads the same."""
+
+    def __init__(self, usage, sot_token: int, eot_token: int):
+        import numpy as np
+        _data = np.load(usage) if isinstance(usage, (str, bytes)) or hasattr(usage, "__fspath__") else np.asarray(usage)
+        if _data.ndim != 2 or _data.shape[1] != 2:
+            raise ValueError(f"vocabulary usage table must be (V',2) [token id, count], got {_data.shape}")
+        self.selected_text_emb_ids = _data[:, 0]                                           # :71
+        dist = _data[:, 1]
+        self.selected_text_emb_ids_dist = torch.from_numpy(dist / np.sum(dist))           # :72-76
+        self.original2Reduced = {int(old): new for new, old in enumerate(self.selected_text_emb_ids)}   # :94-97
+        self.reducedl2Original = {new: int(old) for new, old in enumerate(self.selected_text_emb_ids)}  # :98-101
+        self.startOfTxt_reduced = self.original2Reduced[int(sot_token)]                   # :103-105 (KeyError if absent)
+        self.endOfTxt_reduced = self.original2Reduced[int(eot_token)]                     # :107-109
+
+    def __len__(self) -> int:
+        return len(self.selected_text_emb_ids)
+
+
+def reduce_subword_embedding(token_embedding: torch.nn.Embedding, usage, sot_token: int, eot_token: int,
+                             trainable: bool = False):
+    """Replacement for the ``reduce_subword_embbedding`` branch of ``ClipModel.__init__`` (clip_official.py:63-108):
+    returns ``(reduced nn.Embedding, ReducedVocab, original weight)``.  The reduced table is the frozen (V',D) matrix the
+    VQ runs against; its fp16 unit-norm copy, transpose, norms and mean are built lazily -- once per table version -- by
+    ``TokenTableCache`` (scp_vq_prepare_table), which is where the reference recomputes ``||e_v||`` K times per step.
+    With the by-frequency files row 0 is the pad token ``!``, rows 2 and 3 are SOT / EOT: the ``prob_msk=[0,2,3]`` default
+    of the quantiser (my_vector_quantizer.py:64)."""
+    vocab = ReducedVocab(usage, sot_token, eot_token)
+    original = token_embedding.weight
+    ids = torch.as_tensor(vocab.selected_text_emb_ids, dtype=torch.long, device=original.device)
+    reduced = torch.nn.Embedding.from_pretrained(original.detach()[ids], freeze=not trainable)      # :84-92
+    return reduced, vocab, original
 
 
 class _SpliceFn(torch.autograd.Function):

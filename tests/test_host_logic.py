@@ -40,6 +40,30 @@ def test_upstream_tail_host_logic():
         fuse_upstream_features([torch.zeros(1, 2, 4)] * 3, scp.WeightedSumLayer(3), True, "method1")
 
 
+def test_vocabulary_reduction_matches_reference_format():
+    """N2: the (V',2) [token id, count] by-frequency table of the reference (first 64 rows of
+    avssl/data/flickr_stat/text_clip_vocab_usage_byfreq.npy) -> reduced table, id maps, SOT / EOT positions."""
+    import os
+    import numpy as np
+    from speechclip_plus_b200.module.clip_glue import ReducedVocab, reduce_subword_embedding
+    usage = np.load(os.path.join(os.path.dirname(__file__), "golden", "vocab_usage_byfreq_head64.npy"))
+    assert usage.shape == (64, 2) and usage.dtype == np.int64
+    emb = torch.nn.Embedding(49408, 8)
+    reduced, vocab, original = reduce_subword_embedding(emb, usage, sot_token=49406, eot_token=49407)
+    assert len(vocab) == 64 and reduced.weight.shape == (64, 8) and not reduced.weight.requires_grad
+    assert original is emb.weight
+    assert torch.equal(reduced.weight, emb.weight.detach()[torch.from_numpy(usage[:, 0])])   # clip_official.py:84-86
+    # rows 0 / 2 / 3 are pad, SOT, EOT: exactly the quantiser's default prob_msk (my_vector_quantizer.py:64)
+    assert vocab.reducedl2Original[0] == 0 and vocab.startOfTxt_reduced == 2 and vocab.endOfTxt_reduced == 3
+    assert vocab.original2Reduced[320] == 1 and vocab.reducedl2Original[1] == 320
+    assert abs(float(vocab.selected_text_emb_ids_dist.sum()) - 1.0) < 1e-12
+    assert vocab.selected_text_emb_ids_dist.dtype == torch.float64
+    with pytest.raises(KeyError):                                           # SOT missing from the table (:103-105)
+        ReducedVocab(usage[4:], 49406, 49407)
+    with pytest.raises(ValueError):
+        ReducedVocab(usage[:, 0], 49406, 49407)
+
+
 def test_vector_quantizer_constructor_semantics():
     fixed = scp.SimpleVectorQuantizer("fixed=0.1")
     assert fixed.temp_type == "fixed" and "curr_temp" in dict(fixed.named_buffers())
