@@ -185,6 +185,33 @@ int scp_kw_splice_bwd(const void* g_x, int dtype, const int64_t* kw_num, int64_t
 /* mask[b,j] = (j >= lens[b]) as bytes (True = padding). */
 int scp_keypadding_mask(const int64_t* lens, int64_t B, int64_t max_len, uint8_t* mask, scp_stream_t stream);
 
+/* ---- N4: CIF down-sampler -- replaces CIF.integrate_and_fire (avssl/module/cif.py:157-311), which produces the
+ *      dynamic-length keyword sequence of the "+" branches ------------------------------------------------------------ */
+/* Step 1: csum (B,S) = SEQUENTIAL fp32 cumulative sum of alpha (B,S); feat_len[b] = clip(floor(csum[b,S-1]/threshold), 1,
+ * max_len) (cif.py:183-188, MAX_FEAT_LEN = 75).  The caller then reads T = max_b feat_len (the output shape depends on
+ * it, as in the reference). */
+int scp_cif_plan(const float* alpha, int64_t B, int64_t S, float threshold, int max_len,
+                 float* csum, int64_t* feat_len, scp_stream_t stream);
+/* Step 2: out (B, T+1, C) f32 = integrate-and-fire of x (B,S,C) f32 (cif.py:191-243; row T collects the tail); every
+ * output row is written exactly once.  fire_mask (nullable, (B,S) bytes) = fire_num > 0 (:207); tail_w (nullable, (B,)) =
+ * weight that reached the row just past feat_len[b] (:251-258). */
+int scp_cif_fire_fwd(const float* x, const float* alpha, const float* csum, const int64_t* feat_len,
+                     int64_t B, int64_t S, int64_t C, float threshold, int64_t T,
+                     float* out, uint8_t* fire_mask, float* tail_w, scp_stream_t stream);
+/* Inference tail handling (cif.py:246-296) on out (B,T1,C), T1 = T+1: utterances with tail_w >= firing_threshold fire
+ * once more (row feat_len[b] scaled by threshold/tail_w), feat_len_new = min(feat_len + extend, max_len), rows >=
+ * feat_len_new erased. */
+int scp_cif_tail(float* out, int64_t B, int64_t T1, int64_t C, const int64_t* feat_len, const float* tail_w,
+                 float threshold, float firing_threshold, int max_len, int64_t* feat_len_new, scp_stream_t stream);
+/* Backward of steps 2(+3): g_out (B,T_out,C) is the gradient of the returned slice out[:, :T_out]; keep_len / scale_row /
+ * tail_w (nullable) describe the tail handling of the forward (feat_len_new, feat_len, tail_w).  g_x (B,S,C), g_alpha (B,S)
+ * (through right_weight = csum - right_idx*threshold and left_weight = alpha - right_weight - ..., :209-224).
+ * workspace: 2*B*S floats. */
+int scp_cif_fire_bwd(const float* g_out, int64_t T_out, const float* x, const float* alpha, const float* csum,
+                     int64_t B, int64_t S, int64_t C, float threshold, int64_t T,
+                     const int64_t* keep_len, const int64_t* scale_row, const float* tail_w, float firing_threshold,
+                     float* g_x, float* g_alpha, void* workspace, size_t workspace_bytes, scp_stream_t stream);
+
 /* ---- N0 + G0: L2-normalise the loss features and pack them into the all-gather send buffer
  *      (avssl/model/kwClip.py:857, :905-907, :913-915; gather point kwClip.py:149-169) -------------------- */
 /* packed layout per rank: n_feats blocks of (n,D) f32 followed by n int64 ids.  feats: HOST array of device ptrs.

@@ -34,6 +34,7 @@ __all__ = [
     "upstream_tail",
     "kw_batchnorm",
     "splice_keywords",
+    "cif_integrate_and_fire",
     "keypadding_mask",
     "cosine_scores_loop",
     "cosine_scores",
@@ -326,6 +327,59 @@ def vq_keyword_grad(keywords_in: torch.Tensor, table: torch.Tensor, curr_temp, g
 def l2_normalise(feat: torch.Tensor) -> torch.Tensor:
     """f / ||f||_2 over the last dim, no epsilon (kwClip.py:857)."""
     return feat / feat.norm(dim=-1, keepdim=True)
+
+
+# ----------------------------------------------------------------------------------------
+# N4  CIF integrate-and-fire              avssl/module/cif.py:157-311
+# ----------------------------------------------------------------------------------------
+def cif_integrate_and_fire(x: torch.Tensor, alpha: torch.Tensor, threshold: float = 1.0,
+                           target_lengths: Optional[torch.Tensor] = None, apply_tail_handling: bool = True,
+                           firing_threshold: float = 0.5, max_feat_len: int = 75
+                           ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """CIF.integrate_and_fire restated through an explicit (B,S,T+1) weight matrix ``W`` with ``out = W^T x``:
+    source ``s`` spreads ``alpha_s`` over the output rows ``left_s .. right_s`` (rows = floor(cumsum/threshold), clipped
+    to T, cif.py:193-201): ``right_w = csum - right*thr`` where it fires (:209-211), ``thr`` on each of the
+    ``extra = max(fire_num-1,0)`` rows in between (:226-243), ``left_w = alpha - right_w - extra*thr`` (:219-221).  The
+    indices carry no gradient (:194); the weights do.  Tail handling as cif.py:246-298.
+    Returns (features (B,T',C), lengths (B,), fired marks (B,S))."""
+    B, S, C = x.shape
+    feat_len = (alpha.sum(1) / threshold).floor().clip(min=1, max=max_feat_len).long()   # :183-188
+    T = int(feat_len.max())
+    csum = alpha.cumsum(-1)
+    with torch.no_grad():
+        right = (csum / threshold).floor().long().clip(min=0, max=T)
+        left = torch.cat([torch.zeros(B, 1, dtype=torch.long), right[:, :-1]], dim=1)
+        fire = right - left
+        extra = (fire - 1).clip(min=0)
+    fire_mask = fire > 0
+    right_w = torch.where(fire_mask, csum - right.to(alpha.dtype) * threshold, torch.zeros((), dtype=alpha.dtype))
+    left_w = alpha - right_w - extra.to(alpha.dtype) * threshold
+    W = torch.zeros(B, S, T + 1, dtype=x.dtype)
+    W = W.scatter_add(2, right.unsqueeze(-1), right_w.to(x.dtype).unsqueeze(-1))
+    W = W.scatter_add(2, left.unsqueeze(-1), left_w.to(x.dtype).unsqueeze(-1))
+    for e in range(1, int(extra.max()) + 1):
+        idx = (left + e).clip(max=T)
+        W = W.scatter_add(2, idx.unsqueeze(-1), (threshold * (extra >= e)).to(x.dtype).unsqueeze(-1))
+    out = torch.einsum("bst,bsc->btc", W, x)
+    if apply_tail_handling and target_lengths is None:
+        fl = feat_len.unsqueeze(1)
+        tail_w = (torch.where(right == fl, right_w, torch.zeros(())) + torch.where(left == fl, left_w, torch.zeros(()))).sum(-1)
+        extend = tail_w >= firing_threshold
+        scale = torch.ones(B, T + 1, dtype=out.dtype)
+        scale[torch.arange(B), feat_len] = torch.where(extend, threshold / tail_w, torch.ones(())).to(out.dtype).detach()
+        out = out * scale.unsqueeze(-1)
+        if bool(extend.any()):
+            new_len = feat_len + extend.long()
+            fire_mask = fire_mask.clone()
+            fire_mask[:, new_len - 1] = fire_mask[:, new_len - 1] + extend      # the (B,B) broadcast of :281-283
+            feat_len = new_len.clip(max=max_feat_len)
+        T = int(feat_len.max())
+        out = out[:, :T]
+        keep = torch.arange(T)[None, :] < feat_len[:, None]
+        out = out * keep.unsqueeze(-1)
+    else:
+        out = out[:, :T]
+    return out, feat_len, fire_mask
 
 
 # ----------------------------------------------------------------------------------------

@@ -7,6 +7,7 @@ Public surface (mirrors the reference's ``avssl.module`` names for this path):
     fused_vq_audio_features    body of GeneralBranch.vq_audio_features, avssl/model/kw_branches.py:181-197
     MaskedContrastiveLoss      avssl/module/losses.py
     Kw_BatchNorm(_dynamic)     avssl/module/speechclip_c_modules/kw_bn.py          (keyword batch-norm before the VQ)
+    CIF                        avssl/module/cif.py                                  (integrate-and-fire down-sampler)
     fuse_upstream_features     caller tail of the HuBERT wrapper, avssl/module/speech_encoder_plus.py:572-622
     gather_loss_feats / compute_loss     gather point + loss of avssl/model/kwClip.py:149-193, :999-1040
     install()                  registers the above in the reference's plugin namespaces
@@ -20,6 +21,7 @@ from .module.vector_quantizers import SimpleVectorQuantizer, TokenTableCache, fu
 from .module.losses import MaskedContrastiveLoss  # noqa: F401
 from .module.kw_bn import Kw_BatchNorm, Kw_BatchNorm_dynamic  # noqa: F401
 from .module.speech_encoder_plus import fuse_upstream_features, upstream_feat_len  # noqa: F401
+from .module.cif import CIF  # noqa: F401
 from .model.kw_glue import compute_loss, gather_loss_feats, ddp_grad_scale  # noqa: F401
 from .install import install  # noqa: F401
 

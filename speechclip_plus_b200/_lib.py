@@ -67,6 +67,14 @@ SIGNATURES = {
     "scp_kw_splice_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p,
                                   c_void_p]),
     "scp_keypadding_mask": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "scp_cif_plan": (c_int, [c_void_p, c_int64, c_int64, c_float, c_int, c_void_p, c_void_p, c_void_p]),
+    "scp_cif_fire_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_int64,
+                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "scp_cif_tail": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_float, c_float, c_int, c_void_p,
+                             c_void_p]),
+    "scp_cif_fire_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float,
+                                 c_int64, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_size_t,
+                                 c_void_p]),
     "scp_pack_bytes": (c_size_t, [c_int, c_int64, c_int64]),
     "scp_l2norm_pack": (c_int, [POINTER(c_void_p), c_int, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),

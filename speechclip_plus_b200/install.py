@@ -6,6 +6,7 @@ The reference resolves the three hot-path classes by name on Python modules:
   * ``WeightedSumLayer(...)`` imported by name                    avssl/module/speech_encoder_plus.py:24, :218-220, :472-476
   * the cosine + lookup glue is a method of ``GeneralBranch``     avssl/model/kw_branches.py:158-197
   * ``Kw_BatchNorm`` / ``Kw_BatchNorm_dynamic`` imported by name  avssl/model/kw_branches.py:19, :95, :629
+  * ``CIF`` imported by name                                      avssl/model/kw_branches.py:17, :617
 
 ``install()`` must run after ``import avssl`` and before the model is constructed.
 """
@@ -21,6 +22,7 @@ def install(avssl_package: str = "avssl", strict: bool = False) -> dict:
     from .module.vector_quantizers import SimpleVectorQuantizer, fused_vq_audio_features
     from .module.weighted_sum import WeightedSumLayer
     from .module.kw_bn import Kw_BatchNorm, Kw_BatchNorm_dynamic
+    from .module.cif import CIF
 
     done = {}
 
@@ -47,6 +49,8 @@ def install(avssl_package: str = "avssl", strict: bool = False) -> dict:
     for name, cls in (("Kw_BatchNorm", Kw_BatchNorm), ("Kw_BatchNorm_dynamic", Kw_BatchNorm_dynamic)):
         patch(f"{p}.module.speechclip_c_modules.kw_bn", name, cls)
         patch(f"{p}.model.kw_branches", name, cls)  # imported by name there (kw_branches.py:19)
+    patch(f"{p}.module.cif", "CIF", CIF)                 # N4: imported by name in kw_branches.py
+    patch(f"{p}.model.kw_branches", "CIF", CIF)
     # N3: the text-transformer input splice replaces the body of ClipModel.encode_keywords; get_keypadding_mask by name
     try:
         from .module.clip_glue import encode_keywords, get_keypadding_mask

@@ -16,6 +16,7 @@ Reference entry points exercised (paths relative to /root/reference):
   * avssl/module/speechclip_c_modules/my_vector_quantizer.py  SimpleVectorQuantizer.forward   (V3)
   * avssl/module/clip_official.py:222-279   ClipModel.encode_keywords around a stand-in text tower;
     avssl/util/data_utils.py:6-22           get_keypadding_mask                            (N3)
+  * avssl/module/cif.py:97-311              CIF.forward / CIF.integrate_and_fire           (N4)
   * avssl/module/losses.py:129-245          MaskedContrastiveLoss                          (S3)
   * avssl/model/kwClip.py:999-1040          KWClip_GeneralTransformer.compute_loss         (C0)
 """
@@ -238,6 +239,68 @@ def golden_splice():
 
 
 # ----------------------------------------------------------------------------------------------
+def golden_cif():
+    """The reference's CIF down-sampler (cif.py): integrate_and_fire in training mode (target lengths, scaling, tail
+    ignored), with several fires per source, in inference mode (tail handling with and without an extra fire), without
+    tail handling, and one full CIF.forward (conv weight generator + scaling + integrate)."""
+    cif_mod = ref.load_leaf("avssl/module/cif.py", "ref_cif")
+    cases = [
+        # name, B, S, C, mode, alpha scale
+        ("cif_train_scaled", 4, 40, 64, "train", 0.3),
+        ("cif_train_multifire", 3, 6, 32, "train_multifire", 0.5),
+        ("cif_infer_tail", 6, 37, 64, "infer", 0.35),
+        ("cif_infer_notail", 3, 25, 32, "notail", 0.4),
+    ]
+    for i, (name, B, S, C, mode, a_scale) in enumerate(cases):
+        g = _gen(800 + i)
+        x = torch.randn(B, S, C, generator=g).requires_grad_(True)
+        raw = (torch.rand(B, S, generator=g) * 2 * a_scale)
+        lens = torch.randint(S // 2, S + 1, (B,), generator=g)
+        lens[0] = S
+        pad = torch.arange(S)[None, :] >= lens[:, None]
+        raw = raw.masked_fill(pad, 0.0).requires_grad_(True)
+        layer = cif_mod.CIF(cif_threshold=1.0, cif_output_dim=C, encoder_embed_dim=C,
+                            apply_tail_handling=(mode != "notail"))
+        target = None
+        alpha = raw
+        if mode.startswith("train"):
+            target = torch.tensor([12, 5, 9, 3][:B]) if mode == "train" else torch.tensor([10, 13, 7])
+            alpha = raw * ((1.0 * target.type_as(raw) + 1e-5) / raw.sum(1)).unsqueeze(1)   # the scaling of cif.py:126-129
+        out = layer.integrate_and_fire(x, alpha, target_lengths=target)
+        feats = out["dsample_feats"]
+        gy = torch.randn(feats.shape, generator=g)
+        if mode == "infer":
+            # the reference updates fire_mask in place after autograd saved it (cif.py:281-283): its inference tail path
+            # cannot be back-propagated -- forward values only
+            gx, ga = torch.zeros_like(x), torch.zeros_like(raw)
+        else:
+            gx, ga = torch.autograd.grad(feats, [x, raw], grad_outputs=gy)
+        save(name, x=x, alpha_raw=raw, mode=np.array(mode), target_len=(target if target is not None else np.array([], dtype=np.int64)),
+             apply_tail_handling=np.array(mode != "notail"), alpha=alpha, feats=feats, feat_len=out["dsample_feats_length"],
+             pad_mask=out["dsample_feats_pad_mask"], fired_marks=out["fired_marks"], grad_feats=gy, grad_x=gx,
+             grad_alpha_raw=ga)
+    # full module forward: conv weight generator -> clip / mask -> scaling -> integrate (training-style call, eval() so
+    # that the two nn.Dropout layers are inert)
+    g = _gen(850)
+    B, S, C = 3, 30, 32
+    torch.manual_seed(SEED + 850)
+    layer = cif_mod.CIF(cif_threshold=1.0, cif_output_dim=C, encoder_embed_dim=C, conv_cif_width=3, scaling_step=100).eval()
+    x = torch.randn(B, S, C, generator=g).requires_grad_(True)
+    lens = torch.tensor([30, 21, 26])
+    pad = torch.arange(S)[None, :] >= lens[:, None]
+    target = torch.tensor([4, 2, 3])
+    res = layer({"audio_feat": x, "audio_feat_pad_mask": pad, "global_step": 0}, target)
+    gy = torch.randn(res["dsample_feats"].shape, generator=g)
+    params = list(layer.parameters())
+    grads = torch.autograd.grad(res["dsample_feats"].mul(gy).sum() + res["quantity_out"].sum(), [x] + params)
+    save("cif_forward_train", x=x, pad_mask_in=pad, target_len=target, feats=res["dsample_feats"],
+         feat_len=res["dsample_feats_length"], quantity_out=res["quantity_out"], orig_alpha=res["orig_alpha"],
+         alpha=res["alpha"], original_length=res["original_length"], grad_feats=gy, grad_x=grads[0],
+         **{f"param_{n.replace('.', '_')}": p for n, p in layer.named_parameters()},
+         **{f"grad_{n.replace('.', '_')}": gr for (n, _), gr in zip(layer.named_parameters(), grads[1:])})
+
+
+# ----------------------------------------------------------------------------------------------
 def _fake_branch(kb, vq_mod, table: torch.Tensor, temp_spec: str, training: bool):
     """A GeneralBranch whose projection is the identity, so that vq_audio_features (kw_branches.py:181-197)
     runs V1 + V3 + V4 of the reference on the given keyword vectors."""
@@ -377,6 +440,7 @@ if __name__ == "__main__":
     golden_s1_tail()
     golden_kwbn()
     golden_splice()
+    golden_cif()
     golden_vq()
     golden_nce()
     golden_hybrid_loss()

@@ -340,6 +340,93 @@ def test_keyword_splice_full_size(scp, dtype):
 
 
 # =====================================================================================================================
+# N4 CIF down-sampler
+# =====================================================================================================================
+def _scaled_alpha(raw, target):
+    if target is None:
+        return raw
+    return raw * ((1.0 * target.type_as(raw) + 1e-5) / raw.sum(1)).unsqueeze(1)   # cif.py:126-129
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names("cif_") if n != "cif_forward_train"])
+def test_cif_integrate_and_fire_golden(scp, name):
+    from speechclip_plus_b200.module.cif import integrate_and_fire
+    g = load_golden(name)
+    x = g["x"].cuda().requires_grad_(True)
+    raw = g["alpha_raw"].cuda().requires_grad_(True)
+    target = g["target_len"].cuda() if g["target_len"].numel() else None
+    res = integrate_and_fire(x, _scaled_alpha(raw, target), 1.0, target, g["apply_tail_handling"])
+    assert torch.equal(res["dsample_feats_length"].cpu(), g["feat_len"])
+    assert torch.equal(res["fired_marks"].cpu(), g["fired_marks"])
+    assert torch.equal(res["dsample_feats_pad_mask"].cpu(), g["pad_mask"])
+    assert res["dsample_feats"].shape == g["feats"].shape and rel_err(res["dsample_feats"], g["feats"]) < TOL
+    if g["mode"] != "infer":
+        gx, ga = torch.autograd.grad(res["dsample_feats"], [x, raw], grad_outputs=g["grad_feats"].cuda())
+        assert norm_err(gx, g["grad_x"]) < TOL and norm_err(ga, g["grad_alpha_raw"]) < TOL
+
+
+def test_cif_module_forward_golden(scp):
+    """Full CIF.forward (conv weight generator + clip / mask + scaling + integrate) with the reference's parameters."""
+    from speechclip_plus_b200.module.cif import CIF
+    g = load_golden("cif_forward_train")
+    C = g["x"].shape[-1]
+    layer = CIF(cif_threshold=1.0, cif_output_dim=C, encoder_embed_dim=C, conv_cif_width=3, scaling_step=100)
+    assert sorted(n.replace(".", "_") for n, _ in layer.named_parameters()) == \
+        sorted(k[len("param_"):] for k in g if k.startswith("param_"))          # same parameter names as the reference
+    with torch.no_grad():
+        for n, p in layer.named_parameters():
+            p.copy_(g["param_" + n.replace(".", "_")])
+    layer = layer.cuda().eval()
+    x = g["x"].cuda().requires_grad_(True)
+    res = layer({"audio_feat": x, "audio_feat_pad_mask": g["pad_mask_in"].cuda(), "global_step": 0},
+                g["target_len"].cuda())
+    assert torch.equal(res["dsample_feats_length"].cpu(), g["feat_len"])
+    assert torch.equal(res["original_length"].cpu(), g["original_length"])
+    for key, ref_key in (("dsample_feats", "feats"), ("quantity_out", "quantity_out"), ("orig_alpha", "orig_alpha"),
+                         ("alpha", "alpha")):
+        assert rel_err(res[key], g[ref_key]) < TOL, key
+    params = list(layer.parameters())
+    grads = torch.autograd.grad(res["dsample_feats"].mul(g["grad_feats"].cuda()).sum() + res["quantity_out"].sum(),
+                                [x] + params)
+    assert norm_err(grads[0], g["grad_x"]) < TOL
+    for (n, _), gr in zip(layer.named_parameters(), grads[1:]):
+        assert norm_err(gr, g["grad_" + n.replace(".", "_")]) < 2e-3, n
+    assert layer.apply_scaling                                           # global_step 0 < scaling_step (cif.py:102-104)
+    layer({"audio_feat": x.detach(), "audio_feat_pad_mask": g["pad_mask_in"].cuda(), "global_step": 100}, g["target_len"].cuda())
+    assert not layer.apply_scaling
+
+
+@pytest.mark.parametrize("mode", ["train", "infer"])
+def test_cif_full_size_vs_oracle(scp, mode):
+    """B=64 utterances of 249 HuBERT frames x 768 (the "+" branches' input), ~12 keywords each."""
+    from speechclip_plus_b200.module.cif import integrate_and_fire
+    B, S, C = 64, 249, 768
+    gen = torch.Generator().manual_seed(11 if mode == "train" else 12)
+    x = torch.randn(B, S, C, generator=gen)
+    raw = torch.rand(B, S, generator=gen) * 0.1
+    lens = torch.randint(120, S + 1, (B,), generator=gen)
+    raw = raw.masked_fill(torch.arange(S)[None, :] >= lens[:, None], 0.0)
+    target = (lens / 20).round().long() if mode == "train" else None       # kw_branches.py:684
+    xd, rd = x.cuda().requires_grad_(True), raw.cuda().requires_grad_(True)
+    res = integrate_and_fire(xd, _scaled_alpha(rd, target.cuda() if target is not None else None), 1.0,
+                             target.cuda() if target is not None else None)
+    xr, rr = x.double().requires_grad_(True), raw.double().requires_grad_(True)
+    feats, feat_len, fired = oracle.cif_integrate_and_fire(xr, _scaled_alpha(rr, target), 1.0, target)
+    assert torch.equal(res["dsample_feats_length"].cpu(), feat_len)
+    assert torch.equal(res["fired_marks"].cpu(), fired)
+    assert rel_err(res["dsample_feats"], feats) < TOL
+    gy = torch.randn(feats.shape, generator=gen)
+    gx, ga = torch.autograd.grad(res["dsample_feats"], [xd, rd], grad_outputs=gy.cuda())
+    gx_r, ga_r = torch.autograd.grad(feats, [xr, rr], grad_outputs=gy.double())
+    assert norm_err(gx, gx_r) < TOL and norm_err(ga, ga_r) < TOL
+    # conservation: without scaling every unit of alpha lands in exactly one output row (incl. the tail)
+    if mode == "infer":
+        ones = torch.ones(B, S, 4, device="cuda")
+        r1 = integrate_and_fire(ones, rd.detach(), 1.0, None, apply_tail_handling=False)
+        assert (r1["dsample_feats"][..., 0].sum(1) <= rd.detach().sum(1) + 1e-3).all()
+
+
+# =====================================================================================================================
 # S2 vector quantiser
 # =====================================================================================================================
 def _make_vq(scp, spec, training):
@@ -633,7 +720,7 @@ def test_install_patches_reference_namespaces(scp):
                  f"{pkg}.module.speech_encoder_plus", f"{pkg}.module.speechclip_c_modules",
                  f"{pkg}.module.speechclip_c_modules.my_vector_quantizer",
                  f"{pkg}.module.speechclip_c_modules.vector_quantizers", f"{pkg}.module.speechclip_c_modules.kw_bn",
-                 f"{pkg}.module.clip_official", f"{pkg}.util", f"{pkg}.util.data_utils",
+                 f"{pkg}.module.clip_official", f"{pkg}.module.cif", f"{pkg}.util", f"{pkg}.util.data_utils",
                  f"{pkg}.model", f"{pkg}.model.kw_branches"]:
         mods[name] = types.ModuleType(name)
         sys.modules[name] = mods[name]
@@ -648,6 +735,7 @@ def test_install_patches_reference_namespaces(scp):
         assert all(done.values())
         assert mods[f"{pkg}.module.losses"].MaskedContrastiveLoss is scp.MaskedContrastiveLoss
         assert mods[f"{pkg}.model.kw_branches"].Kw_BatchNorm is scp.Kw_BatchNorm
+        assert mods[f"{pkg}.model.kw_branches"].CIF is scp.CIF and mods[f"{pkg}.module.cif"].CIF is scp.CIF
         from speechclip_plus_b200.module import clip_glue
         assert mods[f"{pkg}.module.clip_official"].ClipModel.encode_keywords is clip_glue.encode_keywords
         assert mods[f"{pkg}.model.kw_branches"].get_keypadding_mask is clip_glue.get_keypadding_mask
