@@ -61,6 +61,15 @@ static EncodeTiledFn get_encode_tiled() {
 int make_tmap_f16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return fail(SCP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  // cuTensorMapEncodeTiled is a DRIVER call and needs a context bound to the calling thread.  A thread that has only
+  // issued cudaSetDevice / cudaGetDevice so far (e.g. PyTorch's autograd worker when one of our backward functions is
+  // the first node it runs) has none yet: the call then fails with CUDA_ERROR_INVALID_CONTEXT (201).  cudaFree(0) binds
+  // the device's primary context to this thread; done once per thread.
+  static thread_local bool context_bound = false;
+  if (!context_bound) {
+    if (cudaFree(nullptr) != cudaSuccess) return fail(SCP_ERR_CUDA, "could not initialise the CUDA context on this thread");
+    context_bound = true;
+  }
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16 != 0 || box_rows < 1 || box_rows > 256)
     return fail(SCP_ERR_INVALID, "tensor map: base/pitch must be 16-byte aligned, box rows in [1,256]");
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};

@@ -18,6 +18,10 @@ from oracle import speechclip_oracle as oracle
 
 pytestmark = pytest.mark.gpu
 
+import os  # noqa: E402
+
+ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 TOL = 1e-3
 
 
@@ -663,6 +667,23 @@ def test_nce_local_rows_match_full(scp):
         gt_sum = gt_sum + gtr.cpu()
     assert rel_err(ga_sum, gaf) < 1e-5
     assert rel_err(gt_sum, gtf) < 1e-4  # the scale gradient is the sum of the ranks' partial sums
+
+
+def test_nce_backward_as_first_node_of_a_fresh_autograd_thread(scp):
+    """Regression: the backward builds TMA descriptors with a driver call; when it is the FIRST thing PyTorch's autograd
+    worker thread ever runs, that thread has no CUDA context bound yet (CUDA_ERROR_INVALID_CONTEXT before the fix)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, torch; sys.path.insert(0, %r); import speechclip_plus_b200 as scp\n"
+        "crit = scp.MaskedContrastiveLoss(temperature=0.07, temperature_trainable=True).cuda()\n"
+        "a = torch.nn.functional.normalize(torch.randn(64, 128, device='cuda'), dim=-1).requires_grad_(True)\n"
+        "b = torch.nn.functional.normalize(torch.randn(64, 128, device='cuda'), dim=-1).requires_grad_(True)\n"
+        "loss = crit(a, b, torch.arange(64, device='cuda'))\n"
+        "g = torch.autograd.grad(loss, [a, b, crit.temperature])\n"
+        "torch.cuda.synchronize(); print('ok', float(g[0].abs().sum()) > 0)\n" % ROOT_DIR)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok True" in r.stdout, r.stderr[-800:]
 
 
 def test_nce_large_logits_do_not_overflow(scp):
