@@ -406,7 +406,7 @@ __device__ __forceinline__ Best rescore_chunk(const float* __restrict__ table, c
 // 3.5 waves, 70 us.  One warp per row needs no block barriers or shared memory and keeps all M rows of the benchmark
 // shape resident in a single wave.
 template <int NV>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, NV <= 4 ? 4 : 2)  // <= 128 registers for D <= 512: all 2048 rows in one wave
 vq_select_kernel(const float* __restrict__ kw, const float* __restrict__ table, const float* __restrict__ table_norm,
                  const __half* __restrict__ table_hat, const __half* __restrict__ kw_hat, int64_t M, int V, int D,
                  const float* __restrict__ chunk_max, const float* __restrict__ group_max, int n_chunks,
