@@ -62,50 +62,44 @@ __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* dst, const 
   *reinterpret_cast<uint2*>(dst) = u;
 }
 
-// plain forward: thread <-> one 16 B input vector per iteration of a grid-stride loop; ALL L loads of the vector are in
-// flight before the first FMA (LCAP = 16: 64 registers of loads).  The grid is a fixed number of resident blocks so that
-// the softmax of the L weights (a warp reduction + a block barrier) is paid once per block and not once per 256
-// vectors -- with one-shot blocks that prologue sat in front of every load.
-template <typename TIn, typename TOut, int LCAP>
-__global__ void __launch_bounds__(kWsumThreads, 3)
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(kWsumThreads)
 wsum_fwd_plain4_kernel(LayerPtrs lp, int L, int64_t n_vec, int vec_per_row, int64_t T, int64_t stride_b,
                        int64_t stride_t, const float* __restrict__ weights, const float* __restrict__ utt_scale,
                        int64_t B, TOut* __restrict__ y) {
+  // plain forward: thread <-> one 16 B input vector of one row, all L loads issued before the first FMA;
+  // output written in groups of 4 elements (any in/out dtype pair)
   constexpr int NE = Vec16<TIn>::NE;
   __shared__ float sw[SCP_MAX_LAYERS];
   softmax_weights_to_smem(weights, L, sw);
-  for (int64_t i = (int64_t)blockIdx.x * kWsumThreads + threadIdx.x; i < n_vec;
-       i += (int64_t)gridDim.x * kWsumThreads) {
-    const int64_t r = i / vec_per_row;
-    const int v = (int)(i - r * vec_per_row);
-    const int64_t b = r / T, t = r - b * T;
-    const int64_t off = b * stride_b + t * stride_t + (int64_t)v * NE;
-    float acc[NE];
+  const int64_t i = (int64_t)blockIdx.x * kWsumThreads + threadIdx.x;
+  if (i >= n_vec) return;
+  const int64_t r = i / vec_per_row;
+  const int v = (int)(i - r * vec_per_row);
+  const int64_t b = r / T, t = r - b * T;
+  const int64_t off = b * stride_b + t * stride_t + (int64_t)v * NE;
+  float acc[NE];
 #pragma unroll
-    for (int e = 0; e < NE; ++e) acc[e] = 0.f;
+  for (int e = 0; e < NE; ++e) acc[e] = 0.f;
+  for (int l0 = 0; l0 < L; l0 += 8) {
+    uint4 raw[8];
 #pragma unroll
-    for (int l0 = 0; l0 < LCAP; l0 += 16) {  // batches of 16 layers (HuBERT-large: 25 layers = two batches)
-      if (l0 < L) {
-        uint4 raw[16];
+    for (int j = 0; j < 8; ++j)
+      if (l0 + j < L) raw[j] = ld_stream16(reinterpret_cast<const TIn*>(lp.p[l0 + j]) + off);
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (l0 + j < L) raw[j] = ld_stream16(reinterpret_cast<const TIn*>(lp.p[l0 + j]) + off);
+    for (int j = 0; j < 8; ++j)
+      if (l0 + j < L) {
+        float f[NE];
+        Vec16<TIn>::unpack(raw[j], f);
+        float w = sw[l0 + j];
+        if (utt_scale) w *= __ldg(utt_scale + (int64_t)(l0 + j) * B + b);  // method2: 1 / mean_t ||x_{l,b,t}||
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (l0 + j < L) {
-            float f[NE];
-            Vec16<TIn>::unpack(raw[j], f);
-            float w = sw[l0 + j];
-            if (utt_scale) w *= __ldg(utt_scale + (int64_t)(l0 + j) * B + b);  // method2: 1 / mean_t ||x_{l,b,t}||
-#pragma unroll
-            for (int e = 0; e < NE; ++e) acc[e] = fmaf(w, f[e], acc[e]);
-          }
+        for (int e = 0; e < NE; ++e) acc[e] = fmaf(w, f[e], acc[e]);
       }
-    }
-    TOut* dst = y + r * (int64_t)vec_per_row * NE + (int64_t)v * NE;
-#pragma unroll
-    for (int c = 0; c < NE / 4; ++c) store4<TOut>(dst + 4 * c, acc + 4 * c);
   }
+  TOut* dst = y + r * (int64_t)vec_per_row * NE + (int64_t)v * NE;
+#pragma unroll
+  for (int c = 0; c < NE / 4; ++c) store4<TOut>(dst + 4 * c, acc + 4 * c);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -444,16 +438,10 @@ static int launch_fwd(const LayerPtrs& lp, int L, int64_t B, int64_t T, int64_t 
   const int64_t n_rows = B * T;
   if (norm_mode == SCP_NORM_NONE || norm_mode == SCP_NORM_UTT_MEAN) {
     const int64_t n_vec = n_rows * vec_per_row;
-    const float* us = norm_mode == SCP_NORM_UTT_MEAN ? utt_scale : nullptr;
-    if (L <= 16) {
-      const int64_t blocks = std::min<int64_t>(ceil_div(n_vec, kWsumThreads), (int64_t)kNumSMs * 3 * 4);
-      wsum_fwd_plain4_kernel<TIn, TOut, 16><<<(unsigned)blocks, kWsumThreads, 0, stream>>>(
-          lp, L, n_vec, vec_per_row, T, sb, st, weights, us, B, reinterpret_cast<TOut*>(y));
-    } else {
-      const int64_t blocks = std::min<int64_t>(ceil_div(n_vec, kWsumThreads), (int64_t)kNumSMs * 3 * 4);
-      wsum_fwd_plain4_kernel<TIn, TOut, 32><<<(unsigned)blocks, kWsumThreads, 0, stream>>>(
-          lp, L, n_vec, vec_per_row, T, sb, st, weights, us, B, reinterpret_cast<TOut*>(y));
-    }
+    const int64_t blocks = ceil_div(n_vec, kWsumThreads);
+    wsum_fwd_plain4_kernel<TIn, TOut><<<(unsigned)blocks, kWsumThreads, 0, stream>>>(
+        lp, L, n_vec, vec_per_row, T, sb, st, weights, norm_mode == SCP_NORM_UTT_MEAN ? utt_scale : nullptr, B,
+        reinterpret_cast<TOut*>(y));
     SCP_CUDA_LAUNCH_CHECK("wsum_fwd_plain");
     return SCP_OK;
   }
