@@ -237,8 +237,9 @@ int scp_nce_fwd(const float* A, const float* Bm, const int64_t* ids, int64_t N, 
                 void* workspace, size_t workspace_bytes, scp_stream_t stream);
 
 /* dA, dB: (row_end-row_begin, D) f32 gradients of g_loss*loss w.r.t. A[row_begin:row_end], Bm[row_begin:row_end]
- * (dB nullable).  d_log_scale (nullable, (1,)): gradient w.r.t. the log-scale parameter, full sum over the N x N
- * matrix (identical on every rank). */
+ * (dB nullable).  d_log_scale (nullable, (1,)): this shard's PART of the gradient w.r.t. the log-scale parameter -- the
+ * sum of G (.) S over rows [row_begin,row_end) and all columns; the parts of all shards add up to the full gradient
+ * (which is what DDP's gradient all-reduce produces; see ddp_grad_scale). */
 int scp_nce_bwd(const float* A, const float* Bm, const int64_t* ids, int64_t N, int64_t D,
                 const float* log_scale, float fixed_scale, float margin, int dcl, int a2b, int b2a,
                 const float* lse_row, const float* lse_col, const float* g_loss,

@@ -558,9 +558,12 @@ def test_vq_edge_cases(scp):
         vq.quantize_keywords(kw.cuda(), table.cuda(), prob_msk=(0, 9999))
 
 
-def test_vq_full_size_properties(scp):
-    """BASELINE config 3 at one GPU: M = 256 x 8 = 2048 keyword rows against the full 49408 x 512 CLIP table."""
-    B, K, V, D = 256, 8, 49408, 512
+@pytest.mark.parametrize("cfg", [(256, 8, 49408, 512), (128, 8, 49408, 768), (128, 12, 49408, 512)],
+                         ids=["c3_base_M2048_D512", "c5_large_M1024_D768", "c4_dynamicK_M1536_D512"])
+def test_vq_full_size_properties(scp, cfg):
+    """BASELINE configs 3 / 5 / 4 per GPU: M = B*K keyword rows against the full 49408-row CLIP table (D = 512: resident-X
+    kernels; D = 768: the streaming kernels)."""
+    B, K, V, D = cfg
     gen = torch.Generator(device="cuda").manual_seed(11)
     table = torch.randn(V, D, device="cuda", generator=gen) * 0.02
     kw = torch.randn(B, K, D, device="cuda", generator=gen) * 0.02
@@ -730,6 +733,42 @@ def test_gather_and_compute_loss_golden(scp):
                              1.0 / float(g["temperature"]), float(g["cascaded_weight"]), float(g["parallel_weight"]))
     rca, rpa = torch.autograd.grad(ref["loss"], [car, par])
     assert norm_err(gca, rca) < TOL and norm_err(gpa, rpa) < TOL
+
+
+@pytest.mark.parametrize("cfg", [(1024, 512, 128, 3, 1.0, 1.0), (512, 768, 64, 5, 1.5, 0.5)],
+                         ids=["c4_hybrid_base_N1024", "c5_hybrid_large_N512"])
+def test_hybrid_loss_global_batch_local_rows(scp, cfg):
+    """BASELINE configs 4 / 5 as ONE rank of eight sees them: the hybrid loss over the gathered global batch (duplicate
+    image ids as in Flickr8k), gradients for this rank's rows only, against the fp64 oracle."""
+    N, D, n_local, rank, w_c, w_p = cfg
+    gen = torch.Generator().manual_seed(N + D)
+    img = torch.nn.functional.normalize(torch.randn(N, D, generator=gen), dim=-1)
+    ca = torch.nn.functional.normalize(torch.randn(N, D, generator=gen) + 0.5 * img, dim=-1)
+    pa = torch.nn.functional.normalize(torch.randn(N, D, generator=gen) + 0.8 * img, dim=-1)
+    ids = torch.randint(0, N // 3, (N,), generator=gen)
+    rows = (rank * n_local, (rank + 1) * n_local)
+    crit = scp.MaskedContrastiveLoss(temperature=0.07, temperature_trainable=True).cuda()
+    cad, pad = ca.cuda().requires_grad_(True), pa.cuda().requires_grad_(True)
+    out = scp.compute_loss({"id": ids.cuda(), "image_feat": img.cuda(), "cascaded_audio_feat": cad,
+                            "parallel_audio_feat": pad}, crit, w_c, w_p, local_rows=rows)
+    gca, gpa, gt = torch.autograd.grad(out["loss"], [cad, pad, crit.temperature])
+    car, par = ca.double().requires_grad_(True), pa.double().requires_grad_(True)
+    log_scale = torch.tensor(float(crit.temperature.item()), dtype=torch.float64, requires_grad=True)
+    ref = oracle.hybrid_loss({"id": ids, "image_feat": img.double(), "cascaded_audio_feat": car,
+                              "parallel_audio_feat": par}, log_scale.exp(), w_c, w_p)
+    rca, rpa, rt = torch.autograd.grad(ref["loss"], [car, par, log_scale])
+    for key in ("loss", "c_cl_loss", "p_cl_loss"):
+        assert rel_err(out[key], ref[key]) < TOL, key
+    lo, hi = rows
+    assert norm_err(gca[lo:hi], rca[lo:hi]) < TOL and norm_err(gpa[lo:hi], rpa[lo:hi]) < TOL
+    assert float(gca[:lo].abs().max()) == 0.0 and float(gca[hi:].abs().max()) == 0.0   # other ranks' rows: no gradient here
+    # the log-scale gradient is produced in shards as well: the parts of all ranks add up to the reference's gradient
+    gt_sum = torch.zeros((), device="cuda")
+    for r in range(N // n_local):
+        o = scp.compute_loss({"id": ids.cuda(), "image_feat": img.cuda(), "cascaded_audio_feat": cad,
+                              "parallel_audio_feat": pad}, crit, w_c, w_p, local_rows=(r * n_local, (r + 1) * n_local))
+        gt_sum = gt_sum + torch.autograd.grad(o["loss"], [crit.temperature])[0]
+    assert rel_err(gt_sum, rt) < TOL
 
 
 def test_install_patches_reference_namespaces(scp):
