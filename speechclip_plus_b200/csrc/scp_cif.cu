@@ -7,7 +7,7 @@
 //   cif_plan      warp <-> utterance: SEQUENTIAL fp32 cumsum of alpha (the firing positions are floor(csum/threshold): the
 //                 summation order decides borderline fires, so it is fixed), fired length per utterance
 //   [host reads max(feat_len) once -- the output shape depends on it, exactly as in the reference]
-//   cif_fire_fwd  block <-> (utterance, 512-channel slab): per-source descriptors in shared memory, then ONE sequential
+//   cif_fire_fwd  block <-> (utterance, 512-channel slab), thread <-> 4 channels: per-source descriptors in shared memory, then ONE sequential
 //                 pass over the sources; every thread keeps the accumulator of the output row being integrated in
 //                 registers and writes each of the T+1 output rows exactly once (no zero-fill, no atomics, deterministic).
 //                 Bytes: B*S*C*4 read + B*(T+1)*C*4 written -- HBM-bound.
@@ -70,20 +70,26 @@ cif_plan_kernel(const float* __restrict__ alpha, int64_t B, int S, float thr, in
   for (int s = lane; s < S; s += 32) csum[b * S + s] = row[s];
 }
 
-// block (128 threads) <-> (utterance b, slab of 512 channels); thread <-> 4 channels
+// block (128 threads) <-> (utterance b, slab of 512 channels); thread <-> 4 channels.
+// The kernel is instruction-issue bound, not latency bound (two channels per thread = twice the warps ran 1.6x SLOWER),
+// so the per-source work is kept minimal: descriptors are stored as (left,right) + two weights, and a source that does
+// not fire -- the common case, ~95 % of the frames -- costs two shared loads, one compare and the four FMAs.
 __global__ void __launch_bounds__(128)
 cif_fire_fwd_kernel(const float* __restrict__ x, const float* __restrict__ alpha, const float* __restrict__ csum,
                     const int64_t* __restrict__ feat_len, int64_t B, int S, int C, float thr, int T,
                     float* __restrict__ out /* (B, T+1, C) */, uint8_t* __restrict__ fire_mask /* (B,S) nullable */,
                     float* __restrict__ tail_w /* (B,) nullable */) {
   extern __shared__ unsigned char s_raw[];
-  CifSrc* src = reinterpret_cast<CifSrc*>(s_raw);
+  int2* s_lr = reinterpret_cast<int2*>(s_raw);                 // (left, right) per source
+  float2* s_w = reinterpret_cast<float2*>(s_lr + S);           // (left_w, right_w) per source
   const int64_t b = blockIdx.x;
   const float* cs = csum + b * S;
   const float* al = alpha + b * S;
   for (int s = threadIdx.x; s < S; s += blockDim.x) {
-    src[s] = cif_source(cs, al, s, thr, T);
-    if (fire_mask && blockIdx.y == 0) fire_mask[b * S + s] = src[s].right > src[s].left ? 1 : 0;
+    const CifSrc d = cif_source(cs, al, s, thr, T);
+    s_lr[s] = make_int2(d.left, d.right);
+    s_w[s] = make_float2(d.left_w, d.right_w);
+    if (fire_mask && blockIdx.y == 0) fire_mask[b * S + s] = d.right > d.left ? 1 : 0;
   }
   __syncthreads();
   if (tail_w && blockIdx.y == 0 && threadIdx.x == 0) {
@@ -91,8 +97,8 @@ cif_fire_fwd_kernel(const float* __restrict__ x, const float* __restrict__ alpha
     const int fl = (int)feat_len[b];
     float tw = 0.f;
     for (int s = 0; s < S; ++s) {
-      if (src[s].right == fl) tw += src[s].right_w;
-      if (src[s].left == fl) tw += src[s].left_w;
+      if (s_lr[s].y == fl) tw += s_w[s].y;
+      if (s_lr[s].x == fl) tw += s_w[s].x;
     }
     tail_w[b] = tw;
   }
@@ -103,7 +109,6 @@ cif_fire_fwd_kernel(const float* __restrict__ x, const float* __restrict__ alpha
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   int t_cur = 0;
   auto move_to = [&](int t) {  // targets are visited in non-decreasing order
-    if (t == t_cur) return;
     *reinterpret_cast<float4*>(ob + (int64_t)t_cur * C) = acc;
     acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int z = t_cur + 1; z < t; ++z) *reinterpret_cast<float4*>(ob + (int64_t)z * C) = acc;
@@ -112,20 +117,31 @@ cif_fire_fwd_kernel(const float* __restrict__ x, const float* __restrict__ alpha
   auto add = [&](float w, const float4& v) {
     acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
   };
-  float4 nxt = *reinterpret_cast<const float4*>(xb), v;
-  for (int s = 0; s < S; ++s) {
-    v = nxt;
-    if (s + 1 < S) nxt = *reinterpret_cast<const float4*>(xb + (int64_t)(s + 1) * C);  // prefetch the next source row
-    const CifSrc d = src[s];
-    move_to(d.left);
-    add(d.left_w, v);
-    for (int e = 1; e <= d.extra; ++e) {
-      move_to(min(d.left + e, T));
-      add(thr, v);
-    }
-    if (d.right > d.left) {
-      move_to(d.right);
-      add(d.right_w, v);
+  constexpr int kAhead = 8;  // source rows in flight per thread: the integration is sequential, the loads are not
+  float4 buf[kAhead];
+#pragma unroll
+  for (int i = 0; i < kAhead; ++i)
+    buf[i] = i < S ? *reinterpret_cast<const float4*>(xb + (int64_t)i * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s0 = 0; s0 < S; s0 += kAhead) {
+#pragma unroll
+    for (int i = 0; i < kAhead; ++i) {
+      const int s = s0 + i;
+      if (s < S) {
+        const float4 v = buf[i];
+        if (s + kAhead < S) buf[i] = *reinterpret_cast<const float4*>(xb + (int64_t)(s + kAhead) * C);
+        const int2 lr = s_lr[s];
+        const float2 w = s_w[s];
+        if (lr.x != t_cur) move_to(lr.x);
+        add(w.x, v);
+        if (lr.y != lr.x) {  // the source fires: thr on every row strictly between, the remainder on the last
+          for (int t = lr.x + 1; t < lr.y; ++t) {  // extra = right - left - 1 rows (clipped indices never exceed T)
+            move_to(t);
+            add(thr, v);
+          }
+          move_to(lr.y);
+          add(w.y, v);
+        }
+      }
     }
   }
   move_to(T + 1);  // flushes the last row and zero-fills up to the tail row
@@ -279,7 +295,7 @@ extern "C" int scp_cif_fire_fwd(const float* x, const float* alpha, const float*
   SCP_CHECK_ARG(x && alpha && csum && feat_len && out && T >= 1, "cif_fire_fwd: bad argument");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const dim3 grid((unsigned)B, (unsigned)ceil_div(C, 512));
-  cif_fire_fwd_kernel<<<grid, 128, (size_t)S * sizeof(CifSrc), s>>>(x, alpha, csum, feat_len, B, (int)S, (int)C, threshold,
+  cif_fire_fwd_kernel<<<grid, 128, (size_t)S * (sizeof(int2) + sizeof(float2)), s>>>(x, alpha, csum, feat_len, B, (int)S, (int)C, threshold,
                                                                   (int)T, out, fire_mask, tail_w);
   SCP_CUDA_LAUNCH_CHECK("cif_fire_fwd");
   return SCP_OK;

@@ -3,6 +3,7 @@
 #   1. plain bench run (exit 0 required)             -> gpurun_out/<tag>_bench.json
 #   2. ncu launch list of the SAME short command     -> gpurun_out/<tag>_launches.csv
 #   3. ncu --set full of one instance of every hot kernel -> gpurun_out/<tag>_full.ncu-rep (+ raw csv)
+#   4. device times of the kernels outside the bench step -> gpurun_out/<tag>_aux_kernels.json
 # usage: tools/profile_round.sh <tag>
 set -u
 cd "$(dirname "$0")/.."
@@ -18,5 +19,7 @@ ncu --set full --import-source on --clock-control none \
     -k regex:'wsum_fwd|wsum_bwd_plain|stream_gemm|vq_select' -s 40 -c 10 -f -o gpurun_out/${tag}_full \
     $SHORT > gpurun_out/${tag}_ncu_full.log 2>&1
 ncu -i gpurun_out/${tag}_full.ncu-rep --page raw --csv > gpurun_out/${tag}_full_raw.csv 2>/dev/null
+# kernels outside the bench step (S1' variants, N1 / N3 / N4): device times and achieved bandwidth
+python tools/aux_kernel_times.py > gpurun_out/${tag}_aux_kernels.json 2> gpurun_out/${tag}_aux_kernels.err
 tail -2 gpurun_out/${tag}_ncu_full.log
 cat gpurun_out/${tag}_bench.json
