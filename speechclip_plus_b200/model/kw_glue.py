@@ -160,7 +160,11 @@ def compute_loss(loss_feats: Dict[str, torch.Tensor], criterion, cascaded_object
             kwargs = {} if local_rows is None else {"local_rows": local_rows}
             losses[f"{branch[0]}_cl_loss"] = criterion(feat_A=loss_feats[key].float(), feat_B=image_feat, index=ids,
                                                       **kwargs)
-            losses["loss"] = losses["loss"] + weight * losses[f"{branch[0]}_cl_loss"]
+            # `loss += weight * term` of the reference, without the no-op kernels for `0 + x` and `1.0 * x`
+            term = losses[f"{branch[0]}_cl_loss"]
+            if weight != 1.0:
+                term = weight * term
+            losses["loss"] = term if isinstance(losses["loss"], int) else losses["loss"] + term
     if ("cif_quantity_out" in loss_feats and "cif_target_len" in loss_feats and quantity_loss_criteria is not None):
         losses["quantity_loss"] = quantity_loss_criteria(loss_feats["cif_quantity_out"], loss_feats["cif_target_len"])
         losses["loss"] = losses["loss"] + quantity_loss_weight * losses["quantity_loss"]
