@@ -15,7 +15,9 @@
  *   - all data pointers are DEVICE pointers valid on the stream's device unless marked "host".
  *   - sizes are int64_t element counts; strides are in elements; the last dimension is contiguous.
  *   - kernels are launched on `stream` (a cudaStream_t / CUstream); re-entrant, no global mutable state
- *     except the lazily resolved driver entry point for tensor-map encoding.
+ *     except the lazily resolved driver entry point for tensor-map encoding and one lazily created helper stream
+ *     (+ two events) per device: scp_vq_fwd forks its arg-max kernel onto it and joins it back before returning, so
+ *     every result is ordered on `stream` as usual (event record / wait only: valid under CUDA-graph capture).
  *   - there is no CPU fallback: on a device that is not sm_100 the functions return SCP_ERR_ARCH.
  */
 #ifndef SCP_B200_H_

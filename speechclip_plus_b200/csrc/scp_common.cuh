@@ -16,6 +16,13 @@ int fail(int code, const char* fmt, ...);
 void count_launch(int n = 1);
 int check_device_arch();  // SCP_OK on a compute-capability-10.x device
 
+// Per-device helper stream + fork/join events (created lazily, never destroyed): lets one entry point run two
+// independent kernels concurrently.  fork_to_side() makes the helper stream wait for everything enqueued on `main` so
+// far and returns it; join_from_side() makes `main` wait for everything enqueued on the helper stream.  Both are
+// capturable (event record / wait only).  Returns nullptr when the helper objects cannot be created.
+cudaStream_t fork_to_side(cudaStream_t main);
+int join_from_side(cudaStream_t main);
+
 #define SCP_CHECK_ARG(cond, ...)                                  \
   do {                                                            \
     if (!(cond)) return ::scp::fail(SCP_ERR_INVALID, __VA_ARGS__); \

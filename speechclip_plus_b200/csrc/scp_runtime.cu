@@ -1,5 +1,6 @@
 // Library bookkeeping: error strings, launch counter, device-architecture gate.
 #include <atomic>
+#include <mutex>
 #include <cstdarg>
 #include <cstring>
 
@@ -39,6 +40,52 @@ int check_device_arch() {
   cached_dev = dev;
   cached_rc = major == 10 ? SCP_OK : fail(SCP_ERR_ARCH, "device %d has compute capability %d.x; sm_100a required", dev, major);
   return cached_rc;
+}
+
+// ---- helper stream (fork / join inside one entry point) ----------------------------------------------------------
+namespace {
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool ok = false, tried = false;
+};
+constexpr int kMaxDevices = 64;
+SideStream g_side[kMaxDevices];
+std::mutex g_side_mutex;
+
+SideStream* side_for_current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+  SideStream& s = g_side[dev];
+  if (!s.tried) {
+    s.tried = true;
+    s.ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess;
+    if (!s.ok) cudaGetLastError();
+  }
+  return s.ok ? &s : nullptr;
+}
+}  // namespace
+
+cudaStream_t fork_to_side(cudaStream_t main) {
+  std::lock_guard<std::mutex> lock(g_side_mutex);
+  SideStream* s = side_for_current_device();
+  if (!s) return nullptr;
+  if (cudaEventRecord(s->fork, main) != cudaSuccess || cudaStreamWaitEvent(s->stream, s->fork, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return s->stream;
+}
+
+int join_from_side(cudaStream_t main) {
+  std::lock_guard<std::mutex> lock(g_side_mutex);
+  SideStream* s = side_for_current_device();
+  if (!s) return fail(SCP_ERR_CUDA, "helper stream missing at join");
+  if (cudaEventRecord(s->join, s->stream) != cudaSuccess || cudaStreamWaitEvent(main, s->join, 0) != cudaSuccess)
+    return fail(SCP_ERR_CUDA, "helper stream join failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return SCP_OK;
 }
 
 // ---- TMA tensor maps ------------------------------------------------------------------------------------------

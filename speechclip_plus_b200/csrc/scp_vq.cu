@@ -413,12 +413,12 @@ vq_select_kernel(const float* __restrict__ kw, const float* __restrict__ table, 
                  const float* __restrict__ partials, int n_groups,
                  const float* __restrict__ tau_ptr, MaskedCols mc, int64_t* __restrict__ idx_out,
                  float* __restrict__ keywords, float* __restrict__ row_stats, float* __restrict__ code_hist,
-                 float* __restrict__ lse1_l2) {
+                 float* __restrict__ lse1_l2, int phases /* bit 0: row statistics, bit 1: arg-max + gather */) {
   const int lane = threadIdx.x & 31;
   const int64_t m = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (m >= M) return;  // whole warp
   // ---- statistics of the row: combine the per-group partials of sweep 1 (lane <-> group, fixed tree order)
-  {
+  if (phases & 1) {
     const float tau = *tau_ptr;
     float z1 = 0.f, c1 = 0.f, gmax = kNegBig;
     for (int g = lane; g < n_groups; g += 32) {
@@ -444,6 +444,7 @@ vq_select_kernel(const float* __restrict__ kw, const float* __restrict__ table, 
       lse1_l2[m] = -lse1 * kLog2e;  // sweep 2 adds it with one packed FMA
     }
   }
+  if (!(phases & 2)) return;
   // ---- this lane's slice of the keyword row (fp32) and of its unit fp16 copy (the tensor-core operand of sweep 1)
   float kreg[NV][4];
   const int nvec = D >> 2;
@@ -1192,20 +1193,43 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
   const size_t sel_smem = (size_t)4 * ws.n_chunks * sizeof(float);  // one row of chunk maxima per warp
   if (sel_smem > 48 * 1024)
     return fail(SCP_ERR_UNSUPPORTED, "vq_fwd: V=%lld exceeds the arg-max kernel's shared-memory scan (V <= 98304)", (long long)V);
-#define SCP_SELECT(NVV)                                                                                              \
-  vq_select_kernel<NVV><<<(unsigned)ceil_div(M, 4), 128, sel_smem, s>>>(kw, table, table_norm, reinterpret_cast<const __half*>(table_hat),   \
-                                                    reinterpret_cast<const __half*>(kw_hat), M, (int)V, (int)D,           \
-                                                    ws.chunk_max, ws.group_max, ws.n_chunks,                              \
-                                                    ws.partials, 2 * ws.n_groups, tau, mc, idx, keywords, row_stats, \
-                                                    code_hist, ws.lse1_l2)
-  if (D <= 128) SCP_SELECT(1);
-  else if (D <= 256) SCP_SELECT(2);
-  else if (D <= 512) SCP_SELECT(4);
-  else if (D <= 768) SCP_SELECT(6);
-  else if (D <= 1024) SCP_SELECT(8);
-  else return fail(SCP_ERR_UNSUPPORTED, "vq_fwd: D > 1024 is not supported by the exact arg-max kernel (got %lld)", (long long)D);
+  // The arg-max phase (latency-bound, light on every unit) and sweep 2 (tensor-bound) are independent once the row
+  // statistics exist: the statistics run on the caller's stream, the arg-max is forked onto the library's helper stream
+  // and joined before the metrics -- it then hides under sweep 2 instead of preceding it.  SCP_VQ_OVERLAP=0 disables.
+  static const bool overlap_on = [] { const char* e = getenv("SCP_VQ_OVERLAP"); return !(e && e[0] == '0'); }();
+#define SCP_SELECT_LAUNCH(NVV, STREAM, PHASES)                                                                         \
+  vq_select_kernel<NVV><<<(unsigned)ceil_div(M, 4), 128, sel_smem, STREAM>>>(                                          \
+      kw, table, table_norm, reinterpret_cast<const __half*>(table_hat), reinterpret_cast<const __half*>(kw_hat), M,   \
+      (int)V, (int)D, ws.chunk_max, ws.group_max, ws.n_chunks, ws.partials, 2 * ws.n_groups, tau, mc, idx, keywords,   \
+      row_stats, code_hist, ws.lse1_l2, PHASES)
+#define SCP_SELECT(STREAM, PHASES)                                                                                     \
+  do {                                                                                                                 \
+    if (D <= 128) SCP_SELECT_LAUNCH(1, STREAM, PHASES);                                                                \
+    else if (D <= 256) SCP_SELECT_LAUNCH(2, STREAM, PHASES);                                                           \
+    else if (D <= 512) SCP_SELECT_LAUNCH(4, STREAM, PHASES);                                                           \
+    else if (D <= 768) SCP_SELECT_LAUNCH(6, STREAM, PHASES);                                                           \
+    else SCP_SELECT_LAUNCH(8, STREAM, PHASES);                                                                         \
+  } while (0)
+  if (D > 1024) return fail(SCP_ERR_UNSUPPORTED, "vq_fwd: D > 1024 is not supported by the exact arg-max kernel (got %lld)", (long long)D);
+  bool forked = false;
+  if (avg_probs && overlap_on) {
+    SCP_SELECT(s, 1);  // row statistics: sweep 2 needs the normalisers
+    SCP_CUDA_LAUNCH_CHECK("vq_select(stats)");
+    cudaStream_t side = fork_to_side(s);
+    if (side) {
+      SCP_SELECT(side, 2);  // arg-max + gather + histogram, concurrently with sweep 2
+      SCP_CUDA_LAUNCH_CHECK("vq_select(argmax)");
+      forked = true;
+    } else {
+      SCP_SELECT(s, 2);
+      SCP_CUDA_LAUNCH_CHECK("vq_select(argmax)");
+    }
+  } else {
+    SCP_SELECT(s, 3);
+    SCP_CUDA_LAUNCH_CHECK("vq_select");
+  }
 #undef SCP_SELECT
-  SCP_CUDA_LAUNCH_CHECK("vq_select");
+#undef SCP_SELECT_LAUNCH
   // ---- sweep 2 (column sums) -- skipped when the caller does not want prob_perplexity
   if (avg_probs) {
     const int64_t Mp2 = round_up(M, 256);
@@ -1231,8 +1255,12 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
                       tc::resident_smem_bytes<256, 1, 5, Sweep2Epi, tc::MC_PAIR>(sc.k_chunks) <= tc::kMaxDynSmem;
     if (xres) rc = tc::launch_stream_gemm<256, 1, 5, Sweep2Epi, 2, tc::MC_PAIR, true>(maps, sc, ep, s, "vq_sweep2");
     else rc = tc::launch_stream_gemm<256, 1, 6, Sweep2Epi, 2, tc::MC_PAIR>(maps, sc, ep, s, "vq_sweep2");
-    if (rc) return rc;
+    if (rc) {
+      if (forked) join_from_side(s);  // never leave the helper stream un-joined (stream capture would be invalidated)
+      return rc;
+    }
   }
+  if (forked && (rc = join_from_side(s))) return rc;  // the metrics need the code histogram of the arg-max phase
   vq_metrics_kernel<<<kMetricBlocks, 256, 0, s>>>(code_hist, avg_probs, row_stats, M, (int)K, (int)V, ws.metric_part,
                                                   reinterpret_cast<unsigned int*>(ws.metric_part + kMetricBlocks * 2),
                                                   metrics);
