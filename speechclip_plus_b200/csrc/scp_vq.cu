@@ -689,10 +689,11 @@ struct Sweep3Epi {
     int want_tau;             // accumulate the two c-weighted sums (only the learnable-temperature gradient needs them)
     MaskedCols mc;
   };
-  // Each warp owns a private 4 KB staging area (32 rows x 32 columns of Q~ and of P~): the accumulator layout gives
-  // every lane one ROW, but a store instruction in which 32 lanes touch 32 different rows costs 32 LSU transactions;
-  // transposing through shared memory turns it into 64-byte row segments (8 rows per instruction, full sectors).
-  static constexpr int kWarpStage = 2 * 32 * 64;
+  // Each warp owns a private 2 KB staging area (32 rows x 32 columns, used for Q~ and then for P~): the accumulator
+  // layout gives every lane one ROW, but a store instruction in which 32 lanes touch 32 different rows costs 32 LSU
+  // transactions; transposing through shared memory turns it into 64-byte row segments (8 rows per instruction, full
+  // sectors).  One tile-sized buffer instead of two frees 16 KB for a fifth ring stage (the sweep is feed-bound).
+  static constexpr int kWarpStage = 32 * 64;
   static constexpr int kWarpVec = 64 * 4;  // table norms of the 64 columns a warp consumes per tile
   static constexpr int kSmemBytes = tc::kEpiWarps * (kWarpStage + kWarpVec);
   const Params& p;
@@ -744,13 +745,12 @@ struct Sweep3Epi {
     const uint32_t n_src = wsm + (uint32_t)(col0 & 63) * 4;  // ||e_v|| of the 32 columns (broadcast reads)
     // staging layout: row r at r*64 B, its four 16-byte units XOR-swizzled with (r >> 1) & 3 (conflict-free both ways)
     const uint32_t qs = stage + lane * 64;
-    const uint32_t ps = stage + 32 * 64 + lane * 64;
     const int sw = (lane >> 1) & 3;
     const tc::f32x2 kt2 = tc::pack2(k_tau, k_tau), b2 = tc::pack2(bias, bias), ns0 = tc::pack2(-s0, -s0);
-    __syncwarp();  // the previous chunk's read-out of the staging area is complete
+    uint4 pk_q[4], pk_p[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      uint32_t pk_q[4], pk_p[4];
+      uint32_t wq[4], wp[4];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const float4 rv = tc::lds128f(n_src + (2 * i + h) * 16);
@@ -771,26 +771,30 @@ struct Sweep3Epi {
           float a, b;
           __half2 hh;
           tc::unpack2(qj, a, b);
-          hh = __floats2half2_rn(a, b); pk_q[2 * h + j] = *reinterpret_cast<uint32_t*>(&hh);
+          hh = __floats2half2_rn(a, b); wq[2 * h + j] = *reinterpret_cast<uint32_t*>(&hh);
           tc::unpack2(pj, a, b);
-          hh = __floats2half2_rn(a, b); pk_p[2 * h + j] = *reinterpret_cast<uint32_t*>(&hh);
+          hh = __floats2half2_rn(a, b); wp[2 * h + j] = *reinterpret_cast<uint32_t*>(&hh);
         }
       }
-      tc::sts128(qs + ((i ^ sw) << 4), make_uint4(pk_q[0], pk_q[1], pk_q[2], pk_q[3]));
-      tc::sts128(ps + ((i ^ sw) << 4), make_uint4(pk_p[0], pk_p[1], pk_p[2], pk_p[3]));
+      pk_q[i] = make_uint4(wq[0], wq[1], wq[2], wq[3]);
+      pk_p[i] = make_uint4(wp[0], wp[1], wp[2], wp[3]);
     }
-    __syncwarp();
-    // read-out: instruction k covers rows 8k..8k+7, four lanes per row -> 64-byte contiguous global segments
+    // transpose + store, Q~ first and then P~ through the same staging tile
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int r = 8 * k + (lane >> 2);
-      const int u = lane & 3;
-      const int off = r * 64 + ((u ^ ((r >> 1) & 3)) << 4);
-      const uint4 q4 = tc::lds128(stage + off);
-      const uint4 p4 = tc::lds128(stage + 32 * 64 + off);
-      const int64_t grow = row0 + r;
-      *reinterpret_cast<uint4*>(p.pq + grow * p.Vp + col0 + u * 8) = q4;
-      *reinterpret_cast<uint4*>(p.pq + (p.Mp + grow) * p.Vp + col0 + u * 8) = p4;
+    for (int which = 0; which < 2; ++which) {
+      __syncwarp();  // the previous read-out of the staging area is complete
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tc::sts128(qs + ((i ^ sw) << 4), which == 0 ? pk_q[i] : pk_p[i]);
+      __syncwarp();
+      // read-out: instruction k covers rows 8k..8k+7, four lanes per row -> 64-byte contiguous global segments
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = 8 * k + (lane >> 2);
+        const int u = lane & 3;
+        const uint4 v4 = tc::lds128(stage + r * 64 + ((u ^ ((r >> 1) & 3)) << 4));
+        const int64_t grow = (which == 0 ? 0 : p.Mp) + row0 + r;
+        *reinterpret_cast<uint4*>(p.pq + grow * p.Vp + col0 + u * 8) = v4;
+      }
     }
   }
   __device__ __forceinline__ void finish() {
@@ -1330,7 +1334,7 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
     ep.D = (int)D;
     ep.want_tau = g_tau != nullptr;
     ep.mc = mc;
-    if (pair) rc = tc::launch_stream_gemm<128, 2, 4, Sweep3Epi, 2, tc::MC_PAIR>(maps, sc, ep, s, "vq_sweep3");
+    if (pair) rc = tc::launch_stream_gemm<128, 2, 5, Sweep3Epi, 2, tc::MC_PAIR>(maps, sc, ep, s, "vq_sweep3");
     else rc = tc::launch_stream_gemm<128, 2, 3, Sweep3Epi>(maps, sc, ep, s, "vq_sweep3");
     if (rc) return rc;
   }
