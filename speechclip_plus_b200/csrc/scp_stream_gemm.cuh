@@ -155,18 +155,20 @@ __device__ __forceinline__ WorkInfo decode_work(const Sched& s) {
 constexpr int kGemmThreads = 64 + kEpiThreads;
 constexpr int kXTileBytes = kTileM * kChunkK * 2;  // 16 KB
 
-template <int BN, int NX, int STAGES, bool PAIR = false, bool XRES = false>
+// NRES = number of X operands (the first NRES of NX) held resident in shared memory instead of riding in the ring
+template <int BN, int NX, int STAGES, bool PAIR = false, int NRES = 0>
 struct GemmCfg {
+  static_assert(NRES >= 0 && NRES <= NX, "NRES");
   static constexpr int kYTileBytes = (PAIR ? BN / 2 : BN) * kChunkK * 2;  // a pair CTA stages half of the Y tile
-  static constexpr int kYOffset = XRES ? 0 : NX * kXTileBytes;            // Y tile inside a ring stage
+  static constexpr int kYOffset = (NX - NRES) * kXTileBytes;              // Y tile inside a ring stage (after the streamed X)
   static constexpr int kStageBytes = kYOffset + kYTileBytes;
   static constexpr int kAccCols = NX * BN;
   static constexpr int kAccStages = (int)kTmemCols / kAccCols >= 2 ? 2 : 1;
   static constexpr int kBarrierBytes = 1024;  // mbarriers + TMEM slot; keeps the epilogue scratch 1024-aligned
   // 1024 B slack for manual alignment of the dynamic smem base
-  // k_res = K chunks held resident per X operand (XRES only)
+  // k_res = K chunks held resident per resident X operand
   static constexpr int smem_bytes(int epi_bytes, int k_res = 0) {
-    return 1024 + (XRES ? NX * k_res * kXTileBytes : 0) + STAGES * kStageBytes + kBarrierBytes + epi_bytes;
+    return 1024 + NRES * k_res * kXTileBytes + STAGES * kStageBytes + kBarrierBytes + epi_bytes;
   }
   static_assert(kAccCols <= (int)kTmemCols, "accumulators exceed TMEM");
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN");
@@ -184,11 +186,12 @@ struct GemmCfg {
 //   void finish();
 // Per-row state lives in the two warps ("halves") that own the row; epilogues combine the halves themselves
 // (separate partial slots, or through ctx.smem + named_bar_sync(kEpiBarrierId, kEpiThreads)).
-template <int BN, int NX, int STAGES, class Epi, int CL, int MC, bool XRES>
+template <int BN, int NX, int STAGES, class Epi, int CL, int MC, int NRES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, const typename Epi::Params ep) {
   constexpr bool kPair = MC == MC_PAIR;
-  using Cfg = GemmCfg<BN, NX, STAGES, kPair, XRES>;
+  constexpr bool XRES = NRES > 0;
+  using Cfg = GemmCfg<BN, NX, STAGES, kPair, NRES>;
   static_assert(!XRES || MC == MC_NONE || MC == MC_PAIR, "resident X is implemented for one-CTA and pair schedules");
   static_assert(CL == 1 || CL == 2 || CL == 4, "cluster size");
   static_assert(!kPair || CL == 2, "a CTA pair is a cluster of two");
@@ -199,7 +202,7 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
   uint8_t* smem_x = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // resident X region (XRES): operand x, chunk j at smem_x + (x * k_res + j) * 16 KB; the ring follows it
   const int k_res = XRES ? (int)(((long long)sched.k_chunks + sched.k_splits - 1) / sched.k_splits) : 0;
-  uint8_t* smem = smem_x + (size_t)NX * k_res * kXTileBytes;
+  uint8_t* smem = smem_x + (size_t)NRES * k_res * kXTileBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
@@ -250,31 +253,29 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
         for (int kc = work.kc0; kc < work.kc1; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * Cfg::kStageBytes;
-          // XRES: the X chunks travel with the first tile's stages and land in the resident region
-          const bool load_x = !XRES || it == 0;
-          const uint32_t stage_tx = (uint32_t)Cfg::kStageBytes + (XRES && it == 0 ? NX * kXTileBytes : 0);
-          uint8_t* xdst = XRES ? smem_x + (size_t)(kc - work.kc0) * kXTileBytes : st;
-          const size_t xstep = XRES ? (size_t)k_res * kXTileBytes : (size_t)kXTileBytes;
+          // resident operands (x < NRES): their chunks travel with the FIRST tile's stages and land in the resident
+          // region; streamed operands (x >= NRES) ride in every stage in front of the Y tile
+          const uint32_t stage_tx = (uint32_t)Cfg::kStageBytes + (it == 0 ? NRES * kXTileBytes : 0);
+          auto xdst = [&](int x) -> uint8_t* {
+            return x < NRES ? smem_x + ((size_t)x * k_res + (size_t)(kc - work.kc0)) * kXTileBytes
+                            : st + (size_t)(x - NRES) * kXTileBytes;
+          };
           if (kPair) {
             // both CTAs' bytes are posted on the leader's barrier, which the leader arms for the two of them
             if (work.rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_tx);
             const uint32_t lead_bar = mapa_u32(&full_bar[stage], 0);
-            if (load_x) {
 #pragma unroll
-              for (int x = 0; x < NX; ++x)
-                tma_load_2d_pair(xdst + x * xstep, &maps.x[x], kc * kChunkK, work.x_row, lead_bar);
-            }
+            for (int x = 0; x < NX; ++x)
+              if (x >= NRES || it == 0) tma_load_2d_pair(xdst(x), &maps.x[x], kc * kChunkK, work.x_row, lead_bar);
             tma_load_2d_pair(st + Cfg::kYOffset, &maps.y, kc * kChunkK, nt * BN + work.rank * (BN / 2), lead_bar);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
           mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
           if (XRES) {
-            if (load_x) {
 #pragma unroll
-              for (int x = 0; x < NX; ++x)
-                tma_load_2d(xdst + x * xstep, &maps.x[x], kc * kChunkK, work.x_row, &full_bar[stage]);
-            }
+            for (int x = 0; x < NX; ++x)
+              if (x >= NRES || it == 0) tma_load_2d(xdst(x), &maps.x[x], kc * kChunkK, work.x_row, &full_bar[stage]);
           } else if (MC == MC_X) {
             constexpr int kRows = kTileM / CL;
 #pragma unroll
@@ -311,11 +312,11 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
           tc_fence_after();
           const uint32_t st = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t b_desc = make_kmajor_sw128_desc(st + Cfg::kYOffset);
-          const uint32_t xbase = XRES ? smem_u32(smem_x) + (uint32_t)(kc - work.kc0) * kXTileBytes : st;
-          const uint32_t xstep = XRES ? (uint32_t)k_res * kXTileBytes : (uint32_t)kXTileBytes;
+          const uint32_t xres0 = smem_u32(smem_x) + (uint32_t)(kc - work.kc0) * kXTileBytes;
 #pragma unroll
           for (int x = 0; x < NX; ++x) {
-            const uint64_t a_desc = make_kmajor_sw128_desc(xbase + x * xstep);
+            const uint64_t a_desc = make_kmajor_sw128_desc(
+                x < NRES ? xres0 + (uint32_t)x * (uint32_t)k_res * kXTileBytes : st + (uint32_t)(x - NRES) * kXTileBytes);
             const uint32_t d = tmem_base + (uint32_t)(as * Cfg::kAccCols + x * BN);
 #pragma unroll
             for (int k = 0; k < kChunkK / kUmmaK; ++k) {
@@ -449,16 +450,18 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
 constexpr int kMaxDynSmem = 227 * 1024;  // sm_100: 232448 B of dynamic shared memory per CTA
 
 // shared memory a resident-X launch needs; callers fall back to the streaming kernel when it exceeds kMaxDynSmem
-template <int BN, int NX, int STAGES, class Epi, int MC>
+template <int BN, int NX, int STAGES, class Epi, int MC, int NRES = NX>
 constexpr int resident_smem_bytes(int k_chunks_per_split) {
-  return GemmCfg<BN, NX, STAGES, MC == MC_PAIR, true>::smem_bytes(Epi::kSmemBytes, k_chunks_per_split);
+  return GemmCfg<BN, NX, STAGES, MC == MC_PAIR, NRES>::smem_bytes(Epi::kSmemBytes, k_chunks_per_split);
 }
 
-template <int BN, int NX, int STAGES, class Epi, int CL = 1, int MC = MC_NONE, bool XRES = false>
+// NRES: number of resident X operands (0 = all streamed; `true` at old call sites means 1)
+template <int BN, int NX, int STAGES, class Epi, int CL = 1, int MC = MC_NONE, int NRES = 0>
 int launch_stream_gemm(const GemmMaps& maps, const Sched& sched, const typename Epi::Params& ep, cudaStream_t stream,
                        const char* name) {
-  using Cfg = GemmCfg<BN, NX, STAGES, MC == MC_PAIR, XRES>;
-  auto kern = stream_gemm_kernel<BN, NX, STAGES, Epi, CL, MC, XRES>;
+  constexpr bool XRES = NRES > 0;
+  using Cfg = GemmCfg<BN, NX, STAGES, MC == MC_PAIR, NRES>;
+  auto kern = stream_gemm_kernel<BN, NX, STAGES, Epi, CL, MC, NRES>;
   const int k_res = XRES ? (sched.k_chunks + sched.k_splits - 1) / sched.k_splits : 0;
   const int smem = Cfg::smem_bytes(Epi::kSmemBytes, k_res);
   if (smem > kMaxDynSmem) return fail(SCP_ERR_UNSUPPORTED, "%s: %d B of shared memory needed (K too large for a resident X tile)", name, smem);

@@ -1334,7 +1334,11 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
     ep.D = (int)D;
     ep.want_tau = g_tau != nullptr;
     ep.mc = mc;
-    if (pair) rc = tc::launch_stream_gemm<128, 2, 5, Sweep3Epi, 2, tc::MC_PAIR>(maps, sc, ep, s, "vq_sweep3");
+    // optional (SCP_VQ_S3_RES=1): keep the keyword operand resident, stream only ghat and the table (24 KB stages, 3 of them)
+    static const bool s3_res = [] { const char* e = getenv("SCP_VQ_S3_RES"); return e && e[0] == '1'; }();
+    if (pair && s3_res && tc::resident_smem_bytes<128, 2, 3, Sweep3Epi, tc::MC_PAIR, 1>(sc.k_chunks) <= tc::kMaxDynSmem)
+      rc = tc::launch_stream_gemm<128, 2, 3, Sweep3Epi, 2, tc::MC_PAIR, 1>(maps, sc, ep, s, "vq_sweep3");
+    else if (pair) rc = tc::launch_stream_gemm<128, 2, 5, Sweep3Epi, 2, tc::MC_PAIR>(maps, sc, ep, s, "vq_sweep3");
     else rc = tc::launch_stream_gemm<128, 2, 3, Sweep3Epi>(maps, sc, ep, s, "vq_sweep3");
     if (rc) return rc;
   }
