@@ -25,4 +25,4 @@ from .module.cif import CIF  # noqa: F401
 from .model.kw_glue import compute_loss, gather_loss_feats, ddp_grad_scale  # noqa: F401
 from .install import install  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -133,7 +133,7 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols
 
 }  // namespace scp
 
-extern "C" int scp_version(void) { return 0 * 10000 + 1 * 100 + 0; }
+extern "C" int scp_version(void) { return 0 * 10000 + 2 * 100 + 0; }
 
 extern "C" int scp_num_launches(void) { return scp::g_launches.load(std::memory_order_relaxed); }
 

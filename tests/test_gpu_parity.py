@@ -531,6 +531,25 @@ def test_vq_fused_vs_oracle(scp, shape, tau):
     assert norm_err(gk, g_ref) < TOL
 
 
+@pytest.mark.parametrize("eps", [1e-2, 1e-4, 1e-6])
+def test_vq_argmax_among_near_ties(scp, eps):
+    """Stress of the exact arg-max: every table row is one of 16 directions plus a perturbation of relative size eps, so
+    ~V/16 columns fall inside the fp16 rescue margin of each row's maximum (eps <= 1e-4: inside the fp32 margin as well)
+    and all three re-scoring levels decide the winner.  The code must equal the fp64 arg-max of the fp32 inputs."""
+    B, K, V, D = 16, 4, 2048 + 40, 256
+    gen = torch.Generator().manual_seed(int(1 / eps))
+    base = torch.nn.functional.normalize(torch.randn(16, D, generator=gen), dim=-1)
+    table = base[torch.randint(0, 16, (V,), generator=gen)] * (1.0 + 0.5 * torch.rand(V, 1, generator=gen))
+    table = table + eps * torch.randn(V, D, generator=gen) / D ** 0.5
+    kw = base[torch.randint(0, 16, (B * K,), generator=gen)] + 0.05 * torch.randn(B * K, D, generator=gen)
+    kw = kw.view(B, K, D)
+    vq = _make_vq(scp, "fixed=0.1", False)
+    res, out = vq.quantize_keywords(kw.cuda(), table.cuda())
+    n_ties = _tie_tolerant_index_check(res["targets"], kw, table)
+    assert n_ties <= 1            # only a gap below fp32 summation noise may differ (asserted inside the helper)
+    assert torch.equal(out.cpu().view(-1, D), table[res["targets"].view(-1).cpu()])
+
+
 def test_vq_edge_cases(scp):
     V, D = 520, 64
     gen = torch.Generator().manual_seed(5)
