@@ -432,15 +432,119 @@ def golden_hybrid_loss():
          loss=out["loss"], c_cl_loss=out["c_cl_loss"], p_cl_loss=out["p_cl_loss"], quantity_loss=out["quantity_loss"],
          grad_cascaded=grads[0], grad_parallel=grads[1], grad_temperature=grads[2])
 
+# ----------------------------------------------------------------------------------------------
+def golden_chain():
+    """The cascaded branch from the CLS keywords to the loss, with the reference's own glue in between
+    (kw_branches.py:143-156, :181-197, :390-395 / :744-750; clip_official.py:222-279; kwClip.py:905-907, :1015-1028):
+
+        audio_feat (B,K,Da) -> linear_proj -> Kw_BatchNorm[_dynamic] -> cosine -> VQ -> subword_prob @ E
+                            -> ClipModel.encode_keywords (stand-in text tower) -> x / ||x|| -> MaskedContrastiveLoss
+
+    Pins the COMPOSITION of N1 + V1 + V3 + V4 + N3 + N0 + S3 and the gradient that flows back through all of them to the
+    projection, the batch-norm parameters, the text tower and the loss temperature."""
+    ref.import_avssl()
+    import avssl.model.kw_branches as kb
+    import avssl.module.clip_official as co
+    vq_mod = ref.load_leaf("avssl/module/speechclip_c_modules/my_vector_quantizer.py", "ref_vq_chain")
+    bn_mod = ref.load_leaf("avssl/module/speechclip_c_modules/kw_bn.py", "ref_kw_bn_chain")
+    losses = ref.load_leaf("avssl/module/losses.py", "ref_losses_chain")
+    cases = [
+        # name, B, K, Da, D, V, dynamic keyword counts (None = fixed K for every utterance)
+        ("chain_cascaded_fixed8", 16, 8, 96, 64, 600, None),
+        ("chain_cascaded_dynamic", 12, 10, 96, 64, 600, [10, 3, 7, 1, 5, 10, 2, 8, 4, 6, 9, 3]),
+    ]
+    for i, (name, B, K, Da, D, V, lens) in enumerate(cases):
+        g = _gen(800 + i)
+        torch.manual_seed(SEED + 800 + i)
+        L = 77
+        table = torch.randn(V, D, generator=g) * 0.02 + 0.003 * torch.randn(1, D, generator=g)
+        emb = torch.nn.Embedding(V, D)
+        with torch.no_grad():
+            emb.weight.copy_(table)
+        emb.weight.requires_grad_(False)
+
+        class Tower(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.mix = torch.nn.Linear(D, D)
+
+            def forward(self, x):  # (L, N, D)
+                return torch.tanh(self.mix(x))
+
+        model = types.SimpleNamespace(token_embedding=emb, positional_embedding=torch.randn(L, D, generator=g) * 0.01,
+                                      transformer=Tower(), ln_final=torch.nn.LayerNorm(D),
+                                      text_projection=torch.randn(D, 32, generator=g) * 0.1)
+        sot, eot = V - 2, V - 1
+        clip = types.SimpleNamespace(model=model, device=torch.device("cpu"), selected_text_emb_ids=None,
+                                     tokenizer=types.SimpleNamespace(encoder={"<|startoftext|>": sot,
+                                                                              "<|endoftext|>": eot}))
+        clip.encode_keywords = types.MethodType(co.ClipModel.encode_keywords, clip)
+
+        branch = kb.GeneralBranch.__new__(kb.GeneralBranch)
+        torch.nn.Module.__init__(branch)
+        branch.text_dim = D
+        branch.clip = clip
+        branch.linear_proj = torch.nn.Linear(Da, D)
+        init_bias, init_scale = table.mean(0), table.std(0)                       # kw_branches.py:99-100
+        if lens is None:
+            branch.bn_layer = bn_mod.Kw_BatchNorm(kw_num=K, kw_dim=D, batchnorm_type="eachKw", init_bias=init_bias,
+                                                  init_scale=init_scale, std_scale=1, learnable=True, parallel=True)
+        else:
+            branch.bn_layer = bn_mod.Kw_BatchNorm_dynamic(kw_dim=D, init_bias=init_bias, init_scale=init_scale,
+                                                          std_scale=1, learnable=True)
+        branch.vector_quantizer = vq_mod.SimpleVectorQuantizer(temp="fixed=0.1")
+        branch.train(True)
+        bn_state_in = {k: v.clone() for k, v in branch.bn_layer.state_dict().items()}
+        criterion = losses.MaskedContrastiveLoss(temperature=0.07, temperature_trainable=True)
+
+        audio_feat = torch.randn(B, K, Da, generator=g).requires_grad_(True)
+        image_feat = torch.randn(B, 32, generator=g)
+        image_feat = image_feat / image_feat.norm(dim=-1, keepdim=True)           # kwClip.py:857
+        ids = torch.randint(0, B // 2, (B,), generator=g)
+
+        # -- the branch forward from the CLS keywords on (kw_branches.py:390-395 / :744-750)
+        vq_results, keywords = branch.vq_audio_features(audio_feat)
+        keyword_num = K if lens is None else torch.tensor(lens)
+        cascaded = clip.encode_keywords(keywords, keyword_num)
+        cascaded_n = cascaded / cascaded.norm(dim=-1, keepdim=True)               # kwClip.py:905-907
+        loss = criterion(feat_A=cascaded_n.float(), feat_B=image_feat.float(), index=ids)  # kwClip.py:1021-1025
+
+        bn_state_out = {k: v.clone() for k, v in branch.bn_layer.state_dict().items()}
+
+        # the chain is only a meaningful pin if no arg-max sits on a knife edge: check the fp64 top-2 gap
+        # (this second training-mode call moves the running statistics again: they were snapshotted above)
+        with torch.no_grad():
+            bn_out = branch.project_feats_to_CLIPspace(audio_feat).double()
+            cos = torch.nn.functional.normalize(bn_out, dim=-1) @ torch.nn.functional.normalize(table.double(), dim=-1).t()
+            cos[..., [0, 2, 3]] = -float("inf")
+            top2 = cos.topk(2, dim=-1).values
+            assert (top2[..., 0] - top2[..., 1]).min() > 1e-5, "regenerate with another seed: near-tie in the fixture"
+
+        params = {"audio_feat": audio_feat, "proj_weight": branch.linear_proj.weight, "proj_bias": branch.linear_proj.bias,
+                  "bn_weight": branch.bn_layer.bn_layer.weight, "bn_bias": branch.bn_layer.bn_layer.bias,
+                  "mix_w": model.transformer.mix.weight, "mix_b": model.transformer.mix.bias,
+                  "ln_weight": model.ln_final.weight, "ln_bias": model.ln_final.bias,
+                  "temperature": criterion.temperature}
+        grads = torch.autograd.grad(loss, list(params.values()))
+        save(name, audio_feat=audio_feat, image_feat=image_feat, ids=ids,
+             keyword_num=np.array(lens if lens is not None else K),
+             table=table, pos_emb=model.positional_embedding, sot=np.array(sot), eot=np.array(eot),
+             proj_weight=branch.linear_proj.weight, proj_bias=branch.linear_proj.bias,
+             mix_w=model.transformer.mix.weight, mix_b=model.transformer.mix.bias,
+             text_projection=model.text_projection,
+             **{f"bn_in__{k.replace('.', '__')}": v for k, v in bn_state_in.items()},
+             **{f"bn_out__{k.replace('.', '__')}": v for k, v in bn_state_out.items()},
+             targets=vq_results["targets"], keywords=keywords, code_perplexity=vq_results["code_perplexity"],
+             prob_perplexity=vq_results["prob_perplexity"], ent_per_t=vq_results["ent_per_t"],
+             cascaded_audio_feat=cascaded, loss=loss, temperature=np.array(0.07),
+             **{f"grad_{k}": gr for k, gr in zip(params, grads)})
+
 
 if __name__ == "__main__":
     assert ref.reference_available(), "needs /root/reference"
     torch.set_num_threads(max(os.cpu_count() or 1, 1))
-    golden_wsum()
-    golden_s1_tail()
-    golden_kwbn()
-    golden_splice()
-    golden_cif()
-    golden_vq()
-    golden_nce()
-    golden_hybrid_loss()
+    groups = {"wsum": golden_wsum, "s1tail": golden_s1_tail, "kwbn": golden_kwbn, "splice": golden_splice,
+              "cif": golden_cif, "vq": golden_vq, "nce": golden_nce, "hybrid_loss": golden_hybrid_loss,
+              "chain": golden_chain}
+    for key in (sys.argv[1:] or list(groups)):   # `make_golden.py chain` regenerates one group only
+        groups[key]()

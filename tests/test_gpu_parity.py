@@ -790,6 +790,66 @@ def test_hybrid_loss_global_batch_local_rows(scp, cfg):
     assert rel_err(gt_sum, rt) < TOL
 
 
+@pytest.mark.parametrize("name", golden_names("chain_"))
+def test_cascaded_chain_golden(scp, name):
+    """The cascaded branch from the CLS keywords to the loss, composed as the reference composes it
+    (kw_branches.py:390-395 / :744-750 -> kwClip.py:905-907 -> :1021-1025): projection (library Linear) -> N1 batch-norm
+    -> fused V1+V3+V4 -> N3 splice + stand-in text tower -> N0 normalise / G0 gather -> S3 loss, against what the
+    reference's own GeneralBranch / ClipModel.encode_keywords / MaskedContrastiveLoss produced for the same tensors.
+    One backward through the whole chain: every CUDA autograd node hands its gradient to the next."""
+    import types
+    from speechclip_plus_b200.module.clip_glue import encode_keywords
+    g = load_golden(name)
+    dynamic = g["keyword_num"].dim() > 0
+    B, K, Da = g["audio_feat"].shape
+    V, D = g["table"].shape
+    clip, _ = _fake_clip(g)
+    clip.encode_keywords = types.MethodType(encode_keywords, clip)
+    proj = torch.nn.Linear(Da, D).cuda()
+    proj.weight.data.copy_(g["proj_weight"]); proj.bias.data.copy_(g["proj_bias"])
+    init_bias, init_scale = g["table"].mean(0), g["table"].std(0)                          # kw_branches.py:99-100
+    if dynamic:
+        bn = scp.Kw_BatchNorm_dynamic(kw_dim=D, init_bias=init_bias, init_scale=init_scale, std_scale=1, learnable=True)
+    else:
+        bn = scp.Kw_BatchNorm(kw_num=K, kw_dim=D, batchnorm_type="eachKw", init_bias=init_bias, init_scale=init_scale,
+                              std_scale=1, learnable=True, parallel=True)
+    state_in = {k[len("bn_in__"):].replace("__", "."): v for k, v in g.items() if k.startswith("bn_in__")}
+    # the constructor's own initialisation from the table statistics equals the reference's (kw_bn.py:68-95)
+    assert rel_err(bn.state_dict()["bn_layer.weight"], state_in["bn_layer.weight"]) < 1e-6
+    assert rel_err(bn.state_dict()["bn_layer.bias"], state_in["bn_layer.bias"]) < 1e-6
+    bn.load_state_dict(state_in)                                                           # same keys as the reference
+    bn = bn.cuda().train()
+    branch = types.SimpleNamespace(clip=clip, vector_quantizer=scp.SimpleVectorQuantizer("fixed=0.1").cuda().train(),
+                                   project_feats_to_CLIPspace=lambda f: bn(proj(f)))      # kw_branches.py:143-156
+    crit = scp.MaskedContrastiveLoss(temperature=float(g["temperature"]), temperature_trainable=True).cuda()
+
+    audio_feat = g["audio_feat"].cuda().requires_grad_(True)
+    vq_results, keywords = scp.fused_vq_audio_features(branch, audio_feat)
+    keyword_num = g["keyword_num"].cuda() if dynamic else int(g["keyword_num"])
+    cascaded = clip.encode_keywords(keywords, keyword_num)
+    gathered, rows = scp.gather_loss_feats({"id": g["ids"].cuda(), "image_feat": g["image_feat"].cuda(),
+                                            "cascaded_audio_feat": cascaded})
+    out = scp.compute_loss(gathered, crit, 1.0, 0.0, local_rows=rows)
+
+    assert torch.equal(vq_results["targets"].cpu(), g["targets"])                          # code indices: bit-exact
+    assert rel_err(keywords, g["keywords"]) < TOL
+    for key in ("code_perplexity", "prob_perplexity", "ent_per_t"):
+        assert rel_err(vq_results[key], g[key]) < TOL, key
+    for key in ("running_mean", "running_var"):
+        assert rel_err(bn.state_dict()[f"bn_layer.{key}"], g[f"bn_out__bn_layer__{key}"]) < TOL, key
+    assert int(bn.state_dict()["bn_layer.num_batches_tracked"]) == int(g["bn_out__bn_layer__num_batches_tracked"])
+    assert rel_err(cascaded, g["cascaded_audio_feat"]) < TOL
+    assert rel_err(out["loss"], g["loss"]) < TOL and out["loss"] is out["c_cl_loss"]
+    params = {"audio_feat": audio_feat, "proj_weight": proj.weight, "proj_bias": proj.bias,
+              "bn_weight": bn.bn_layer.weight, "bn_bias": bn.bn_layer.bias,
+              "mix_w": clip.model.transformer.mix.weight, "mix_b": clip.model.transformer.mix.bias,
+              "ln_weight": clip.model.ln_final.weight, "ln_bias": clip.model.ln_final.bias,
+              "temperature": crit.temperature}
+    grads = torch.autograd.grad(out["loss"], list(params.values()))
+    for k, gr in zip(params, grads):
+        assert norm_err(gr, g[f"grad_{k}"]) < TOL, k
+
+
 def test_install_patches_reference_namespaces(scp):
     import sys
     import types
