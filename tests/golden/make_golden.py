@@ -473,7 +473,7 @@ def golden_chain():
 
         model = types.SimpleNamespace(token_embedding=emb, positional_embedding=torch.randn(L, D, generator=g) * 0.01,
                                       transformer=Tower(), ln_final=torch.nn.LayerNorm(D),
-                                      text_projection=torch.randn(D, 32, generator=g) * 0.1)
+                                      text_projection=torch.randn(D, 64, generator=g) * 0.1)
         sot, eot = V - 2, V - 1
         clip = types.SimpleNamespace(model=model, device=torch.device("cpu"), selected_text_emb_ids=None,
                                      tokenizer=types.SimpleNamespace(encoder={"<|startoftext|>": sot,
@@ -498,7 +498,7 @@ def golden_chain():
         criterion = losses.MaskedContrastiveLoss(temperature=0.07, temperature_trainable=True)
 
         audio_feat = torch.randn(B, K, Da, generator=g).requires_grad_(True)
-        image_feat = torch.randn(B, 32, generator=g)
+        image_feat = torch.randn(B, 64, generator=g)
         image_feat = image_feat / image_feat.norm(dim=-1, keepdim=True)           # kwClip.py:857
         ids = torch.randint(0, B // 2, (B,), generator=g)
 

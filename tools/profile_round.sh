@@ -21,5 +21,9 @@ ncu --set full --import-source on --clock-control none \
 ncu -i gpurun_out/${tag}_full.ncu-rep --page raw --csv > gpurun_out/${tag}_full_raw.csv 2>/dev/null
 # kernels outside the bench step (S1' variants, N1 / N3 / N4): device times and achieved bandwidth
 python tools/aux_kernel_times.py > gpurun_out/${tag}_aux_kernels.json 2> gpurun_out/${tag}_aux_kernels.err
+
+
+# the three kernel groups at the per-GPU sizes of every BASELINE config (the bench line is config 3 only)
+python tools/config_kernel_times.py > gpurun_out/${tag}_config_kernels.json 2> gpurun_out/${tag}_config_kernels.err
 tail -2 gpurun_out/${tag}_ncu_full.log
 cat gpurun_out/${tag}_bench.json
