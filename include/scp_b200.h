@@ -123,6 +123,9 @@ int scp_vq_prepare_table(const float* table, int64_t V, int64_t D,
                          void* table_hat, void* table_hat_t, float* table_norm, float* table_mean,
                          scp_stream_t stream);
 
+/* The workspace holds the per-chunk / per-group maxima scanned by the exact arg-max, the split row statistics and --
+ * unless the environment sets SCP_VQ_COLSUM=0 (older two-sweep mode) -- an (Mp, Vp) fp16 scratch of e^c from which avg_probs
+ * is reduced in one HBM pass: 2*Mp*Vp bytes (202 MB at M = 2048, V = 49408). */
 size_t scp_vq_fwd_workspace_bytes(int64_t M, int64_t V, int64_t D);
 
 /* Forward.  kw (M,D) fp32 = keyword vectors in CLIP space, M = B*K rows ordered (b,k).

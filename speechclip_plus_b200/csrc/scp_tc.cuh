@@ -158,6 +158,20 @@ __device__ __forceinline__ f32x2 ex2_2(f32x2 x) {  // two MUFU.EX2
   unpack2(x, a, b);
   return pack2(fast_ex2(a), fast_ex2(b));
 }
+// two fp32 -> one packed fp16 pair (element `a` of pack2(a, b) in the low half, i.e. at the lower address)
+__device__ __forceinline__ uint32_t cvt_f16x2(f32x2 v) {
+  float lo, hi;
+  unpack2(v, lo, hi);
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// 32-byte global store (one full sector per thread per instruction; sm_100+, PTX 8.8)
+__device__ __forceinline__ void stg256(void* gptr, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(gptr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));

@@ -175,9 +175,12 @@ struct Sweep1Epi {
     float* group_max;   // (Mp, n_chunks, 4): maximum of every 8-column group (read for candidate chunks only)
     float* partials;    // (Mp, n_slots, 4): sum e^c, sum c e^c, running max, sum e^{(c-max)/tau};  n_slots = 2*n_groups
     const float* tau;   // device scalar
+    __half* e16;        // nullable (Mp, ldE) fp16: e^c of every logit, consumed by vq_colsum_kernel (avg_probs)
+    int64_t ldE;
     int n_chunks;
     int n_groups;
     int V;
+    int dbg;            // timing ablations (env SCP_VQ_S1_DBG, results invalid): 1 = no chunk/group maxima stores
     MaskedCols mc;
   };
   static constexpr int kSmemBytes = 0;
@@ -203,7 +206,7 @@ struct Sweep1Epi {
   __device__ __forceinline__ void tile_begin(int) {}
   __device__ __forceinline__ void tile_end(int) {}
   template <int N>
-  __device__ __forceinline__ void pow_chunk(const float (&c)[32]) {
+  __device__ __forceinline__ void pow_chunk(const float (&c)[32], uint32_t (&h)[16]) {
     const tc::f32x2 kl = tc::pack2(kLog2e, kLog2e);
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
@@ -213,7 +216,16 @@ struct Sweep1Epi {
       acc_e[a] = tc::add2(acc_e[a], e1);
       acc_ce[a] = tc::fma2(cc, e1, acc_ce[a]);
       acc_et[a] = tc::add2(acc_et[a], ipow2<N>(e1));
+      h[i >> 1] = tc::cvt_f16x2(e1);
     }
+  }
+  // e^c of the chunk's 32 columns as fp16: 64 contiguous bytes of this thread's row, two full-sector stores.  e^c lies in
+  // [1/e, e], so fp16 keeps 11 significant bits (relative error <= 4.9e-4 per element, unbiased; avg_probs averages M of
+  // them).  Masked / out-of-range columns hold 0 or are never written: vq_colsum_kernel selects them away by index.
+  __device__ __forceinline__ void store_e(int col0, const uint32_t (&h)[16]) {
+    __half* dst = p.e16 + row * p.ldE + col0;
+    tc::stg256(dst, h);
+    tc::stg256(dst + 16, h + 8);
   }
   __device__ __forceinline__ void chunk(int col0, float (&v)[1][32]) {
     float(&c)[32] = v[0];
@@ -231,15 +243,22 @@ struct Sweep1Epi {
       gm[g] = tc::fmax3(tc::fmax3(c[8 * g], c[8 * g + 1], c[8 * g + 2]), tc::fmax3(c[8 * g + 3], c[8 * g + 4], c[8 * g + 5]),
                         fmaxf(c[8 * g + 6], c[8 * g + 7]));
     const float cmax = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-    p.chunk_max[row * p.n_chunks + (col0 >> 5)] = cmax;
-    *reinterpret_cast<float4*>(p.group_max + (row * p.n_chunks + (col0 >> 5)) * 4) = make_float4(gm[0], gm[1], gm[2], gm[3]);
+    if (!(p.dbg & 1)) {
+      p.chunk_max[row * p.n_chunks + (col0 >> 5)] = cmax;
+      // with the e^c scratch the arg-max kernel filters the groups of a candidate chunk from those 64 bytes instead: the
+      // 16-byte group store and the two 32-byte e^c stores together saturated the store path (sweep 1: 92 -> 123 us)
+      if (!p.e16)
+        *reinterpret_cast<float4*>(p.group_max + (row * p.n_chunks + (col0 >> 5)) * 4) = make_float4(gm[0], gm[1], gm[2], gm[3]);
+    }
     if (cmax <= kNegBig) return;  // fully masked / padding chunk: contributes nothing (and has no finite maximum)
     if (pow10) {
       // |c| <= 1 and 1/tau = 10: e^{c/tau} = (e^c)^10 cannot overflow, so no running maximum is needed and the
       // second exponential becomes four packed multiplies -- ONE SFU op per logit instead of two.  Only this one
       // specialisation is compiled: every extra variant is another unrolled copy of the loop in the instruction cache.
       run_max = 0.f;  // the partial sum is relative to a shift of 0
-      pow_chunk<10>(c);
+      uint32_t h[16];
+      pow_chunk<10>(c, h);
+      if (p.e16) store_e(col0, h);
       return;
     }
     if (cmax > run_max) {  // rescale the temperature-tau sum to the new running maximum
@@ -251,6 +270,7 @@ struct Sweep1Epi {
     }
     const float shift = -run_max * k_tau;
     const tc::f32x2 kl = tc::pack2(kLog2e, kLog2e), kt = tc::pack2(k_tau, k_tau), sh = tc::pack2(shift, shift);
+    uint32_t h[16];
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
       const int a = (i >> 1) & 1;
@@ -259,7 +279,9 @@ struct Sweep1Epi {
       acc_e[a] = tc::add2(acc_e[a], e1);
       acc_ce[a] = tc::fma2(cc, e1, acc_ce[a]);
       acc_et[a] = tc::add2(acc_et[a], tc::ex2_2(tc::fma2(cc, kt, sh)));
+      h[i >> 1] = tc::cvt_f16x2(e1);
     }
+    if (p.e16) store_e(col0, h);
   }
   __device__ __forceinline__ void finish() {
     float4 o = make_float4(tc::hsum2(tc::add2(acc_e[0], acc_e[1])), tc::hsum2(tc::add2(acc_ce[0], acc_ce[1])), run_max,
@@ -413,7 +435,8 @@ vq_select_kernel(const float* __restrict__ kw, const float* __restrict__ table, 
                  const float* __restrict__ partials, int n_groups,
                  const float* __restrict__ tau_ptr, MaskedCols mc, int64_t* __restrict__ idx_out,
                  float* __restrict__ keywords, float* __restrict__ row_stats, float* __restrict__ code_hist,
-                 float* __restrict__ lse1_l2, int phases /* bit 0: row statistics, bit 1: arg-max + gather */) {
+                 float* __restrict__ lse1_l2, int phases /* bit 0: row statistics, bit 1: arg-max + gather */,
+                 const __half* __restrict__ e16 /* nullable: (Mp, ldE) fp16 e^c, replaces group_max */, int64_t ldE) {
   const int lane = threadIdx.x & 31;
   const int64_t m = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (m >= M) return;  // whole warp
@@ -484,6 +507,9 @@ vq_select_kernel(const float* __restrict__ kw, const float* __restrict__ table, 
     mx = warp_max(mx);  // (the shuffles also order the shared-memory writes before the reads below)
     __syncwarp();
     const float thr = mx - kRescueMargin;
+    // group filter from the e^c scratch: fp16(e^c) >= e^thr (1 - 1e-3) holds for every column with c >= thr (fp16 rounding
+    // 4.9e-4 + ex2.approx 2^-22), i.e. the filter only ever admits MORE groups than the exact test c >= thr
+    const float thr_e = expf(thr) * (1.0f - 1.0e-3f);
     // every chunk whose maximum could hide the true arg-max is re-scored exactly (usually one or two per row), and
     // inside it only the 8-column groups whose own maximum qualifies
 #pragma unroll 1
@@ -494,11 +520,19 @@ vq_select_kernel(const float* __restrict__ kw, const float* __restrict__ table, 
       while (todo) {
         const int chunk = c0 + __ffs(todo) - 1;
         todo &= todo - 1;
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(group_max + (m * n_chunks + chunk) * 4));
-        const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+        unsigned gq;  // bit g: group g of this chunk can hold the arg-max (warp-uniform)
+        if (e16) {
+          const float e = __half2float(e16[m * ldE + (int64_t)chunk * 32 + lane]);
+          const unsigned cols = __ballot_sync(0xffffffffu, e >= thr_e);
+          gq = ((cols & 0xffu) ? 1u : 0u) | ((cols & 0xff00u) ? 2u : 0u) | ((cols & 0xff0000u) ? 4u : 0u) |
+               ((cols & 0xff000000u) ? 8u : 0u);
+        } else {
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(group_max + (m * n_chunks + chunk) * 4));
+          gq = (g4.x >= thr ? 1u : 0u) | (g4.y >= thr ? 2u : 0u) | (g4.z >= thr ? 4u : 0u) | (g4.w >= thr ? 8u : 0u);
+        }
 #pragma unroll 1
         for (int g = 0; g < 4; ++g)
-          if (gv[g] >= thr)
+          if ((gq >> g) & 1u)
             best = better(best, rescore_chunk<NV>(table, table_norm, table_hat, V, D, chunk * 4 + g, kreg, khreg,
                                                   margin2, thr, mc, lane));
       }
@@ -578,6 +612,64 @@ struct Sweep2Epi {
 };
 
 // =====================================================================================================================
+// column sums of the normalised logits: avg_probs[v] = 1/M sum_m e^{c[m,v]} / Z_m      (HBM-bound, one pass)
+// =====================================================================================================================
+// e16 (Mp, ldE) fp16 = e^c from sweep 1, lse1_l2[m] = -log2(Z_m) from the statistics phase of vq_select.  Block <-> strip
+// of 64 columns x all M rows: warp w takes the rows m = w (mod 8), lane l the columns 2l, 2l+1 of the strip (one 128-byte
+// row segment per warp load, eight loads in flight per lane); the eight warps are combined through shared memory in a
+// fixed order, so the result is deterministic.  Vp/64 = 772 blocks of 256 threads at the full vocabulary: all resident.
+constexpr int kColsumCols = 64;
+__global__ void __launch_bounds__(256)
+vq_colsum_kernel(const __half* __restrict__ e16, int64_t ldE, const float* __restrict__ lse1_l2, int64_t M, int V,
+                 float inv_m, MaskedCols mc, float* __restrict__ avg_probs) {
+  __shared__ float2 s_part[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t col = (int64_t)blockIdx.x * kColsumCols + 2 * lane;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(e16 + col);
+  const int64_t ld32 = ldE >> 1;
+  float a0 = 0.f, a1 = 0.f;
+  int64_t m = warp;
+  for (; m + 56 < M; m += 64) {
+    uint32_t h[8];
+    float w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      h[j] = __ldcs(src + (m + 8 * j) * ld32);   // streamed once: evict first
+      w[j] = __ldg(lse1_l2 + m + 8 * j);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
+      const float wj = tc::fast_ex2(w[j]);
+      a0 = fmaf(e.x, wj, a0);
+      a1 = fmaf(e.y, wj, a1);
+    }
+  }
+  for (; m < M; m += 8) {
+    const uint32_t hh = __ldcs(src + m * ld32);
+    const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&hh));
+    const float wj = tc::fast_ex2(__ldg(lse1_l2 + m));
+    a0 = fmaf(e.x, wj, a0);
+    a1 = fmaf(e.y, wj, a1);
+  }
+  s_part[warp][lane] = make_float2(a0, a1);
+  __syncthreads();
+  if (warp == 0) {
+    float2 t = s_part[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      t.x += s_part[w][lane].x;
+      t.y += s_part[w][lane].y;
+    }
+    const int v0 = (int)col, v1 = v0 + 1;
+    float2 o;
+    o.x = (v0 < V && !is_masked(mc, v0)) ? t.x * inv_m : 0.f;
+    o.y = (v1 < V && !is_masked(mc, v1)) ? t.y * inv_m : 0.f;
+    *reinterpret_cast<float2*>(avg_probs + col) = o;
+  }
+}
+
+// =====================================================================================================================
 // metrics: code_perplexity, prob_perplexity, diversity_loss, ent_per_t      (one block)
 // =====================================================================================================================
 constexpr int kMetricBlocks = 64;
@@ -588,29 +680,36 @@ constexpr int kMetricBlocks = 64;
 __global__ void __launch_bounds__(256)
 vq_metrics_kernel(const float* __restrict__ code_hist, const float* __restrict__ avg_probs,
                   const float* __restrict__ row_stats, int64_t M, int K, int V,
-                  float* __restrict__ partial /* (kMetricBlocks, 2) */, unsigned int* __restrict__ ticket,
-                  float* __restrict__ metrics) {
-  __shared__ float s_red[2][8];
+                  float* __restrict__ partial /* (kMetricBlocks, 2) | ticket | (kMetricBlocks,) */,
+                  unsigned int* __restrict__ ticket, float* __restrict__ metrics) {
+  __shared__ float s_red[3][8];
   __shared__ bool s_last;
   const float inv_m = 1.0f / (float)M;
-  float hc = 0.f, hp = 0.f;
+  float* partial_sum = partial + kMetricBlocks * 2 + 1;  // third partial (sum of avg_probs), behind the ticket word
+  float hc = 0.f, hp = 0.f, sp = 0.f;
   for (int v = blockIdx.x * 256 + threadIdx.x; v < V; v += kMetricBlocks * 256) {
     const float h = code_hist[v] * inv_m;  // my_vector_quantizer.py:94-99
     hc += h * logf(h + 1e-7f);
     if (avg_probs) {
       const float a = avg_probs[v];  // :119-121
       hp += a * logf(a + 1e-7f);
+      sp += a;
     }
   }
   hc = warp_sum(hc);
   hp = warp_sum(hp);
-  if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = hc; s_red[1][threadIdx.x >> 5] = hp; }
+  sp = warp_sum(sp);
+  if ((threadIdx.x & 31) == 0) {
+    s_red[0][threadIdx.x >> 5] = hc;
+    s_red[1][threadIdx.x >> 5] = hp;
+    s_red[2][threadIdx.x >> 5] = sp;
+  }
   __syncthreads();
-  if (threadIdx.x < 2) {
+  if (threadIdx.x < 3) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += s_red[threadIdx.x][i];
-    __stcg(&partial[blockIdx.x * 2 + threadIdx.x], t);
+    __stcg(threadIdx.x < 2 ? &partial[blockIdx.x * 2 + threadIdx.x] : &partial_sum[blockIdx.x], t);
   }
   __threadfence();
   __syncthreads();
@@ -619,13 +718,21 @@ vq_metrics_kernel(const float* __restrict__ code_hist, const float* __restrict__
   if (!s_last) return;
   __threadfence();
   if (threadIdx.x < 32) {
-    float hc2 = 0.f, hp2 = 0.f;
-    for (int i = threadIdx.x; i < kMetricBlocks; i += 32) { hc2 += __ldcg(&partial[2 * i]); hp2 += __ldcg(&partial[2 * i + 1]); }
+    float hc2 = 0.f, hp2 = 0.f, sp2 = 0.f;
+    for (int i = threadIdx.x; i < kMetricBlocks; i += 32) {
+      hc2 += __ldcg(&partial[2 * i]);
+      hp2 += __ldcg(&partial[2 * i + 1]);
+      sp2 += __ldcg(&partial_sum[i]);
+    }
     hc2 = warp_sum(hc2);
     hp2 = warp_sum(hp2);
+    sp2 = warp_sum(sp2);
     if (threadIdx.x == 0) {
       metrics[0] = expf(-hc2);
-      const float pp = avg_probs ? expf(-hp2) : nanf("");
+      // avg_probs is a mean of softmax rows, so its entries sum to one exactly; the column-sum path carries a common
+      // factor S = 1 + O(1e-5) (fp16 rounding of e^c against the unrounded normaliser).  The entropy of a/S follows in
+      // closed form: -sum (a/S) log(a/S) = (-sum a log a)/S + log S  -- an identity when S = 1.
+      const float pp = avg_probs ? expf(-hp2 / sp2 + logf(sp2)) : nanf("");
       metrics[1] = pp;
       metrics[2] = ((float)V - pp) / (float)V;  // diversity_loss, :155-158
       *ticket = 0u;
@@ -1020,12 +1127,21 @@ struct VqFwdWs {
   float* partials;
   float* lse1_l2;
   float* metric_part;
+  __half* e16;   // (Mp, Vp) fp16 e^c written by sweep 1 for the column sums (null in the two-sweep mode)
   size_t total;
   int n_chunks, n_groups;
 };
 // CTA pairs (cta_group::2) need at least two row tiles; single-tile problems run the one-CTA kernel.
 static bool vq_use_pair(int m_tiles) { return m_tiles >= 2; }
 static int vq_m_ctas(int m_tiles) { return vq_use_pair(m_tiles) ? 2 * (int)ceil_div(m_tiles, 2) : m_tiles; }
+
+// avg_probs = mean_m softmax(c)[m,:] needs the row normalisers, i.e. a second pass over the logits.  Default: sweep 1
+// also writes e^c as fp16 (Mp x Vp x 2 bytes of workspace) and vq_colsum_kernel reduces it in one HBM pass;
+// SCP_VQ_COLSUM=0 selects the older second tensor-core sweep (transposed product, no logit scratch).
+static bool vq_colsum_enabled() {
+  static const bool on = [] { const char* e = getenv("SCP_VQ_COLSUM"); return !(e && e[0] == '0'); }();
+  return on;
+}
 
 // bring-up switch: SCP_VQ_RESIDENT=0 selects the streaming-X kernels (A/B measurement of the resident-X mode)
 static bool vq_resident_enabled() {
@@ -1056,7 +1172,8 @@ static VqFwdWs vq_fwd_ws(void* base, int64_t M, int64_t V) {
   w.group_max = static_cast<float*>(take((size_t)Mp * w.n_chunks * 4 * 4));  // four 8-column group maxima per chunk
   w.partials = static_cast<float*>(take((size_t)Mp * w.n_groups * 2 * 16));
   w.lse1_l2 = static_cast<float*>(take((size_t)round_up(M, 256) * 4));
-  w.metric_part = static_cast<float*>(take((size_t)(kMetricBlocks * 2 + 1) * 4));  // + the ticket counter
+  w.metric_part = static_cast<float*>(take((size_t)(kMetricBlocks * 3 + 1) * 4));  // + the ticket counter
+  w.e16 = vq_colsum_enabled() ? static_cast<__half*>(take((size_t)Mp * Vp * 2)) : nullptr;
   w.total = off;
   return w;
 }
@@ -1181,6 +1298,10 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
     ep.group_max = ws.group_max;
     ep.partials = ws.partials;
     ep.tau = tau;
+    ep.e16 = avg_probs ? ws.e16 : nullptr;
+    ep.ldE = Vp;
+    static const int s1_dbg = [] { const char* e = getenv("SCP_VQ_S1_DBG"); return e ? atoi(e) : 0; }();
+    ep.dbg = s1_dbg;
     ep.n_chunks = ws.n_chunks;
     ep.n_groups = ws.n_groups;
     ep.V = (int)V;
@@ -1205,7 +1326,7 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
   vq_select_kernel<NVV><<<(unsigned)ceil_div(M, 4), 128, sel_smem, STREAM>>>(                                          \
       kw, table, table_norm, reinterpret_cast<const __half*>(table_hat), reinterpret_cast<const __half*>(kw_hat), M,   \
       (int)V, (int)D, ws.chunk_max, ws.group_max, ws.n_chunks, ws.partials, 2 * ws.n_groups, tau, mc, idx, keywords,   \
-      row_stats, code_hist, ws.lse1_l2, PHASES)
+      row_stats, code_hist, ws.lse1_l2, PHASES, avg_probs ? ws.e16 : nullptr, Vp)
 #define SCP_SELECT(STREAM, PHASES)                                                                                     \
   do {                                                                                                                 \
     if (D <= 128) SCP_SELECT_LAUNCH(1, STREAM, PHASES);                                                                \
@@ -1234,8 +1355,16 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
   }
 #undef SCP_SELECT
 #undef SCP_SELECT_LAUNCH
-  // ---- sweep 2 (column sums) -- skipped when the caller does not want prob_perplexity
-  if (avg_probs) {
+  // ---- column sums -- skipped when the caller does not want prob_perplexity
+  if (avg_probs && ws.e16) {
+    vq_colsum_kernel<<<(unsigned)(Vp / kColsumCols), 256, 0, s>>>(ws.e16, Vp, ws.lse1_l2, M, (int)V, 1.0f / (float)M, mc,
+                                                                 avg_probs);
+    if (cudaGetLastError() != cudaSuccess) {
+      if (forked) join_from_side(s);  // never leave the helper stream un-joined (stream capture would be invalidated)
+      return fail(SCP_ERR_CUDA, "vq_colsum launch failed");
+    }
+    count_launch();
+  } else if (avg_probs) {  // two-sweep mode (SCP_VQ_COLSUM=0)
     const int64_t Mp2 = round_up(M, 256);
     GemmMaps maps{};
     if ((rc = tc::make_tmap_f16(&maps.x[0], table_hat, Vp, D, D, tc::kTileM))) return rc;
@@ -1374,7 +1503,7 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
   return SCP_OK;
 }
 
-extern "C" size_t scp_vq_dense_workspace_bytes(int64_t, int64_t) { return (size_t)(kMetricBlocks * 2 + 1) * 4; }
+extern "C" size_t scp_vq_dense_workspace_bytes(int64_t, int64_t) { return (size_t)(kMetricBlocks * 3 + 1) * 4; }
 
 extern "C" int scp_vq_dense_fwd(float* x, int64_t M, int64_t K, int64_t V, int64_t ldx, const int32_t* masked_cols,
                                 int n_masked, const float* tau, int training, int64_t* idx, float* row_stats,

@@ -31,12 +31,13 @@ g = lambda *names: int(sum(v for k, v in per.items() if any(n in k for n in name
 json.dump({"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch (bytes) from the ncu --set full capture of `python bench.py "
            "--steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-breakdown --no-graph` (profiles/%s_ncu_full_hot_kernels.csv, "
            "tools/profile_round.sh); keyed like bench.py's kernel groups (group = sum of its kernels)" % tag,
-           "wsum_fwd": g('wsum_fwd'), "wsum_bwd": g('wsum_bwd'), "vq_fwd": g('Sweep1', 'Sweep2', 'vq_select'),
+           "wsum_fwd": g('wsum_fwd'), "wsum_bwd": g('wsum_bwd'), "vq_fwd": g('Sweep1', 'Sweep2', 'vq_select', 'vq_colsum'),
            "vq_bwd": g('Sweep3', 'StoreEpi<2>'), "nce_fwd_bwd": g('Nce')}, open(f"{pr}/traffic.json", "w"), indent=2)
 shutil.copy(f"{go}/{tag}_bench.json", f"{pr}/{tag}_bench.json")
 shutil.copy(f"{go}/{tag}_launches.csv", f"{pr}/{tag}_launches_bench_steps2.csv")
-if os.path.exists(f"{go}/{tag}_aux_kernels.json"):
-    shutil.copy(f"{go}/{tag}_aux_kernels.json", f"{pr}/{tag}_aux_kernels.json")
+for extra in ("aux_kernels", "config_kernels"):
+    if os.path.exists(f"{go}/{tag}_{extra}.json"):
+        shutil.copy(f"{go}/{tag}_{extra}.json", f"{pr}/{tag}_{extra}.json")
 d = json.load(open(f"{pr}/{tag}_bench.json"))
 print(d["value"], d["ms_per_step"], d["roofline"]["kernel"], round(d["roofline"]["frac"], 3), d["clocks"]["reasons"])
 for k, v in d["kernels"].items():

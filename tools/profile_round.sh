@@ -14,9 +14,9 @@ python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err ||
 $SHORT > gpurun_out/${tag}_short.json 2> gpurun_out/${tag}_short.err || { echo "short bench failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
     $SHORT > gpurun_out/${tag}_ncu_launches.log 2>&1
-# one instance of each hot kernel, taken from the last (5th) step: 11 matching kernels per step (vq_select runs twice), skip the first 4 steps
+# one instance of each hot kernel, taken from the last (5th) step: 11 matching kernels per step (vq_select runs twice, vq_colsum once), skip the first 4 steps
 ncu --set full --import-source on --clock-control none \
-    -k regex:'wsum_fwd|wsum_bwd_plain|stream_gemm|vq_select' -s 44 -c 11 -f -o gpurun_out/${tag}_full \
+    -k regex:'wsum_fwd|wsum_bwd_plain|stream_gemm|vq_select|vq_colsum' -s 44 -c 11 -f -o gpurun_out/${tag}_full \
     $SHORT > gpurun_out/${tag}_ncu_full.log 2>&1
 ncu -i gpurun_out/${tag}_full.ncu-rep --page raw --csv > gpurun_out/${tag}_full_raw.csv 2>/dev/null
 # kernels outside the bench step (S1' variants, N1 / N3 / N4): device times and achieved bandwidth
