@@ -168,7 +168,7 @@ def run_reference_arm(args):
                 data="synthetic", impl="reference", config=dict(WORKLOAD, cpu_sample_pairs=batch),
                 cpu_baseline=cb, e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 # =====================================================================================================================
@@ -472,9 +472,9 @@ def run_gpu_arm(args):
     line = None
     if rank == 0 and args.no_breakdown:
         clocks = sampler.stop()
-        print(json.dumps(dict(metric=METRIC, value=pairs_per_s, unit=UNIT, n_gpus=world, steps=args.steps,
-                              ms_per_step=ms / args.steps, gpu_launches=int(launches), clocks=clocks,
-                              note="profiling run: no roofline / e2e legs")), flush=True)
+        emit_json(dict(metric=METRIC, value=pairs_per_s, unit=UNIT, n_gpus=world, steps=args.steps,
+                       ms_per_step=ms / args.steps, gpu_launches=int(launches), clocks=clocks,
+                       note="profiling run: no roofline / e2e legs"))
     elif rank == 0:
         kb = kernel_breakdown(hp)
         clocks = sampler.stop()
@@ -505,7 +505,7 @@ def run_gpu_arm(args):
                                          "fp64 arg-max re-scoring; InfoNCE split-fp16 (hi/lo) operands"),
                     roofline=roofline, kernels=kernels, cpu_baseline=cpu_baseline, e2e=e2e,
                     gpu_launches=int(launches), clocks=clocks)
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if world > 1:
         # NCCL communicators that were captured into CUDA graphs do not tear down cleanly (destroy_process_group
         # dead-locks); nothing after this point needs the group, so leave without running the destructors.
@@ -516,7 +516,31 @@ def run_gpu_arm(args):
     return line
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries print there at C level (NCCL writes its version banner to fd 1 when
+    the first communicator comes up), so fd 1 is pointed at stderr for the duration of the run and the line goes to a
+    duplicate of the original descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
