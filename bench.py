@@ -495,7 +495,7 @@ def run_gpu_arm(args):
                               bound=v["bound"])
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu_baseline, _ = time_cpu(2, 2, 1)
+            cpu_baseline, _ = time_cpu(2, 8, 1)  # ~10-15 s of CPU work on the box's host cores
         line = dict(metric=METRIC, value=pairs_per_s, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                     data="synthetic", impl="b200",
