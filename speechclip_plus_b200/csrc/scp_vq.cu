@@ -732,7 +732,7 @@ vq_metrics_kernel(const float* __restrict__ code_hist, const float* __restrict__
       // avg_probs is a mean of softmax rows, so its entries sum to one exactly; the column-sum path carries a common
       // factor S = 1 + O(1e-5) (fp16 rounding of e^c against the unrounded normaliser).  The entropy of a/S follows in
       // closed form: -sum (a/S) log(a/S) = (-sum a log a)/S + log S  -- an identity when S = 1.
-      const float pp = avg_probs ? expf(-hp2 / sp2 + logf(sp2)) : nanf("");
+      const float pp = !avg_probs ? nanf("") : (sp2 > 0.f ? expf(-hp2 / sp2 + logf(sp2)) : expf(-hp2));
       metrics[1] = pp;
       metrics[2] = ((float)V - pp) / (float)V;  // diversity_loss, :155-158
       *ticket = 0u;
