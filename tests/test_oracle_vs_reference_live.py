@@ -280,3 +280,46 @@ def test_keyword_splice_live(seed):
     (gk2,) = torch.autograd.grad(out2, [kw2], grad_outputs=gout)
     assert rel_err(gk2, gk) < 1e-6
     assert torch.equal(oracle.keypadding_mask(Kmax, num), du.get_keypadding_mask(Kmax, num))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(N_CASES // 2))
+def test_hybrid_compute_loss_live(refmods, seed):
+    """C0: KWClip_GeneralTransformer.compute_loss (kwClip.py:999-1040) with random objective weights, either or both
+    branches, with and without the CIF quantity loss."""
+    ref.import_avssl()
+    import avssl.model.kwClip as kc
+    g = _gen(600 + seed)
+    N, D = _randint(g, 2, 64), 8 * _randint(g, 1, 16)
+    w_c = [0.0, 1.0, 1.5][_randint(g, 0, 2)]
+    w_p = [1.0, 0.5][_randint(g, 0, 1)] if w_c == 0.0 else [0.0, 1.0, 0.5][_randint(g, 0, 2)]
+    with_quantity = _coin(g)
+    img = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=-1)
+    ca = torch.nn.functional.normalize(torch.randn(N, D, generator=g) + img, dim=-1).requires_grad_(True)
+    pa = torch.nn.functional.normalize(torch.randn(N, D, generator=g) + 2 * img, dim=-1).requires_grad_(True)
+    ids = torch.randint(0, max(N // 3, 1), (N,), generator=g)
+    fake = types.SimpleNamespace()
+    fake.config = types.SimpleNamespace(model_settings=types.SimpleNamespace(cascaded_objective_weight=w_c,
+                                                                             parallel_objective_weight=w_p))
+    refmods.losses.MAX_EYE = 256
+    fake.criterion = refmods.losses.MaskedContrastiveLoss(temperature=0.07, temperature_trainable=True)
+    feats = {"id": ids, "image_feat": img, "cascaded_audio_feat": ca, "parallel_audio_feat": pa}
+    q_w = 0.0
+    if with_quantity:
+        fake.quantity_loss_criteria = torch.nn.L1Loss()
+        fake.quantity_loss_weight = q_w = float(torch.rand(1, generator=g))
+        feats["cif_quantity_out"] = torch.rand(N, generator=g) * 10
+        feats["cif_target_len"] = torch.randint(4, 12, (N,), generator=g).float()
+    out = kc.KWClip_GeneralTransformer.compute_loss(fake, feats)
+    params = [p for p, w in ((ca, w_c), (pa, w_p)) if w > 0] + [fake.criterion.temperature]
+    grads = torch.autograd.grad(out["loss"], params)
+    t = torch.tensor(math.log(1.0 / 0.07), requires_grad=True)
+    ca2, pa2 = ca.detach().clone().requires_grad_(True), pa.detach().clone().requires_grad_(True)
+    feats2 = dict(feats, cascaded_audio_feat=ca2, parallel_audio_feat=pa2)
+    out2 = oracle.hybrid_loss(feats2, t.exp(), w_c, w_p, quantity_loss_weight=q_w)
+    assert set(out2) == set(out), (sorted(out2), sorted(out))
+    for key in out:
+        assert rel_err(out2[key], out[key]) < 2e-5, key
+    params2 = [p for p, w in ((ca2, w_c), (pa2, w_p)) if w > 0] + [t]
+    for a, b in zip(torch.autograd.grad(out2["loss"], params2), grads):
+        assert norm_err(a, b) < 1e-4
