@@ -502,7 +502,8 @@ def run_gpu_arm(args):
                     config=dict(WORKLOAD, global_batch=B * world, parallelism=f"dp{world}",
                                 launch="one CUDA graph per step" if not args.no_graph else "eager launches",
                                 numerics="fp32 I/O; VQ tensor-core operands fp16 with fp32 accumulation and exact "
-                                         "fp64 arg-max re-scoring; InfoNCE split-fp16 (hi/lo) operands"),
+                                         "fp64 arg-max re-scoring, avg_probs reduced from an fp16 e^c scratch; "
+                                         "InfoNCE split-fp16 (hi/lo) operands"),
                     roofline=roofline, kernels=kernels, cpu_baseline=cpu_baseline, e2e=e2e,
                     gpu_launches=int(launches), clocks=clocks)
         emit_json(line)
