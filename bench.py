@@ -3,17 +3,21 @@
     python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...      # the reference algorithm's CPU path (oracle port) on the host cores
+    python bench.py --impl reference ...            # the reference algorithm's CPU path (oracle port) on the host cores
+    python bench.py --workload {c2,c3,c4,c5} --scaling {weak,strong}
 
-Workload (config.workload = "c3_cascaded_plus_base", BASELINE.json configs[2] -- the config the metric is quoted on at
-1/2/4/8 GPUs, and it fits one GPU): per GPU 256 audio-image pairs; one STEP is one pass of the hot path:
-  S1  weighted sum over L=13 HuBERT-base hidden states (256 x 249 x 768 fp32 each, (T,B,D) storage)   fwd + bwd(weights)
-  S2  keyword VQ: M = 256*8 = 2048 keyword rows vs the 49408 x 512 CLIP token table                   fwd + bwd
+Default workload (config.workload = "c3_cascaded_plus_base", BASELINE.json configs[2] -- the config the metric is quoted on
+at 1/2/4/8 GPUs, and it fits one GPU), WEAK scaling: per GPU 256 audio-image pairs; one STEP is one pass of the hot path:
+  S1     weighted sum over L=13 HuBERT-base hidden states (256 x 249 x 768 fp32 each, (T,B,D) storage)   fwd + bwd(weights)
+  S2     keyword VQ: M = 256*8 = 2048 keyword rows vs the 49408 x 512 CLIP token table                   fwd + bwd
   N0/G0  L2-normalise + pack + all-gather of the (256 x 512) audio / image features and ids
-  S3  masked InfoNCE over the gathered global batch N = 256 * n_gpus                                   fwd + bwd
+  S3     masked InfoNCE over the gathered global batch N = 256 * n_gpus (each rank evaluates the denominators of its own
+         rows / columns; one 3 KB all-gather completes the loss)                                          fwd + bwd
+  OPT    packed gradients of the path's trainable tensors (layer weights, temperature) -> all-reduce (SUM) -> fused Adam
 The frozen HuBERT / CLIP towers and the branch transformer are out of scope: their outputs are
-synthetic tensors of the named shapes (seeded), resident in HBM before the timed region.  Scaling is WEAK: per-GPU
-work is fixed, the loss sees the global batch.
+synthetic tensors of the named shapes (seeded), resident in HBM before the timed region.
+The other BASELINE configs (c2 parallel, c3 strong-scaled, c4 hybrid, c5 hybrid large) are measured in the same run at the
+run's GPU count and reported in the `configs` table of the JSON line.
 """
 from __future__ import annotations
 
@@ -21,7 +25,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -29,12 +32,41 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "train pairs/sec (hot path: layer weighted-sum + keyword VQ + masked InfoNCE, fwd+bwd)"
+METRIC = "train pairs/sec (hot path: layer weighted-sum + keyword VQ + masked InfoNCE, fwd+bwd+optimiser)"
 UNIT = "pairs/s"
-WORKLOAD = dict(workload="c3_cascaded_plus_base", per_gpu_batch=256, hubert_layers=13, frames=249, hubert_dim=768,
-                keywords=8, vocab=49408, clip_dim=512, loss="masked InfoNCE, cascaded branch, trainable temperature",
-                vq_temp="fixed=0.1", l2_policy="inputs (2.7 GB/step) exceed the 126 MB L2; no explicit flush")
 SEED = 7122
+
+# BASELINE.json configs[1..4]; batches: `weak` = per-GPU batch held fixed, `strong` = the config's global batch split
+CONFIGS = {
+    "c2": dict(workload="c2_parallel_base", hubert_layers=13, frames=249, hubert_dim=768, keywords=0, vocab=0,
+               clip_dim=512, branches="parallel", cascaded_weight=0.0, parallel_weight=1.0, temperature_trainable=False,
+               weak_batch=256, strong_batch=256),
+    "c3": dict(workload="c3_cascaded_plus_base", hubert_layers=13, frames=249, hubert_dim=768, keywords=8, vocab=49408,
+               clip_dim=512, branches="cascaded", cascaded_weight=1.0, parallel_weight=0.0, temperature_trainable=True,
+               weak_batch=256, strong_batch=256),
+    "c4": dict(workload="c4_hybrid_plus_base", hubert_layers=13, frames=249, hubert_dim=768, keywords=8, vocab=49408,
+               clip_dim=512, branches="cascaded+parallel", cascaded_weight=1.0, parallel_weight=1.0,
+               temperature_trainable=True, weak_batch=128, strong_batch=1024),
+    "c5": dict(workload="c5_hybrid_plus_large", hubert_layers=25, frames=249, hubert_dim=1024, keywords=8, vocab=49408,
+               clip_dim=768, branches="cascaded+parallel", cascaded_weight=1.5, parallel_weight=0.5,
+               temperature_trainable=True, weak_batch=64, strong_batch=512),
+}
+
+
+def per_gpu_batch(cfg: dict, scaling: str, world: int) -> int:
+    return cfg["weak_batch"] if scaling == "weak" else max(1, cfg["strong_batch"] // world)
+
+
+def make_config(name: str, scaling: str, world: int, graph: bool = True) -> dict:
+    """The `config` object of the JSON line -- identical for the b200 and the reference arm."""
+    cfg = CONFIGS[name]
+    B = per_gpu_batch(cfg, scaling, world)
+    out = {k: v for k, v in cfg.items() if k not in ("weak_batch", "strong_batch")}
+    out.update(per_gpu_batch=B, global_batch=B * world, parallelism=f"dp{world}", scaling=scaling,
+               loss="masked InfoNCE" + (", trainable temperature" if cfg["temperature_trainable"] else ", fixed temperature"),
+               vq_temp="fixed=0.1", optimiser="Adam lr 1e-4 weight_decay 1e-6 on the path's trainable tensors",
+               l2_policy="inputs per step exceed the 126 MB L2 (S1 streams >= 0.6 GB); no explicit flush")
+    return out
 
 
 def load_peaks():
@@ -113,97 +145,176 @@ class ClockSampler:
 # =====================================================================================================================
 # CPU arm: the reference algorithm (oracle port) on the host cores
 # =====================================================================================================================
-def cpu_hot_path_step(state):
+def cpu_hot_path_step(state, fair: bool = False):
     """One pass of the same hot path with the oracle (plain torch CPU ops, structured like the reference, incl. the
-    per-keyword cosine loop of kw_branches.py:167-177)."""
+    per-keyword cosine loop of kw_branches.py:167-177; `fair`: the same maths as normalise + one GEMM)."""
     import torch
     from oracle import speechclip_oracle as oracle
-    layers, w, gy, kw, table, img, ids, logt = (state[k] for k in ("layers", "w", "gy", "kw", "table", "img", "ids", "logt"))
-    y = oracle.wsum_forward(layers, w)
-    (dw,) = torch.autograd.grad(y, [w], grad_outputs=gy)
-    vq, kws = oracle.vq_audio_features(kw, table, torch.tensor([0.1]), training=True, faithful_loop=True)
-    feat = oracle.l2_normalise(kws.mean(dim=1))
-    loss = oracle.nce_forward(feat, oracle.l2_normalise(img), ids, logt.exp())
-    g_kw, g_t = torch.autograd.grad(loss, [kw, logt])
-    return float(loss.detach())
+    cfg = state["cfg"]
+    y = oracle.wsum_forward(state["layers"], state["w"])
+    (dw,) = torch.autograd.grad(y, [state["w"]], grad_outputs=state["gy"])
+    feats = {"id": state["ids"], "image_feat": oracle.l2_normalise(state["img"])}
+    wrt = [state["logt"]] if cfg["temperature_trainable"] else []
+    if cfg["keywords"]:
+        vq, kws = oracle.vq_audio_features(state["kw"], state["table"], torch.tensor([0.1]), training=True,
+                                           faithful_loop=not fair)
+        feats["cascaded_audio_feat"] = oracle.l2_normalise(kws.mean(dim=1))
+        wrt.append(state["kw"])
+    if "parallel" in cfg["branches"]:
+        feats["parallel_audio_feat"] = oracle.l2_normalise(state["par"])
+        wrt.append(state["par"])
+    out = oracle.hybrid_loss(feats, state["logt"].exp(), cfg["cascaded_weight"], cfg["parallel_weight"])
+    torch.autograd.grad(out["loss"], wrt)
+    return float(out["loss"].detach())
 
 
-def make_cpu_state(batch: int):
+def make_cpu_state(cfg: dict, batch: int):
     import math
     import torch
     g = torch.Generator().manual_seed(SEED)
-    L, T, Da, K, V, D = (WORKLOAD[k] for k in ("hubert_layers", "frames", "hubert_dim", "keywords", "vocab", "clip_dim"))
+    L, T, Da, K, V, D = (cfg[k] for k in ("hubert_layers", "frames", "hubert_dim", "keywords", "vocab", "clip_dim"))
     storage = [torch.randn(T, batch, Da, generator=g) for _ in range(L)]
-    return dict(layers=[s.transpose(0, 1) for s in storage], w=(torch.randn(L, generator=g) * 0.5).requires_grad_(True),
-                gy=torch.randn(batch, T, Da, generator=g), table=torch.randn(V, D, generator=g) * 0.02,
-                kw=(torch.randn(batch, K, D, generator=g) * 0.02).requires_grad_(True),
-                img=torch.randn(batch, D, generator=g), ids=torch.arange(batch),
-                logt=torch.tensor(math.log(1 / 0.07), requires_grad=True))
+    st = dict(cfg=cfg, layers=[s.transpose(0, 1) for s in storage], w=(torch.randn(L, generator=g) * 0.5).requires_grad_(True),
+              gy=torch.randn(batch, T, Da, generator=g), img=torch.randn(batch, D, generator=g), ids=torch.arange(batch),
+              logt=torch.tensor(math.log(1 / 0.07), requires_grad=True))
+    if K:
+        st["table"] = torch.randn(V, D, generator=g) * 0.02
+        st["kw"] = (torch.randn(batch, K, D, generator=g) * 0.02).requires_grad_(True)
+    if "parallel" in cfg["branches"]:
+        st["par"] = torch.randn(batch, D, generator=g).requires_grad_(True)
+    return st
 
 
-def time_cpu(batch: int, steps: int, warmup: int):
+def time_cpu(cfg: dict, batch: int, steps: int, warmup: int, fair: bool = False):
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    state = make_cpu_state(batch)
+    state = make_cpu_state(cfg, batch)
     for _ in range(warmup):
-        cpu_hot_path_step(state)
+        cpu_hot_path_step(state, fair)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_hot_path_step(state)
+        cpu_hot_path_step(state, fair)
     dt = (time.perf_counter() - t0) / max(steps, 1)
+    how = ("normalise + one GEMM restatement of the cosine scores ('fair CPU', BASELINE.md section 4)" if fair else
+           "per-keyword cosine loop as in the reference (kw_branches.py:167-177)")
     return dict(value=batch / dt, unit=UNIT, cores=cores, kind="port",
-                sample=f"same hot-path step on a {batch}-pair slice of the workload (full 49408x512 table, per-keyword "
-                       f"cosine loop as in the reference), {steps} timed step(s), {dt:.2f} s/step, torch CPU fp32"), dt
+                sample=f"same hot-path step on a {batch}-pair slice of the workload (full token table, {how}), "
+                       f"{steps} timed step(s), {dt:.2f} s/step, torch CPU fp32"), dt
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 2 if args.steps + args.warmup <= 30 else 1  # bounded sample: ~3-6 s of CPU work per step
-    cb, dt = time_cpu(batch, args.steps, max(args.warmup, 1))
+    cfg = CONFIGS[args.workload]
+    batch = 2 if args.steps + args.warmup <= 30 else 1  # bounded sample: ~1-3 s of CPU work per step
+    if not cfg["keywords"]:
+        batch = 32
+    cb, dt = time_cpu(cfg, batch, args.steps, max(args.warmup, 1))
+    fair, _ = time_cpu(cfg, 16, 3, 1, fair=True) if cfg["keywords"] else (None, None)
     line = dict(metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                data="synthetic", impl="reference", config=dict(WORKLOAD, cpu_sample_pairs=batch),
-                cpu_baseline=cb, e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                gpu_launches=0)
+                ms_per_step=dt * 1e3, higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference", config=make_config(args.workload, args.scaling, args.gpus),
+                cpu_baseline=cb, cpu_baseline_fair=fair,
+                e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     emit_json(line)
 
 
 # =====================================================================================================================
 # GPU arm
 # =====================================================================================================================
+def make_inputs(cfg: dict, B: int, dev, seed: int, layer_dtype=None):
+    """Synthetic tower outputs of one rank (seeded: rank r of any world size draws the same numbers)."""
+    import torch
+    g = torch.Generator(device=dev).manual_seed(seed)
+    L, T, Da, K, V, D = (cfg[k] for k in ("hubert_layers", "frames", "hubert_dim", "keywords", "vocab", "clip_dim"))
+    # HuBERT hands over L tensors of (T,B,D) storage viewed as (B,T,D) (speech_encoder_plus.py:596-599)
+    inp = dict(storage=[torch.randn(T, B, Da, device=dev, generator=g) for _ in range(L)],
+               grad_y=torch.randn(B, T, Da, device=dev, generator=g))
+    if layer_dtype is not None:
+        inp["storage"] = [s.to(layer_dtype) for s in inp["storage"]]
+    if K:
+        inp["kw"] = torch.randn(B, K, D, device=dev, generator=g) * 0.02
+    if "parallel" in cfg["branches"]:
+        inp["par"] = torch.randn(B, D, device=dev, generator=g)
+    inp["img"] = torch.randn(B, D, device=dev, generator=g)
+    inp["ids"] = torch.randint(0, 6000, (B,), device=dev, generator=g)  # Flickr8k: 6000 training images x 5 captions
+    return inp
+
+
+def concat_inputs(parts):
+    import torch
+    out = dict(storage=[torch.cat([p["storage"][l] for p in parts], dim=1) for l in range(len(parts[0]["storage"]))],
+               grad_y=torch.cat([p["grad_y"] for p in parts], dim=0))
+    for k in ("kw", "par", "img", "ids"):
+        if k in parts[0]:
+            out[k] = torch.cat([p[k] for p in parts], dim=0)
+    return out
+
+
 class HotPath:
     """Device-resident state + one step of the hot path through the public modules."""
 
-    def __init__(self, dev, rank, world, group=None):
-        import math
+    def __init__(self, cfg: dict, inputs: dict, dev, rank: int, world: int, group=None, distributed: bool = True):
         import torch
         import speechclip_plus_b200 as scp
         self.torch, self.scp, self.dev, self.rank, self.world, self.group = torch, scp, dev, rank, world, group
-        w = WORKLOAD
-        self.B, self.L, self.T, self.Da = w["per_gpu_batch"], w["hubert_layers"], w["frames"], w["hubert_dim"]
-        self.K, self.V, self.D = w["keywords"], w["vocab"], w["clip_dim"]
-        g = torch.Generator(device=dev).manual_seed(SEED + rank)
-        B, L, T, Da, K, V, D = self.B, self.L, self.T, self.Da, self.K, self.V, self.D
-        # HuBERT hands over L tensors of (T,B,D) storage viewed as (B,T,D) (speech_encoder_plus.py:596-599)
-        self.storage = [torch.randn(T, B, Da, device=dev, generator=g) for _ in range(L)]
+        self.cfg = cfg
+        self.distributed = distributed and world > 1
+        self.L, self.T, self.Da = cfg["hubert_layers"], cfg["frames"], cfg["hubert_dim"]
+        self.K, self.V, self.D = cfg["keywords"], cfg["vocab"], cfg["clip_dim"]
+        self.storage = inputs["storage"]
         self.layers = [s.transpose(0, 1) for s in self.storage]
-        self.grad_y = torch.randn(B, T, Da, device=dev, generator=g)
-        gt = torch.Generator(device=dev).manual_seed(SEED)  # the frozen table is identical on every rank
-        self.table = torch.randn(V, D, device=dev, generator=gt) * 0.02
-        self.kw = (torch.randn(B, K, D, device=dev, generator=g) * 0.02).requires_grad_(True)
-        self.img = torch.randn(B, D, device=dev, generator=g)
-        self.ids = torch.randint(0, 6000, (B,), device=dev, generator=g)  # Flickr8k: 6000 training images x 5 captions
-        self.wsum = scp.WeightedSumLayer(L).to(dev)
+        self.B = self.layers[0].shape[0]
+        self.grad_y = inputs["grad_y"]
+        self.img, self.ids = inputs["img"], inputs["ids"]
+        self.kw = inputs["kw"].clone().requires_grad_(True) if "kw" in inputs else None
+        self.par = inputs["par"].clone().requires_grad_(True) if "par" in inputs else None
+        self.table = None
+        if self.K:
+            gt = torch.Generator(device=dev).manual_seed(SEED)  # the frozen table is identical on every rank
+            self.table = torch.randn(self.V, self.D, device=dev, generator=gt) * 0.02
+        self.wsum = scp.WeightedSumLayer(self.L).to(dev)
         with torch.no_grad():
-            self.wsum.weights.copy_(torch.linspace(-0.5, 0.5, L))
-        self.vq = scp.SimpleVectorQuantizer(w["vq_temp"]).to(dev).train()
-        self.crit = scp.MaskedContrastiveLoss(temperature=0.07, temperature_trainable=True).to(dev)
-        self.params = [self.wsum.weights, self.crit.temperature, self.kw]
+            self.wsum.weights.copy_(torch.linspace(-0.5, 0.5, self.L))
+        self.vq = scp.SimpleVectorQuantizer("fixed=0.1").to(dev).train() if self.K else None
+        self.crit = scp.MaskedContrastiveLoss(temperature=0.07, temperature_trainable=cfg["temperature_trainable"]).to(dev)
+        self.params = [self.wsum.weights] + ([self.crit.temperature] if cfg["temperature_trainable"] else [])
+        self.acts = [t for t in (self.kw, self.par) if t is not None]
+        # the reference's single Adam group (kwClip.py:636-668; yaml audio_encoder.optim)
+        self.opt = scp.PackedAdam(self.params, lr=1e-4, weight_decay=1e-6, group=group, all_reduce=self.distributed)
         self.graph = None
         self.run_step = self.step
+        self.apply_optimizer = True
+
+    def loss_and_grads(self):
+        torch, scp, cfg = self.torch, self.scp, self.cfg
+        for p in self.params + self.acts:
+            p.grad = None
+        y = self.wsum(self.layers)                                                      # S1 fwd
+        feats = {"id": self.ids, "image_feat": self.img}
+        res = None
+        if self.K:
+            res, kws = self.vq.quantize_keywords(self.kw, self.table)                   # V1+V3+V4 fwd
+            feats["cascaded_audio_feat"] = kws.mean(dim=1)
+        if self.par is not None:
+            feats["parallel_audio_feat"] = self.par
+        if self.distributed:
+            gathered, rows = scp.gather_loss_feats(feats, self.group)                   # N0 + G0 (NCCL all-gather)
+            out = scp.compute_loss(gathered, self.crit, cfg["cascaded_weight"], cfg["parallel_weight"], local_rows=rows,
+                                   group=self.group)                                    # S3 fwd (sharded)
+        else:
+            gathered, _ = scp.gather_loss_feats(feats, None)
+            out = scp.compute_loss(gathered, self.crit, cfg["cascaded_weight"], cfg["parallel_weight"])
+        torch.autograd.backward([out["loss"], y], [None, self.grad_y])                 # S3 bwd, V bwd, S1 bwd
+        return out["loss"].detach(), res
+
+    def step(self):
+        loss, res = self.loss_and_grads()
+        if self.apply_optimizer:
+            self.opt.step()                                                             # pack -> all-reduce -> Adam
+        return loss, res
 
     def capture(self):
         """Capture one step into a CUDA graph (the launch-bound tail of the step -- ~25 sub-10us kernels of the loss
@@ -222,40 +333,30 @@ class HotPath:
         with torch.cuda.graph(self.graph):
             self.static_loss, _ = self.step()
         self.launches_per_step = _lib.num_launches() - l0  # kernels of libscp_b200.so recorded in the graph
-        self.static_grads = [p.grad for p in self.params]
+        self.static_grads = {"weights": self.wsum.weights.grad, "kw": self.kw.grad if self.kw is not None else None,
+                             "par": self.par.grad if self.par is not None else None}
+        self.run_step = self.step_graph
         return self.graph
 
     def step_graph(self):
         self.graph.replay()
         return self.static_loss, None
 
-    def step(self):
-        torch, scp = self.torch, self.scp
-        for p in self.params:
-            p.grad = None
-        y = self.wsum(self.layers)                                             # S1 fwd
-        res, kws = self.vq.quantize_keywords(self.kw, self.table)              # V1+V3+V4 fwd
-        feats = {"id": self.ids, "image_feat": self.img, "cascaded_audio_feat": kws.mean(dim=1)}
-        gathered, rows = scp.gather_loss_feats(feats, self.group)              # N0 + G0 (NCCL all-gather when world > 1)
-        out = scp.compute_loss(gathered, self.crit, cascaded_objective_weight=1.0, local_rows=rows)   # S3 fwd
-        loss = out["loss"] * scp.ddp_grad_scale(self.world)
-        torch.autograd.backward([loss, y], [None, self.grad_y])               # S3 bwd, V bwd, S1 bwd
-        return out["loss"].detach(), res
-
     # ---- host-buffer variant for the end-to-end number ----------------------------------------------------------
     def make_host_buffers(self):
         torch = self.torch
         self.h_storage = [s.cpu().pin_memory() for s in self.storage]
         self.h_grad_y = self.grad_y.cpu().pin_memory()
-        self.h_kw = self.kw.detach().cpu().pin_memory()
+        self.h_acts = [a.detach().cpu().pin_memory() for a in self.acts]
         self.h_img = self.img.cpu().pin_memory()
         self.h_ids = self.ids.cpu().pin_memory()
         self.h_loss = torch.empty((), dtype=torch.float32).pin_memory()
         self.h_dw = torch.empty(self.L, dtype=torch.float32).pin_memory()
-        self.h_gkw = torch.empty_like(self.h_kw).pin_memory()
-        self.h2d_bytes = (sum(t.numel() * t.element_size() for t in self.h_storage) + self.h_grad_y.numel() * 4 +
-                          self.h_kw.numel() * 4 + self.h_img.numel() * 4 + self.h_ids.numel() * 8)
-        self.d2h_bytes = 4 + self.h_dw.numel() * 4 + self.h_gkw.numel() * 4
+        self.h_gacts = [torch.empty_like(a).pin_memory() for a in self.h_acts]
+        nbytes = lambda t: t.numel() * t.element_size()  # noqa: E731
+        self.h2d_bytes = (sum(nbytes(t) for t in self.h_storage) + nbytes(self.h_grad_y) + sum(nbytes(t) for t in self.h_acts) +
+                          nbytes(self.h_img) + nbytes(self.h_ids))
+        self.d2h_bytes = 4 + nbytes(self.h_dw) + sum(nbytes(t) for t in self.h_gacts)
 
     def upload(self, host: "HotPath"):
         """H2D of one step's inputs from the pinned host buffers of `host` into THIS object's device tensors."""
@@ -264,19 +365,20 @@ class HotPath:
             d.copy_(h, non_blocking=True)
         self.grad_y.copy_(host.h_grad_y, non_blocking=True)
         with torch.no_grad():
-            self.kw.copy_(host.h_kw, non_blocking=True)
+            for a, h in zip(self.acts, host.h_acts):
+                a.copy_(h, non_blocking=True)
         self.img.copy_(host.h_img, non_blocking=True)
         self.ids.copy_(host.h_ids, non_blocking=True)
 
     def compute_and_download(self, host: "HotPath"):
         loss, _ = self.run_step()
         host.h_loss.copy_(loss, non_blocking=True)
-        host.h_dw.copy_(self.wsum.weights.grad if self.graph is None else self.static_grads[0], non_blocking=True)
-        host.h_gkw.copy_(self.kw.grad if self.graph is None else self.static_grads[2], non_blocking=True)
-
-    def step_e2e(self):
-        self.upload(self)
-        self.compute_and_download(self)
+        graphed = self.graph is not None
+        host.h_dw.copy_(self.static_grads["weights"] if graphed else self.wsum.weights.grad, non_blocking=True)
+        grads = [self.static_grads[k] for k in ("kw", "par") if self.static_grads.get(k) is not None] if graphed else \
+            [a.grad for a in self.acts]
+        for h, g in zip(host.h_gacts, grads):
+            h.copy_(g, non_blocking=True)
 
 
 def run_e2e_pipelined(torch, hps, steps):
@@ -326,8 +428,42 @@ def time_region(torch, dist_mod, world, fn, steps):
     return ms
 
 
-def kernel_breakdown(hp: "HotPath", iters: int = 10):
-    """Per-API-call device time (CUDA events around the C-ABI calls, after warm-up) and achieved roofline numbers."""
+class GraphTimer:
+    """Device time of a kernel group as a CUDA-graph replay (no Python launch gaps, exactly what the step's graph runs),
+    median over `iters` replays, each preceded by a write of a buffer larger than the L2 so that no group inherits its
+    operands from the previous replay."""
+
+    def __init__(self, torch, dev):
+        self.torch = torch
+        self.flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 192 MB > 126 MB L2
+
+    def time(self, fn, iters: int = 7):
+        torch = self.torch
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                fn()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        g.replay()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        for a, b in evs:
+            self.flush.zero_()
+            a.record()
+            g.replay()
+            b.record()
+        torch.cuda.synchronize()
+        return statistics.median(a.elapsed_time(b) for a, b in evs) * 1e-3  # seconds
+
+
+def kernel_breakdown(hp: "HotPath", timer: GraphTimer):
+    """Device time of every kernel group of the step (graph replays, cold L2) and achieved roofline numbers.
+    Runs identically on every rank (the loss group contains the collectives); rank 0 reports."""
     import ctypes
     torch = hp.torch
     from speechclip_plus_b200 import _lib
@@ -335,66 +471,187 @@ def kernel_breakdown(hp: "HotPath", iters: int = 10):
     dev = hp.dev
     B, L, T, Da, K, V, D = hp.B, hp.L, hp.T, hp.Da, hp.K, hp.V, hp.D
     M = B * K
-    stream = _lib.stream_ptr(dev)
-
-    def timed(fn):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
-        for a, b in evs:
-            a.record()
-            fn()
-            b.record()
-        torch.cuda.synchronize()
-        return statistics.median(a.elapsed_time(b) for a, b in evs) * 1e-3  # seconds
-
     out = {}
-    # S1 forward / backward
-    w = hp.wsum.weights.detach()
+    # S1 forward / backward (C-ABI calls)
+    w = hp.wsum.weights.detach().clone()
     y = torch.empty((B, T, Da), device=dev)
     ptrs = _lib.ptr_array(hp.layers)
     v0 = hp.layers[0]
-    t = timed(lambda: lib.scp_wsum_fwd(ptrs, L, B, T, Da, v0.stride(0), v0.stride(1), 0, _lib.ptr(w), 0, 1e-5,
-                                       None, _lib.ptr(y), 0, stream))
-    by = (L + 1) * B * T * Da * 4
+    esz = v0.element_size()
+    dt_code = _lib.dtype_code(v0.dtype)
+
+    def s1_fwd():
+        lib.scp_wsum_fwd(ptrs, L, B, T, Da, v0.stride(0), v0.stride(1), dt_code, _lib.ptr(w), 0, 1e-5, None, _lib.ptr(y), 0,
+                         _lib.stream_ptr(dev))
+    t = timer.time(s1_fwd)
+    by = L * B * T * Da * esz + B * T * Da * 4
     out["wsum_fwd"] = dict(seconds=t, bound="hbm", algorithmic=by, achieved=by / t / 1e9, unit="GB/s")
     dw = torch.empty(L, device=dev)
     ws_b = lib.scp_wsum_bwd_workspace_bytes(L, B, T, Da)
     ws = torch.empty(ws_b, dtype=torch.uint8, device=dev)
     null_pp = ctypes.cast(None, ctypes.POINTER(ctypes.c_void_p))
-    t = timed(lambda: lib.scp_wsum_bwd(ptrs, L, B, T, Da, v0.stride(0), v0.stride(1), 0, _lib.ptr(w), 0, 1e-5,
-                                       None, _lib.ptr(hp.grad_y), 0, _lib.ptr(dw), null_pp, _lib.ptr(ws), ws_b, stream))
+
+    def s1_bwd():
+        lib.scp_wsum_bwd(ptrs, L, B, T, Da, v0.stride(0), v0.stride(1), dt_code, _lib.ptr(w), 0, 1e-5, None,
+                         _lib.ptr(hp.grad_y), 0, _lib.ptr(dw), null_pp, _lib.ptr(ws), ws_b, _lib.stream_ptr(dev))
+    t = timer.time(s1_bwd)
     out["wsum_bwd"] = dict(seconds=t, bound="hbm", algorithmic=by, achieved=by / t / 1e9, unit="GB/s")
     # S2 forward / backward through the module (includes its small helper kernels)
-    kw = hp.kw.detach().clone().requires_grad_(True)
-    state = {}
+    if K:
+        kw = hp.kw.detach().clone().requires_grad_(True)
+        g = torch.randn(B, K, D, device=dev)
+        state = {}
 
-    def vq_f():
-        state["res"], state["out"] = hp.vq.quantize_keywords(kw, hp.table)
-    t = timed(vq_f)
-    fl = 2.0 * M * V * D
-    out["vq_fwd"] = dict(seconds=t, bound="tensor", algorithmic=fl, achieved=fl / t / 1e12, unit="TFLOP/s")
-    g = torch.randn(B, K, D, device=dev)
+        def vq_f():
+            state["res"], state["out"] = hp.vq.quantize_keywords(kw, hp.table)
 
-    def vq_fb():
-        vq_f()
-        torch.autograd.grad(state["out"], [kw], grad_outputs=g)
-    t2 = timed(vq_fb) - t
-    fl = 6.0 * M * V * D
-    out["vq_bwd"] = dict(seconds=t2, bound="tensor", algorithmic=fl, achieved=fl / t2 / 1e12, unit="TFLOP/s")
-    # S3 forward + backward
-    N = B
-    a = torch.nn.functional.normalize(torch.randn(N, D, device=dev), dim=-1).requires_grad_(True)
-    b = torch.nn.functional.normalize(torch.randn(N, D, device=dev), dim=-1)
+        def vq_fb():
+            vq_f()
+            torch.autograd.grad(state["out"], [kw], grad_outputs=g)
+        t = timer.time(vq_f)
+        fl = 2.0 * M * V * D
+        out["vq_fwd"] = dict(seconds=t, bound="tensor", algorithmic=fl, achieved=fl / t / 1e12, unit="TFLOP/s")
+        t2 = timer.time(vq_fb) - t
+        fl = 6.0 * M * V * D
+        out["vq_bwd"] = dict(seconds=t2, bound="tensor", algorithmic=fl, achieved=fl / t2 / 1e12, unit="TFLOP/s")
+    # N0 + G0 + S3 forward + backward (+ the collectives at N > 1) through the public functions
+    scp = hp.scp
+    N = B * hp.world
+    n_calls = (1 if hp.cfg["cascaded_weight"] > 0 else 0) + (1 if hp.cfg["parallel_weight"] > 0 else 0)
+    fa = {k: torch.randn(B, D, device=dev).requires_grad_(True) for k in ("cascaded_audio_feat", "parallel_audio_feat")}
+    wrt = [fa[k] for k in fa] + ([hp.crit.temperature] if hp.cfg["temperature_trainable"] else [])
 
     def nce_fb():
-        loss = hp.crit(a, b, hp.ids)
-        torch.autograd.grad(loss, [a, hp.crit.temperature])
-    t = timed(nce_fb)
-    fl = 2.0 * N * N * D + 4.0 * N * N * D
+        feats = {"id": hp.ids, "image_feat": hp.img}
+        if hp.cfg["cascaded_weight"] > 0:
+            feats["cascaded_audio_feat"] = fa["cascaded_audio_feat"]
+        if hp.cfg["parallel_weight"] > 0:
+            feats["parallel_audio_feat"] = fa["parallel_audio_feat"]
+        if hp.distributed:
+            gathered, rows = scp.gather_loss_feats(feats, hp.group)
+            o = scp.compute_loss(gathered, hp.crit, hp.cfg["cascaded_weight"], hp.cfg["parallel_weight"], local_rows=rows,
+                                 group=hp.group)
+        else:
+            gathered, _ = scp.gather_loss_feats(feats, None)
+            o = scp.compute_loss(gathered, hp.crit, hp.cfg["cascaded_weight"], hp.cfg["parallel_weight"])
+        torch.autograd.grad(o["loss"], wrt, allow_unused=True)
+    t = timer.time(nce_fb)
+    fl = n_calls * (2.0 * N * N * D + 4.0 * N * N * D)
     out["nce_fwd_bwd"] = dict(seconds=t, bound="tensor (launch/latency-bound in practice)", algorithmic=fl,
-                              achieved=fl / t / 1e12, unit="TFLOP/s")
+                              achieved=fl / t / 1e12, unit="TFLOP/s",
+                              note=f"{n_calls} criterion call(s) over N={N} incl. normalise/pack/gather" +
+                                   (" and the NCCL collectives" if hp.distributed else ""))
+    # packed gradients -> all-reduce -> Adam
+    grads = [torch.randn_like(p) for p in hp.params]
+    t = timer.time(lambda: hp.opt.step(grads))
+    out["optimiser"] = dict(seconds=t, bound="latency", algorithmic=0.0, achieved=0.0, unit="-")
+    return out
+
+
+def summarize_kernels(kb: dict, peaks: dict) -> dict:
+    kernels = {}
+    for k, v in kb.items():
+        if v["bound"] == "hbm":
+            pk = peaks["hbm_gbs"]
+        elif v["bound"].startswith("tensor"):
+            pk = peaks["tflops_burst"]
+        else:
+            pk = None
+        kernels[k] = dict(ms=v["seconds"] * 1e3, achieved=v["achieved"], unit=v["unit"],
+                          frac=(v["achieved"] / pk) if pk else None, bound=v["bound"])
+        if "note" in v:
+            kernels[k]["note"] = v["note"]
+    return kernels
+
+
+def multi_gpu_check(torch, dist, cfg, B, dev, rank, world):
+    """N-rank step vs a single-process step on the concatenated batch (rank 0 rebuilds every rank's seeded inputs):
+    loss, the all-reduced gradients of the trainable tensors and the gathered activation gradients.  kwClip.py:149-193."""
+    inputs = make_inputs(cfg, B, dev, SEED + rank)
+    hp = HotPath(cfg, inputs, dev, rank, world)
+    hp.apply_optimizer = False
+    loss, _ = hp.loss_and_grads()
+    hp.opt.pack_grads()
+    dist.all_reduce(hp.opt.packed, op=dist.ReduceOp.SUM)
+    summed = [g.clone() for g in hp.opt.unpacked_grads()]
+    gathered_acts = []
+    for a in hp.acts:
+        buf = torch.empty((world * a.shape[0],) + tuple(a.shape[1:]), device=dev)
+        dist.all_gather_into_tensor(buf, a.grad.contiguous())
+        gathered_acts.append(buf)
+    result = None
+    if rank == 0:
+        parts = [make_inputs(cfg, B, dev, SEED + r) for r in range(world)]
+        ref = HotPath(cfg, concat_inputs(parts), dev, 0, 1, distributed=False)
+        del parts
+        ref.apply_optimizer = False
+        ref_loss, _ = ref.loss_and_grads()
+
+        def rel(a, b):
+            a, b = a.double().flatten(), b.double().flatten()
+            return float((a - b).norm() / b.norm().clamp_min(1e-30))
+        result = dict(world=world, global_batch=B * world, loss=float(loss), loss_single_process=float(ref_loss),
+                      loss_rel_err=abs(float(loss) - float(ref_loss)) / max(abs(float(ref_loss)), 1e-30),
+                      d_weights_rel_err=rel(summed[0], ref.wsum.weights.grad))
+        if cfg["temperature_trainable"]:
+            result["d_log_scale_rel_err"] = rel(summed[1], ref.crit.temperature.grad)
+        for name, got, want in zip(["g_kw_rel_err", "g_par_rel_err"] if hp.kw is not None else ["g_par_rel_err"],
+                                   gathered_acts, ref.acts):
+            result[name] = rel(got, want.grad)
+        result["max_rel_err"] = max(v for k, v in result.items() if k.endswith("rel_err"))
+        del ref
+    del hp, inputs
+    torch.cuda.empty_cache()
+    dist.barrier()
+    return result
+
+
+def bind_to_local_numa_node(local_rank: int, n_local: int):
+    """Pinned host memory lands on the NUMA node of the thread that first touches it.  With every rank on the default
+    affinity mask all pinned buffers of an 8-GPU job come from one node and the ranks share that node's memory and PCIe
+    root complexes (round 1: 55 -> 23 GB/s of H2D per GPU from 1 to 8 ranks).  Bind each rank to the NUMA node of its GPU
+    when the PCI topology distinguishes the GPUs, else spread the ranks round-robin over the host's nodes -- BEFORE any
+    pinned allocation (and before torch starts its threads)."""
+    info = dict(nodes=0, node=None, cpus=None, source=None)
+    try:
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+        info["nodes"] = len(nodes)
+        if len(nodes) < 2 or os.environ.get("SCP_NUMA_BIND", "1") == "0":
+            return info
+        gpu_nodes = []
+        try:  # NUMA node of every local GPU, from its PCI device
+            import pynvml as nv
+            nv.nvmlInit()
+            for i in range(max(n_local, local_rank + 1)):
+                bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(i)).busId
+                bus = bus.decode() if isinstance(bus, bytes) else bus
+                path = f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node"
+                gpu_nodes.append(int(open(path).read().strip()) if os.path.exists(path) else -1)
+        except Exception:
+            gpu_nodes = []
+        if gpu_nodes and min(gpu_nodes) >= 0 and (len(set(gpu_nodes)) > 1 or n_local == 1):
+            node, info["source"] = gpu_nodes[local_rank], "GPU-local node (pci numa_node)"
+        else:  # the host reports one node (or none) for every GPU: do not pin every rank's buffers on it
+            node, info["source"] = nodes[(local_rank * len(nodes)) // max(n_local, 1)], "round-robin over the host's nodes"
+        cpus = sorted(set(_parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())) & os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(node=node, cpus=len(cpus))
+    except Exception as exc:  # affinity is an optimisation: never fail the run over it
+        info["error"] = repr(exc)[:120]
+    return info
+
+
+def _parse_cpulist(text: str):
+    out = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            out.extend(range(int(a), int(b) + 1))
+        else:
+            out.append(int(part))
     return out
 
 
@@ -403,12 +660,33 @@ def _trace(msg):
         print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
 
 
+def measure_config(torch, dist, name, scaling, dev, rank, world, steps, peaks, timer, graph=True):
+    """ms/step and per-kernel roofline fractions of one BASELINE config at this run's GPU count."""
+    cfg = CONFIGS[name]
+    B = per_gpu_batch(cfg, scaling, world)
+    hp = HotPath(cfg, make_inputs(cfg, B, dev, SEED + rank), dev, rank, world)
+    for _ in range(3):
+        hp.step()
+    if graph:
+        hp.capture()
+        hp.run_step()
+    torch.cuda.synchronize()
+    ms = time_region(torch, dist, world, hp.run_step, steps)
+    kb = kernel_breakdown(hp, timer)
+    rec = dict(workload=cfg["workload"], scaling=scaling, per_gpu_batch=B, global_batch=B * world,
+               ms_per_step=ms / steps, pairs_per_s=B * world * steps / (ms * 1e-3), kernels=summarize_kernels(kb, peaks))
+    del hp
+    torch.cuda.empty_cache()
+    return rec
+
+
 def run_gpu_arm(args):
-    import torch
-    import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_local_numa_node(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
+    import torch
+    import torch.distributed as dist
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -416,13 +694,23 @@ def run_gpu_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
-    import speechclip_plus_b200 as scp
+    import speechclip_plus_b200 as scp  # noqa: F401
     from speechclip_plus_b200 import _lib
     peaks = load_peaks()
-    hp = HotPath(dev, rank, world)
-    B = hp.B
+    cfg = CONFIGS[args.workload]
+    B = per_gpu_batch(cfg, args.scaling, world)
 
-    # ---- parity guard: the first step's loss must match the oracle evaluated on the same features (rank 0, N = 1 GPU rows)
+    check = None
+    if world > 1 and not args.no_check:
+        check = multi_gpu_check(torch, dist, cfg, B, dev, rank, world)
+        _trace(f"multi-GPU check {check}")
+    if args.check_only:
+        if rank == 0:
+            emit_json(dict(multi_gpu_check=check, n_gpus=world, config=make_config(args.workload, args.scaling, world)))
+        _finish(torch, world)
+        return
+
+    hp = HotPath(cfg, make_inputs(cfg, B, dev, SEED + rank), dev, rank, world)
     _trace("state built")
     for _ in range(args.warmup):
         hp.step()
@@ -431,7 +719,6 @@ def run_gpu_arm(args):
     if not args.no_graph:
         hp.capture()
         _trace("graph captured")
-        hp.run_step = hp.step_graph
         for _ in range(2):
             hp.run_step()
         torch.cuda.synchronize()
@@ -449,64 +736,96 @@ def run_gpu_arm(args):
 
     # ---- end to end: host buffers, H2D of every input and D2H of the results inside the timed region
     e2e = None
+    e2e_fp16 = None
     if not args.no_e2e:
-        hp.make_host_buffers()
-        e2e_steps = max(3, min(args.steps, 10))
-        # a second set of device inputs (and its own captured graph) so that the H2D of step k+1 overlaps step k
-        hp2 = HotPath(dev, rank, world)
-        for _ in range(3):
-            hp2.step()
-        if not args.no_graph:
-            hp2.capture()
-            hp2.run_step = hp2.step_graph
-        hp.copy_stream = torch.cuda.Stream()
-        hps = [hp, hp2]
-        run_e2e_pipelined(torch, hps, 3)
-        torch.cuda.synchronize()
-        ms_e2e = time_region(torch, dist, world, lambda: run_e2e_pipelined(torch, hps, e2e_steps), 1)
-        e2e = dict(value=B * world * e2e_steps / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=int(hp.h2d_bytes),
-                   d2h_bytes_per_step=int(hp.d2h_bytes), steps=e2e_steps, ms_per_step=ms_e2e / e2e_steps,
-                   pipeline="H2D of step k+1 (copy stream, second device input set) overlaps the compute of step k")
-        del hp2
+        def e2e_leg(layer_dtype):
+            a = HotPath(cfg, make_inputs(cfg, B, dev, SEED + rank, layer_dtype), dev, rank, world)
+            b = HotPath(cfg, make_inputs(cfg, B, dev, SEED + rank, layer_dtype), dev, rank, world)
+            for h in (a, b):
+                for _ in range(3):
+                    h.step()
+                if not args.no_graph:
+                    h.capture()
+            a.make_host_buffers()
+            a.copy_stream = torch.cuda.Stream()
+            hps = [a, b]
+            n = max(3, min(args.steps, 10))
+            run_e2e_pipelined(torch, hps, 3)
+            torch.cuda.synchronize()
+            ms_e = time_region(torch, dist, world, lambda: run_e2e_pipelined(torch, hps, n), 1)
+            rec = dict(value=B * world * n / (ms_e * 1e-3), unit=UNIT, h2d_bytes_per_step=int(a.h2d_bytes),
+                       d2h_bytes_per_step=int(a.d2h_bytes), steps=n, ms_per_step=ms_e / n,
+                       h2d_gbs_per_gpu=a.h2d_bytes / (ms_e / n * 1e-3) / 1e9,
+                       pipeline="H2D of step k+1 (copy stream, second device input set) overlaps the compute of step k",
+                       host_numa=numa)
+            del a, b, hps
+            torch.cuda.empty_cache()
+            return rec
+        e2e = e2e_leg(None)
+        e2e_fp16 = e2e_leg(torch.float16)
+        e2e_fp16["note"] = ("same step with the upstream hidden states handed over as fp16 (the reference trains with "
+                            "precision: 16; the S1 kernels read fp16 layers directly): half the host bytes. NOT the headline.")
 
-    line = None
-    if rank == 0 and args.no_breakdown:
-        clocks = sampler.stop()
-        emit_json(dict(metric=METRIC, value=pairs_per_s, unit=UNIT, n_gpus=world, steps=args.steps,
-                       ms_per_step=ms / args.steps, gpu_launches=int(launches), clocks=clocks,
-                       note="profiling run: no roofline / e2e legs"))
-    elif rank == 0:
-        kb = kernel_breakdown(hp)
-        clocks = sampler.stop()
-        dom = max(kb, key=lambda k: kb[k]["seconds"])
-        traffic = None
+    timer = GraphTimer(torch, dev)
+    kb = kernel_breakdown(hp, timer)
+    clocks = sampler.stop() if rank == 0 else None
+    del hp
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs at this GPU count (graph replays, same methodology)
+    configs = None
+    if not args.no_configs:
+        configs = {}
+        for name, scaling in (("c2", "weak"), ("c3", "strong"), ("c4", "strong"), ("c5", "strong")):
+            if (name, scaling) == (args.workload, args.scaling):
+                continue
+            try:
+                configs[f"{name}_{scaling}"] = measure_config(torch, dist, name, scaling, dev, rank, world, 10, peaks, timer,
+                                                              graph=not args.no_graph)
+            except Exception as exc:  # a config that does not fit must not take the headline down
+                configs[f"{name}_{scaling}"] = dict(error=repr(exc)[:300])
+                torch.cuda.empty_cache()
+            _trace(f"config {name}/{scaling} done")
+
+    if rank == 0:
+        kernels = summarize_kernels(kb, peaks)
+        dom = max((k for k in kb if kb[k]["bound"] in ("hbm", "tensor")), key=lambda k: kb[k]["seconds"])
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(dom)
+        tr = json.load(open(tpath)) if os.path.exists(tpath) else {}
         d = kb[dom]
         peak = peaks["hbm_gbs"] if d["bound"] == "hbm" else peaks["tflops_burst"]
         roofline = dict(kernel=dom, bound=d["bound"], achieved=d["achieved"], peak=peak, unit=d["unit"],
-                        frac=d["achieved"] / peak, traffic=traffic, peak_source=peaks["source"],
+                        frac=d["achieved"] / peak, traffic=tr.get(dom), peak_source=peaks["source"],
                         ms_per_launch=d["seconds"] * 1e3)
-        kernels = {}
-        for k, v in kb.items():
-            pk = peaks["hbm_gbs"] if v["bound"] == "hbm" else peaks["tflops_burst"]
-            kernels[k] = dict(ms=v["seconds"] * 1e3, achieved=v["achieved"], unit=v["unit"], frac=v["achieved"] / pk,
-                              bound=v["bound"])
-        cpu_baseline = None
+        roofline_vq = None
+        if "vq_fwd" in kb:
+            roofline_vq = {}
+            for k in ("vq_fwd", "vq_bwd"):
+                v = kb[k]
+                roofline_vq[k] = dict(bound="tensor", achieved=v["achieved"], peak=peaks["tflops_burst"], unit="TFLOP/s",
+                                      frac=v["achieved"] / peaks["tflops_burst"], traffic=tr.get(k),
+                                      ms_per_launch=v["seconds"] * 1e3)
+        cpu_baseline = cpu_fair = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu_baseline, _ = time_cpu(2, 8, 1)  # ~10-15 s of CPU work on the box's host cores
+            cpu_baseline, _ = time_cpu(cfg, 2 if cfg["keywords"] else 32, 8, 1)  # ~10-15 s of CPU work on the host cores
+            if cfg["keywords"]:
+                cpu_fair, _ = time_cpu(cfg, 16, 3, 1, fair=True)
+        config = make_config(args.workload, args.scaling, world)
         line = dict(metric=METRIC, value=pairs_per_s, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                    data="synthetic", impl="b200",
-                    config=dict(WORKLOAD, global_batch=B * world, parallelism=f"dp{world}",
-                                launch="one CUDA graph per step" if not args.no_graph else "eager launches",
-                                numerics="fp32 I/O; VQ tensor-core operands fp16 with fp32 accumulation and exact "
-                                         "fp64 arg-max re-scoring, avg_probs reduced from an fp16 e^c scratch; "
-                                         "InfoNCE split-fp16 (hi/lo) operands"),
-                    roofline=roofline, kernels=kernels, cpu_baseline=cpu_baseline, e2e=e2e,
-                    gpu_launches=int(launches), clocks=clocks)
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f32",
+                    data="synthetic", impl="b200", config=config,
+                    launch="one CUDA graph per step" if not args.no_graph else "eager launches",
+                    numerics="fp32 I/O; VQ tensor-core operands fp16 with fp32 accumulation and exact fp64 arg-max "
+                             "re-scoring, avg_probs reduced from an fp16 e^c scratch; InfoNCE split-fp16 (hi/lo) operands",
+                    kernel_timing="every kernel group = one CUDA-graph replay after a 192 MB L2 flush, median of 7",
+                    roofline=roofline, roofline_vq=roofline_vq, kernels=kernels, configs=configs,
+                    multi_gpu_check=check, cpu_baseline=cpu_baseline, cpu_baseline_fair=cpu_fair, e2e=e2e,
+                    e2e_fp16_layers=e2e_fp16, gpu_launches=int(launches), clocks=clocks)
         emit_json(line)
+    _finish(torch, world)
+
+
+def _finish(torch, world):
     if world > 1:
         # NCCL communicators that were captured into CUDA graphs do not tear down cleanly (destroy_process_group
         # dead-locks); nothing after this point needs the group, so leave without running the destructors.
@@ -514,7 +833,6 @@ def run_gpu_arm(args):
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
-    return line
 
 
 _JSON_FD = None
@@ -547,10 +865,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
-    ap.add_argument("--no-breakdown", action="store_true", help="skip the per-kernel timing leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end legs (profiling runs)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the table of the other BASELINE configs")
+    ap.add_argument("--no-check", action="store_true", help="skip the N-rank vs single-process value check (N > 1)")
+    ap.add_argument("--check-only", action="store_true", help="run only the N-rank vs single-process check")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -44,6 +44,7 @@ enum {
 enum { SCP_F32 = 0, SCP_F16 = 1, SCP_BF16 = 2 };
 
 #define SCP_MAX_LAYERS 32
+#define SCP_MAX_PACKED 16
 #define SCP_MAX_MASKED 8
 
 /* ---- library ------------------------------------------------------------------------------------------- */
@@ -241,6 +242,22 @@ int scp_nce_fwd(const float* A, const float* Bm, const int64_t* ids, int64_t N, 
                 float* loss, float* lse_row, float* lse_col,
                 void* workspace, size_t workspace_bytes, scp_stream_t stream);
 
+/* Sharded forward for the one-process-per-GPU layout (option B): A, Bm, ids hold the GATHERED
+ * global batch; this rank evaluates only the denominators of its own samples -- rows [row_begin,row_end) of A against
+ * every row of Bm and rows [row_begin,row_end) of Bm against every row of A: 2 n N D instead of 2 N^2 D multiply-adds.
+ *   stats_local (3, n) f32: [0] = log sum_j mask*exp(S_ij) for the local rows i, [1] = log sum_i mask*exp(S_ij) for the
+ *   local columns j, [2] = <A_i, Bm_i>.
+ * The ranks all-gather stats_local (12 bytes per sample) into stats_all (world, 3, n) and call scp_nce_loss_from_stats,
+ * which returns the loss over all N samples and the contiguous (N,) lse_row / lse_col vectors that scp_nce_bwd reads.
+ * With world = 1 the pair equals scp_nce_fwd. */
+int scp_nce_fwd_local(const float* A, const float* Bm, const int64_t* ids, int64_t N, int64_t D,
+                      const float* log_scale, float fixed_scale, float margin, int dcl,
+                      int64_t row_begin, int64_t row_end, int prepare_bwd, float* stats_local,
+                      void* workspace, size_t workspace_bytes, scp_stream_t stream);
+int scp_nce_loss_from_stats(const float* stats_all, int world, int64_t n_local, const float* log_scale,
+                            float fixed_scale, float margin, int a2b, int b2a,
+                            float* loss, float* lse_row, float* lse_col, scp_stream_t stream);
+
 /* dA, dB: (row_end-row_begin, D) f32 gradients of g_loss*loss w.r.t. A[row_begin:row_end], Bm[row_begin:row_end]
  * (dB nullable).  d_log_scale (nullable, (1,)): this shard's PART of the gradient w.r.t. the log-scale parameter -- the
  * sum of G (.) S over rows [row_begin,row_end) and all columns; the parts of all shards add up to the full gradient
@@ -252,6 +269,22 @@ int scp_nce_bwd(const float* A, const float* Bm, const int64_t* ids, int64_t N, 
                 int fwd_state_valid /* `workspace` is the untouched workspace of scp_nce_fwd(prepare_bwd=1) on the same inputs */,
                 float* dA, float* dB, float* d_log_scale,
                 void* workspace, size_t workspace_bytes, scp_stream_t stream);
+
+/* ---- tail of the data-parallel step: packed gradient exchange + fused Adam for the path's own trainable tensors
+ *      (weightedsum_layer.weights, criterion.temperature, ...; avssl/model/kwClip.py:636-668: ONE Adam group, yaml
+ *      audio_encoder.optim: lr 1e-4, weight_decay 1e-6).  The reference's DataParallel reduce_add_coalesced +
+ *      torch.optim.Adam become: scp_grad_pack -> one NCCL all-reduce of `packed` (issued by the caller) ->
+ *      scp_adam_packed.  grads / params: HOST arrays of n <= SCP_MAX_PACKED device pointers (f32), sizes: HOST array of
+ *      element counts; packed, exp_avg, exp_avg_sq: (sum sizes) f32; a NULL grads[i] packs zeros. ---------------- */
+int scp_grad_pack(const float* const* grads, const int64_t* sizes, int n, float scale, float* packed,
+                  scp_stream_t stream);
+/* torch.optim.Adam semantics (betas, eps, L2 weight_decay, bias correction; no amsgrad) applied in place to every
+ * registered tensor; g = grad_scale * packed.  step: device int64 counter, read and incremented by the kernel (a
+ * replayed CUDA graph therefore advances it).  lr_device (nullable): device f32 learning rate written by the caller's
+ * scheduler; otherwise `lr`. */
+int scp_adam_packed(float* const* params, const int64_t* sizes, int n, const float* packed_grads, float grad_scale,
+                    float* exp_avg, float* exp_avg_sq, int64_t* step, const float* lr_device, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, scp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -18,6 +18,7 @@ SCP_F32, SCP_F16, SCP_BF16 = 0, 1, 2
 SCP_NORM_NONE, SCP_NORM_LAYERNORM, SCP_NORM_L2_FRAME, SCP_NORM_UTT_MEAN = 0, 1, 2, 3
 SCP_MAX_LAYERS = 32
 SCP_MAX_MASKED = 8
+SCP_MAX_PACKED = 16
 
 
 class ScpError(RuntimeError):
@@ -79,9 +80,16 @@ SIGNATURES = {
     "scp_l2norm_pack": (c_int, [POINTER(c_void_p), c_int, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),
     "scp_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "scp_grad_pack": (c_int, [POINTER(c_void_p), POINTER(c_int64), c_int, c_float, c_void_p, c_void_p]),
+    "scp_adam_packed": (c_int, [POINTER(c_void_p), POINTER(c_int64), c_int, c_void_p, c_float, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float, c_void_p]),
     "scp_nce_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "scp_nce_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_float, c_float, c_int, c_int,
                             c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "scp_nce_fwd_local": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_float, c_float, c_int, c_int64,
+                                  c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "scp_nce_loss_from_stats": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_float, c_float, c_int, c_int, c_void_p,
+                                        c_void_p, c_void_p, c_void_p]),
     "scp_nce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_float, c_float, c_int, c_int,
                             c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                             c_void_p, c_size_t, c_void_p]),

@@ -19,7 +19,7 @@ INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libscp_b200.so")
 OBJ_DIR = os.path.join(PKG_DIR, "build")
 
-SOURCES = ["scp_runtime.cu", "scp_wsum.cu", "scp_kwbn.cu", "scp_splice.cu", "scp_cif.cu", "scp_vq.cu", "scp_nce.cu"]
+SOURCES = ["scp_runtime.cu", "scp_wsum.cu", "scp_kwbn.cu", "scp_splice.cu", "scp_cif.cu", "scp_vq.cu", "scp_nce.cu", "scp_optim.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -45,14 +45,37 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Serialised across processes (torchrun starts one per GPU and every rank may find the library stale at once):
+    an exclusive file lock is held for the whole build, the late ranks re-check under the lock and find the library
+    fresh; objects and the linked library are written under per-process names and renamed into place."""
     if not force and not needs_build():
         return LIB_PATH
-    nvcc = _nvcc()
+    import fcntl
     os.makedirs(OBJ_DIR, exist_ok=True)
+    with open(os.path.join(OBJ_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():  # another process built it while we waited
+                return LIB_PATH
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
+    nvcc = _nvcc()
     sources = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    tag = f".{os.getpid()}"
+
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers += [os.path.join(INCLUDE, "scp_b200.h"), __file__]
+    hdr_mtime = max(os.path.getmtime(f) for f in headers)
 
     def compile_one(src: str) -> str:
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        final = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        if os.path.exists(final) and os.path.getmtime(final) > max(hdr_mtime, os.path.getmtime(os.path.join(CSRC, src))):
+            return final  # this unit and every header it can include are older than its object
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", tag + ".o"))
         cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd), flush=True)
@@ -63,7 +86,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(len(sources), os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, sources))
-    tmp = LIB_PATH + ".tmp"
+    tmp = LIB_PATH + tag + ".tmp"
     # cudart is linked statically (nvcc default): the library has no runtime dependency besides libcuda (resolved
     # lazily through cudaGetDriverEntryPoint) and libstdc++
     cmd = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
@@ -71,6 +94,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     os.replace(tmp, LIB_PATH)
+    for obj in objs:  # canonical object names: the next build recompiles only the units that changed
+        if obj.endswith(tag + ".o"):
+            os.replace(obj, obj.replace(tag + ".o", ".o"))
     return LIB_PATH
 
 

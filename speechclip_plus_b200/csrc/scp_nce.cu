@@ -110,8 +110,9 @@ __device__ __forceinline__ bool nce_in_denominator(bool diag, bool same_id, int 
 struct NceFwdEpi {
   struct Params {
     NceCommon c;
-    float* partials;  // (2*Np, 2*n_groups, 2): running max, sum
+    float* partials;  // (2*Lp, 2*n_groups, 2): running max, sum
     int Np, n_groups;
+    int Lp, row_begin, n_local;  // the stacked X rows are the samples [row_begin, row_begin + n_local) in both directions
   };
   static constexpr int kSmemBytes = 0;
   const Params& p;
@@ -121,9 +122,10 @@ struct NceFwdEpi {
   float k, run_max, sum;
   __device__ __forceinline__ NceFwdEpi(const Params& p_, const WorkInfo& w, const tc::EpiCtx& ctx)
       : p(p_), r(w.m_tile * tc::kTileM + ctx.row_in_tile), group(w.n_group * 2 + ctx.half) {
-    dir = r >= p.Np;
-    own = r - dir * p.Np;
-    own_valid = own < p.c.N;
+    dir = r >= p.Lp;
+    const int loc = r - dir * p.Lp;
+    own = p.row_begin + loc;
+    own_valid = loc < p.n_local;
     own_id = (p.c.ids && own_valid) ? __ldg(p.c.ids + own) : (int64_t)own;
     k = p.c.scale() / kProdScale;
     run_max = kNegBigN;
@@ -140,7 +142,7 @@ struct NceFwdEpi {
       const int j = j0 + i;
       const bool diag = j == own;
       const int64_t jid = (p.c.ids && j < p.c.N) ? __ldg(p.c.ids + j) : (int64_t)j;
-      const bool inc = j < p.c.N && nce_in_denominator(diag, !diag && jid == own_id, p.c.dcl);
+      const bool inc = own_valid && j < p.c.N && nce_in_denominator(diag, !diag && jid == own_id, p.c.dcl);
       float x = v[0][i] * k;
       if (diag) x -= p.c.margin;
       l[i] = inc ? x : kNegBigN;
@@ -193,6 +195,55 @@ nce_loss_kernel(const float* __restrict__ partials, int Np, int n_groups, const 
     float t = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : 0.f;
     t = warp_sum(t);
     if (threadIdx.x == 0) *loss = t / ((float)c.N * (float)(a2b + b2a));
+  }
+}
+
+// ---- sharded forward (one process per GPU): each rank evaluates the denominators of ITS rows / columns only ----------
+// stats (3, n_local): [0] = log sum_j mask e^{S_ij} (row i local), [1] = log sum_i mask e^{S_ij} (column j local),
+// [2] = <A_i, B_i>.  The ranks all-gather this vector (12 bytes per sample) instead of recomputing the N x N problem.
+__global__ void nce_local_stats_kernel(const float* __restrict__ partials, int Lp, int n_groups,
+                                       const float* __restrict__ pos, int row_begin, int n_local,
+                                       float* __restrict__ stats) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_local) return;
+#pragma unroll
+  for (int dir = 0; dir < 2; ++dir) {
+    const float2* pp = reinterpret_cast<const float2*>(partials + ((int64_t)(dir * Lp + l) * n_groups) * 2);
+    float mx = kNegBigN;
+    for (int g = 0; g < n_groups; ++g) mx = fmaxf(mx, pp[g].x);
+    float sm = 0.f;
+    for (int g = 0; g < n_groups; ++g) sm += pp[g].y * expf(pp[g].x - mx);
+    stats[dir * n_local + l] = mx + logf(sm);
+  }
+  stats[2 * n_local + l] = pos[row_begin + l];
+}
+
+// one block: the loss (losses.py:234-243) from the gathered (world, 3, n) statistics; also writes the contiguous
+// (N,) denominators the backward reads.  Every rank evaluates the same N terms in the same order: identical loss values.
+__global__ void __launch_bounds__(1024)
+nce_loss_from_stats_kernel(const float* __restrict__ stats, int world, int n, float scale_fixed,
+                           const float* __restrict__ log_scale, float margin, int a2b, int b2a, float* __restrict__ loss,
+                           float* __restrict__ lse_row, float* __restrict__ lse_col) {
+  __shared__ float s_red[32];
+  const float scale = log_scale ? expf(__ldg(log_scale)) : scale_fixed;
+  const int N = world * n;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const int r = i / n, l = i - r * n;
+    const float* st = stats + (int64_t)r * 3 * n;
+    const float lr = st[l], lc = st[n + l], p = st[2 * n + l] * scale - margin;
+    lse_row[i] = lr;
+    lse_col[i] = lc;
+    if (a2b) acc += lr - p;
+    if (b2a) acc += lc - p;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) *loss = t / ((float)N * (float)(a2b + b2a));
   }
 }
 
@@ -469,10 +520,65 @@ extern "C" int scp_nce_fwd(const float* A, const float* Bm, const int64_t* ids, 
   maps.x[1] = maps.x[0];
   if ((rc = tc::make_tmap_f16(&maps.y, ws.y3, 2 * Np, 3 * D, 3 * D, kNceBN))) return rc;
   const Sched sc = nce_sweep_sched(Np, Np, D, ws.n_groups);
-  NceFwdEpi::Params ep{c, ws.partials, (int)Np, ws.n_groups};
+  NceFwdEpi::Params ep{c, ws.partials, (int)Np, ws.n_groups, (int)Np, 0, (int)N};
   if ((rc = tc::launch_stream_gemm<kNceBN, 1, 6, NceFwdEpi>(maps, sc, ep, s, "nce_fwd_sweep"))) return rc;
   nce_loss_kernel<<<1, 1024, 0, s>>>(ws.partials, (int)Np, 2 * ws.n_groups, ws.pos, c, a2b, b2a, loss, lse_row, lse_col);
   SCP_CUDA_LAUNCH_CHECK("nce_loss");
+  return SCP_OK;
+}
+
+extern "C" int scp_nce_fwd_local(const float* A, const float* Bm, const int64_t* ids, int64_t N, int64_t D,
+                                 const float* log_scale, float fixed_scale, float margin, int dcl, int64_t row_begin,
+                                 int64_t row_end, int prepare_bwd, float* stats_local, void* workspace,
+                                 size_t workspace_bytes, scp_stream_t stream) {
+  int rc = check_device_arch();
+  if (rc) return rc;
+  rc = check_nce_shape(N, D);
+  if (rc) return rc;
+  SCP_CHECK_ARG(A && Bm && stats_local && workspace, "nce_fwd_local: null pointer");
+  SCP_CHECK_ARG(0 <= row_begin && row_begin < row_end && row_end <= N, "nce_fwd_local: bad local row range");
+  const NceWs ws = nce_ws(workspace, N, D, N);
+  if (workspace_bytes < ws.total) return fail(SCP_ERR_WORKSPACE, "nce_fwd_local: workspace %zu < %zu", workspace_bytes, ws.total);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t n_local = row_end - row_begin;
+  const int64_t Np = round_up(N, tc::kTileM), Lp = round_up(n_local, tc::kTileM);
+  NceCommon c{ids, log_scale, fixed_scale, margin, dcl, (int)N};
+  nce_prep_kernel<<<(unsigned)ceil_div(Np, 8), 256, 0, s>>>(A, Bm, N, Np, (int)D, ws.x3, ws.y3, ws.pos);
+  SCP_CUDA_LAUNCH_CHECK("nce_prep");
+  if (prepare_bwd) {
+    dim3 tb(32, 8), tg((unsigned)(Np / 32), (unsigned)ceil_div(D, 32));
+    nce_prep_t_kernel<<<tg, tb, 0, s>>>(A, Bm, N, Np, (int)D, ws.t3);
+    SCP_CUDA_LAUNCH_CHECK("nce_prep_t");
+  }
+  // X = the local rows of the stacked split operands, addressed in place (as in scp_nce_bwd)
+  const int sweep_m_tiles = (int)(2 * Lp / tc::kTileM);
+  const int sweep_groups = std::max(1, std::min((int)(Np / kNceBN), kNumSMs / sweep_m_tiles));
+  GemmMaps maps{};
+  if ((rc = tc::make_tmap_f16(&maps.x[0], ws.x3 + row_begin * 3 * D, 2 * Np - row_begin, 3 * D, 3 * D, tc::kTileM))) return rc;
+  maps.x[1] = maps.x[0];
+  if ((rc = tc::make_tmap_f16(&maps.y, ws.y3, 2 * Np, 3 * D, 3 * D, kNceBN))) return rc;
+  Sched sc = nce_sweep_sched(Lp, Np, D, sweep_groups);
+  sc.x_upper_row_off = (int)(Np - Lp);
+  // the partials of a local sweep live at the start of the (larger) split-K buffer of the backward: the forward's own
+  // partial buffer is sized for n_groups of the FULL sweep, a local sweep has more groups per row
+  float* partials = ws.out;
+  NceFwdEpi::Params ep{c, partials, (int)Np, sweep_groups, (int)Lp, (int)row_begin, (int)n_local};
+  if ((rc = tc::launch_stream_gemm<kNceBN, 1, 6, NceFwdEpi>(maps, sc, ep, s, "nce_fwd_local_sweep"))) return rc;
+  nce_local_stats_kernel<<<(unsigned)ceil_div(n_local, 128), 128, 0, s>>>(partials, (int)Lp, 2 * sweep_groups, ws.pos,
+                                                                         (int)row_begin, (int)n_local, stats_local);
+  SCP_CUDA_LAUNCH_CHECK("nce_local_stats");
+  return SCP_OK;
+}
+
+extern "C" int scp_nce_loss_from_stats(const float* stats_all, int world, int64_t n_local, const float* log_scale,
+                                       float fixed_scale, float margin, int a2b, int b2a, float* loss, float* lse_row,
+                                       float* lse_col, scp_stream_t stream) {
+  SCP_CHECK_ARG(stats_all && loss && lse_row && lse_col, "nce_loss_from_stats: null pointer");
+  SCP_CHECK_ARG(world >= 1 && n_local >= 1 && (int64_t)world * n_local <= (1 << 20), "nce_loss_from_stats: bad shape");
+  SCP_CHECK_ARG(a2b || b2a, "nce_loss_from_stats: a2b and b2a both off");
+  nce_loss_from_stats_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      stats_all, world, (int)n_local, fixed_scale, log_scale, margin, a2b, b2a, loss, lse_row, lse_col);
+  SCP_CUDA_LAUNCH_CHECK("nce_loss_from_stats");
   return SCP_OK;
 }
 

@@ -754,8 +754,12 @@ vq_metrics_kernel(const float* __restrict__ code_hist, const float* __restrict__
 // warp <-> row: ghat = g/||g|| (fp16), gscale = ||g||, s0 = <ghat, mean(E)> / norm_ref
 __global__ void vq_bwd_prep_kernel(const float* __restrict__ g, int64_t M, int64_t Mp, int D,
                                    const float* __restrict__ table_mean /* (D+1): [D] = norm_ref */,
-                                   __half* __restrict__ g_hat, float* __restrict__ g_aux /* (Mp,2): scale, s0 */) {
+                                   __half* __restrict__ g_hat, float* __restrict__ g_aux /* (Mp,2): scale, s0 */,
+                                   unsigned int* __restrict__ flags /* nullable: pipeline hand-off counters */,
+                                   int n_flags) {
   const int lane = threadIdx.x & 31;
+  if (flags && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < n_flags; i += blockDim.x) flags[i] = 0u;
   const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= Mp) return;
   __half* dst = g_hat + m * D;
@@ -1111,6 +1115,10 @@ vq_dense_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g_p, 
   }
 }
 
+}  // namespace scp
+#include "scp_vq_pipe.cuh"
+namespace scp {
+
 // =====================================================================================================================
 // host side
 // =====================================================================================================================
@@ -1186,11 +1194,67 @@ struct VqBwdWs {
   float* uw;
   size_t total;
   int n_groups, k_splits, bn_out;
+  // producer/consumer pipeline (scp_vq_pipe.cuh)
+  int pipe_mode;  // 0 = two-kernel path, 1 = fused pipeline (ring in L2), 2 = the two roles as separate launches
+  int NP, ring, uw_slots, sa, sc, MT, NVT;
+  unsigned int* flags;  // ready[NP] | done[NP]
+  size_t pipe_smem;
 };
 static int vq_out_bn(int64_t D) { return D % 256 == 0 ? 256 : (D % 128 == 0 ? 128 : 64); }
+
+// SCP_VQ_BWD_PIPE: 1 (default) fused pipeline, 2 the same roles as two launches through a full-size scratch, 0 the older
+// sweep-3 + gemm_out kernels (always used when D is not 128 / 256 / 512: the pipeline keeps a 128 x D fp16 tile resident)
+static int vq_bwd_pipe_mode(int64_t D) {
+  static const int env = [] { const char* e = getenv("SCP_VQ_BWD_PIPE"); return e ? atoi(e) : 1; }();
+  if (!(D == 128 || D == 256 || D == 512)) return 0;
+  return env;
+}
+static int vq_pipe_ring() {
+  static const int r = [] { const char* e = getenv("SCP_VQ_BWD_RING"); const int v = e ? atoi(e) : 4; return v < 2 ? 2 : (v > 64 ? 64 : v); }();
+  return r;
+}
+
 static VqBwdWs vq_bwd_ws(void* base, int64_t M, int64_t V, int64_t D) {
   const int64_t Mp = round_up(M, tc::kTileM), Vp = scp_vq_padded_vocab(V);
   VqBwdWs w{};
+  w.pipe_mode = vq_bwd_pipe_mode(D);
+  if (w.pipe_mode) {
+    w.MT = (int)(Mp / tc::kTileM);
+    w.NVT = (int)(Vp / pipe::kStepV);
+    const long long total = (long long)w.MT * w.NVT;
+    const int max_pipes = w.pipe_mode == 1 ? kNumSMs / 4 : kNumSMs / 2;
+    w.NP = (int)std::max<long long>(1, std::min<long long>(max_pipes, total));
+    w.ring = vq_pipe_ring();
+    w.uw_slots = 1;
+    for (int mt = 0; mt < w.MT; ++mt) {
+      const int qa = pipe::pipe_of_step((long long)mt * w.NVT, total, w.NP);
+      const int qb = pipe::pipe_of_step((long long)(mt + 1) * w.NVT - 1, total, w.NP);
+      w.uw_slots = std::max(w.uw_slots, qb - qa + 1);
+    }
+    const int KC = (int)(D / tc::kChunkK);
+    const int smem_budget = tc::kMaxDynSmem - 1024 - pipe::kBarBytes;
+    w.sa = std::min(pipe::kMaxStages, (smem_budget - KC * tc::kXTileBytes - 1024) / tc::kXTileBytes);
+    const int c_stage = tc::kXTileBytes + (int)D * 64;
+    w.sc = std::min(pipe::kMaxStages, smem_budget / c_stage);
+    const size_t prod = (size_t)KC * tc::kXTileBytes + (size_t)w.sa * tc::kXTileBytes + 1024;
+    const size_t cons = (size_t)w.sc * c_stage;
+    w.pipe_smem = 1024 + pipe::kBarBytes + std::max(prod, cons);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+      void* p = base ? static_cast<uint8_t*>(base) + off : nullptr;
+      off += (bytes + 255) & ~size_t(255);
+      return p;
+    };
+    w.g_hat = static_cast<__half*>(take((size_t)Mp * D * 2));
+    w.g_aux = static_cast<float*>(take((size_t)Mp * 2 * 4));
+    w.flags = static_cast<unsigned int*>(take((size_t)2 * w.NP * 4));
+    const size_t slots = w.pipe_mode == 1 ? (size_t)w.NP * w.ring : (size_t)total;
+    w.pq = static_cast<__half*>(take(slots * pipe::kSlotHalfs * 2));
+    w.partials = static_cast<float*>(take((size_t)Mp * w.uw_slots * 8 * 16));
+    w.uw = static_cast<float*>(take((size_t)w.uw_slots * 2 * Mp * D * 4));
+    w.total = off;
+    return w;
+  }
   const int m_tiles = (int)(Mp / tc::kTileM);
   const int n_tiles3 = (int)(Vp / 128);
   w.n_groups = std::max(1, std::min(n_tiles3, kNumSMs / vq_m_ctas(m_tiles)));
@@ -1432,8 +1496,64 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
   const int64_t Mp = round_up(M, tc::kTileM), Vp = scp_vq_padded_vocab(V);
   const MaskedCols mc = make_masked(masked_cols, n_masked);
 
-  vq_bwd_prep_kernel<<<(unsigned)ceil_div(Mp, 8), 256, 0, s>>>(g_keywords, M, Mp, (int)D, table_mean, ws.g_hat, ws.g_aux);
+  vq_bwd_prep_kernel<<<(unsigned)ceil_div(Mp, 8), 256, 0, s>>>(g_keywords, M, Mp, (int)D, table_mean, ws.g_hat, ws.g_aux,
+                                                               ws.pipe_mode ? ws.flags : nullptr, 2 * ws.NP);
   SCP_CUDA_LAUNCH_CHECK("vq_bwd_prep");
+  if (ws.pipe_mode) {
+    pipe::PipeMaps maps{};
+    if ((rc = tc::make_tmap_f16(&maps.tab_k, table_hat, Vp, D, D, 128))) return rc;
+    if ((rc = tc::make_tmap_f16(&maps.kw, kw_hat, Mp, D, D, 128))) return rc;
+    if ((rc = tc::make_tmap_f16(&maps.gh, ws.g_hat, Mp, D, D, 128))) return rc;
+    const int64_t slots = ws.pipe_mode == 1 ? (int64_t)ws.NP * ws.ring : (int64_t)ws.MT * ws.NVT;
+    if ((rc = tc::make_tmap_f16(&maps.scr, ws.pq, slots * 512, 128, 128, 64))) return rc;
+    if ((rc = tc::make_tmap_f16(&maps.tab_mn, table_hat, Vp, D, D, 64))) return rc;
+    pipe::PipeParams pp{};
+    pp.MT = ws.MT; pp.NVT = ws.NVT; pp.NP = ws.NP; pp.KC = (int)(D / tc::kChunkK); pp.D = (int)D; pp.V = (int)V;
+    pp.M = M; pp.Mp = Mp;
+    pp.fused = ws.pipe_mode == 1;
+    pp.ring = ws.ring; pp.sa = ws.sa; pp.sc = ws.sc; pp.uw_slots = ws.uw_slots;
+    pp.scratch = ws.pq;
+    pp.ready = ws.flags; pp.done = ws.flags + ws.NP;
+    pp.row_stats = row_stats; pp.g_aux = ws.g_aux; pp.table_norm = table_norm; pp.table_mean = table_mean; pp.tau = tau;
+    pp.sums = ws.partials; pp.uw = ws.uw; pp.mc = mc;
+    auto kern = g_tau ? pipe::vq_bwd_pipe_kernel<true> : pipe::vq_bwd_pipe_kernel<false>;
+    static thread_local bool configured[2] = {false, false};
+    if (!configured[g_tau ? 1 : 0]) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kMaxDynSmem);
+      if (e != cudaSuccess) return fail(SCP_ERR_CUDA, "vq_bwd_pipe: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      configured[g_tau ? 1 : 0] = true;
+    }
+    if (ws.pipe_smem > (size_t)tc::kMaxDynSmem) return fail(SCP_ERR_UNSUPPORTED, "vq_bwd_pipe: %zu B of shared memory", ws.pipe_smem);
+    auto launch = [&](int role) -> int {
+      pp.role = role;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)(pp.fused ? 4 * ws.NP : 2 * ws.NP));
+      cfg.blockDim = dim3(tc::kGemmThreads);
+      cfg.dynamicSmemBytes = ws.pipe_smem;
+      cfg.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps, pp);
+      if (e != cudaSuccess) return fail(SCP_ERR_CUDA, "vq_bwd_pipe: launch failed: %s", cudaGetErrorString(e));
+      count_launch();
+      return SCP_OK;
+    };
+    if (pp.fused) {
+      if ((rc = launch(0))) return rc;
+    } else {
+      if ((rc = launch(0))) return rc;
+      if ((rc = launch(1))) return rc;
+    }
+    if (g_tau && cudaMemsetAsync(g_tau, 0, 4, s) != cudaSuccess) return fail(SCP_ERR_CUDA, "memset g_tau");
+    pipe::vq_bwd_pipe_finalize_kernel<<<(unsigned)M, (unsigned)(D / 4), 0, s>>>(
+        ws.uw, ws.uw_slots, ws.NVT, ws.MT, ws.NP, M, Mp, (int)D, ws.partials, ws.g_aux, kw, row_stats, table_mean, tau, g_kw,
+        g_tau);
+    SCP_CUDA_LAUNCH_CHECK("vq_bwd_pipe_finalize");
+    return SCP_OK;
+  }
   // ---- sweep 3: P~, Q~ and row sums
   {
     GemmMaps maps{};

@@ -76,19 +76,23 @@ class _NormPackGatherFn(torch.autograd.Function):
         _lib.require_cuda(f0, "gather_loss_feats")
         n, D = f0.shape
         dev = f0.device
+        # one storage type for the pack kernel: the features' own type when they agree, else fp32 (never round an fp32
+        # audio feature to the image tower's half precision: the reference normalises each tensor in its own type and
+        # calls .float() before the criterion, kwClip.py:1015-1028)
+        common = f0.dtype if all(f.dtype == f0.dtype for f in feats) else torch.float32
         srcs = []
         for f in feats:
             assert f.shape == (n, D), (f.shape, (n, D))
             fd = f.detach()
-            if fd.dtype != f0.dtype:
-                fd = fd.to(f0.dtype)
+            if fd.dtype != common:
+                fd = fd.to(common)
             srcs.append(fd.contiguous())
         ids64 = ids.detach().reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
         nbytes = int(lib.scp_pack_bytes(len(srcs), n, D))
         packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         inv = torch.empty((len(srcs), n), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            st = lib.scp_l2norm_pack(_lib.ptr_array(srcs), len(srcs), n, D, _lib.dtype_code(f0.dtype),
+            st = lib.scp_l2norm_pack(_lib.ptr_array(srcs), len(srcs), n, D, _lib.dtype_code(common),
                                      _lib.ptr(ids64), _lib.ptr(packed), _lib.ptr(inv), _lib.stream_ptr(dev))
         _lib.check(st, "scp_l2norm_pack")
         gathered = all_gather_packed(packed, group)
@@ -143,10 +147,33 @@ def gather_loss_feats(loss_feats: Dict[str, torch.Tensor], group=None) -> Tuple[
     return out, shard_rows(n, rank)
 
 
+def _world(group) -> int:
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def global_mean_with_local_grad(local_mean: torch.Tensor, group=None) -> torch.Tensor:
+    """A per-rank mean -> a tensor whose VALUE is the mean over all ranks (what the reference's DataParallel gather +
+    ``nn.L1Loss`` produces, kwClip.py:1031-1038) and whose gradient is ``d local_mean / world``: after the loss is
+    multiplied by ``ddp_grad_scale(world)`` and DDP averages the parameter gradients over ranks, the result equals the
+    gradient of the global mean.  Equal per-rank batch sizes are assumed (the data-parallel sampler guarantees them)."""
+    world = _world(group)
+    if world == 1:
+        return local_mean
+    g = local_mean.detach().clone()
+    dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+    g = g / world
+    return g + (local_mean - local_mean.detach()) / world
+
+
 def compute_loss(loss_feats: Dict[str, torch.Tensor], criterion, cascaded_objective_weight: float = 0.0,
                  parallel_objective_weight: float = 0.0, quantity_loss_weight: float = 0.0,
-                 quantity_loss_criteria=None, local_rows: Optional[Tuple[int, int]] = None) -> Dict[str, torch.Tensor]:
-    """``KWClip_GeneralTransformer.compute_loss`` (kwClip.py:999-1040) with the same keys in and out."""
+                 quantity_loss_criteria=None, local_rows: Optional[Tuple[int, int]] = None,
+                 group=None) -> Dict[str, torch.Tensor]:
+    """``KWClip_GeneralTransformer.compute_loss`` (kwClip.py:999-1040) with the same keys in and out.
+
+    ``local_rows`` / ``group`` (one process per GPU): ``loss_feats`` holds the gathered global batch, the contrastive
+    terms back-propagate into this rank's rows only, and the CIF quantity loss -- whose inputs stay rank-local -- is
+    turned into the global mean (see :func:`global_mean_with_local_grad`)."""
     assert isinstance(loss_feats, dict)
     required_keys = {"id", "image_feat"}
     assert required_keys.issubset(set(loss_feats.keys())), f"required: {required_keys}, input: {loss_feats.keys()}"
@@ -157,7 +184,7 @@ def compute_loss(loss_feats: Dict[str, torch.Tensor], criterion, cascaded_object
         if weight > 0.0:
             key = f"{branch}_audio_feat"
             assert key in loss_feats, f"{loss_feats.keys()}"
-            kwargs = {} if local_rows is None else {"local_rows": local_rows}
+            kwargs = {} if local_rows is None else {"local_rows": local_rows, "group": group}
             losses[f"{branch[0]}_cl_loss"] = criterion(feat_A=loss_feats[key].float(), feat_B=image_feat, index=ids,
                                                       **kwargs)
             # `loss += weight * term` of the reference, without the no-op kernels for `0 + x` and `1.0 * x`
@@ -166,6 +193,9 @@ def compute_loss(loss_feats: Dict[str, torch.Tensor], criterion, cascaded_object
                 term = weight * term
             losses["loss"] = term if isinstance(losses["loss"], int) else losses["loss"] + term
     if ("cif_quantity_out" in loss_feats and "cif_target_len" in loss_feats and quantity_loss_criteria is not None):
-        losses["quantity_loss"] = quantity_loss_criteria(loss_feats["cif_quantity_out"], loss_feats["cif_target_len"])
+        q_loss = quantity_loss_criteria(loss_feats["cif_quantity_out"], loss_feats["cif_target_len"])
+        if local_rows is not None:
+            q_loss = global_mean_with_local_grad(q_loss, group)
+        losses["quantity_loss"] = q_loss
         losses["loss"] = losses["loss"] + quantity_loss_weight * losses["quantity_loss"]
     return losses

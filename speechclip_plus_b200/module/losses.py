@@ -23,7 +23,8 @@ MAX_EYE = 256  # losses.py:126 -- only the size of the compatibility buffers
 
 class _MaskedNceFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feat_a, feat_b, log_scale, index, fixed_scale, margin, dcl, a2b, b2a, row_begin, row_end):
+    def forward(ctx, feat_a, feat_b, log_scale, index, fixed_scale, margin, dcl, a2b, b2a, row_begin, row_end,
+                group=None, sharded=False):
         lib = _lib.load()
         _lib.require_cuda(feat_a, "MaskedContrastiveLoss")
         N, D = feat_a.shape
@@ -47,11 +48,29 @@ class _MaskedNceFn(torch.autograd.Function):
         ws_bytes = lib.scp_nce_workspace_bytes(N, D)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         need_bwd = any(ctx.needs_input_grad[:3])
-        with torch.cuda.device(dev):
-            st = lib.scp_nce_fwd(_lib.ptr(a), _lib.ptr(b), _lib.ptr(ids), N, D, _lib.ptr(ls), float(fixed_scale),
-                                 float(margin), int(dcl), int(a2b), int(b2a), int(need_bwd), _lib.ptr(loss),
-                                 _lib.ptr(lse_row), _lib.ptr(lse_col), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
-        _lib.check(st, "scp_nce_fwd")
+        if sharded:
+            # SURVEY.md section 8(e) option B: this rank evaluates the denominators of its own rows / columns only and
+            # the ranks exchange 12 bytes per sample (losses.py:224-243 restated per shard)
+            n_local = int(row_end) - int(row_begin)
+            world = N // n_local
+            stats = torch.empty((3, n_local), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                st = lib.scp_nce_fwd_local(_lib.ptr(a), _lib.ptr(b), _lib.ptr(ids), N, D, _lib.ptr(ls),
+                                           float(fixed_scale), float(margin), int(dcl), int(row_begin), int(row_end),
+                                           int(need_bwd), _lib.ptr(stats), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
+            _lib.check(st, "scp_nce_fwd_local")
+            stats_all = all_gather_stats(stats, world, group)
+            with torch.cuda.device(dev):
+                st = lib.scp_nce_loss_from_stats(_lib.ptr(stats_all), world, n_local, _lib.ptr(ls), float(fixed_scale),
+                                                 float(margin), int(a2b), int(b2a), _lib.ptr(loss), _lib.ptr(lse_row),
+                                                 _lib.ptr(lse_col), _lib.stream_ptr(dev))
+            _lib.check(st, "scp_nce_loss_from_stats")
+        else:
+            with torch.cuda.device(dev):
+                st = lib.scp_nce_fwd(_lib.ptr(a), _lib.ptr(b), _lib.ptr(ids), N, D, _lib.ptr(ls), float(fixed_scale),
+                                     float(margin), int(dcl), int(a2b), int(b2a), int(need_bwd), _lib.ptr(loss),
+                                     _lib.ptr(lse_row), _lib.ptr(lse_col), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
+            _lib.check(st, "scp_nce_fwd")
         # the workspace holds the split fp16 operands; keeping it alive lets the backward skip their re-computation
         ctx.save_for_backward(a, b, ids, ls, lse_row, lse_col, ws if need_bwd else None)
         ctx.cfg = (float(fixed_scale), float(margin), int(dcl), int(a2b), int(b2a), int(row_begin), int(row_end))
@@ -95,7 +114,27 @@ class _MaskedNceFn(torch.autograd.Function):
         gA = full(dA, ctx.in_dtypes[0]) if ctx.needs_input_grad[0] else None
         gB = full(dB, ctx.in_dtypes[1])
         gT = dT.reshape(()) if dT is not None else None
-        return gA, gB, gT, None, None, None, None, None, None, None, None
+        return gA, gB, gT, None, None, None, None, None, None, None, None, None, None
+
+
+def all_gather_stats(stats: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """(3, n) per rank -> (world, 3, n), rank-major (the row order of ``gather_loss_feats``)."""
+    if world == 1:
+        return stats.reshape(1, *stats.shape)
+    import torch.distributed as dist
+    out = torch.empty(world * stats.numel(), dtype=stats.dtype, device=stats.device)
+    dist.all_gather_into_tensor(out, stats.reshape(-1).contiguous(), group=group)
+    return out.reshape(world, *stats.shape)
+
+
+def _use_sharded_forward(N: int, begin: int, end: int, group) -> bool:
+    """The sharded forward needs every rank to own an equal, rank-ordered slice of the gathered batch."""
+    import torch.distributed as dist
+    if (begin, end) == (0, N) or not (dist.is_available() and dist.is_initialized()):
+        return False
+    world = dist.get_world_size(group)
+    n = end - begin
+    return world > 1 and n * world == N and begin == dist.get_rank(group) * n
 
 
 class MaskedContrastiveLoss(nn.Module):
@@ -128,14 +167,18 @@ class MaskedContrastiveLoss(nn.Module):
         return float(temp)
 
     def forward(self, feat_A: torch.Tensor, feat_B: torch.Tensor, index: torch.LongTensor = None,
-                local_rows: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+                local_rows: Optional[Tuple[int, int]] = None, group=None) -> torch.Tensor:
         """``local_rows=(begin, end)`` (extension for the one-process-per-GPU layout): the loss is the global one over
-        all rows, gradients are produced only for this rank's rows -- see ``model.kw_glue.gather_loss_feats``."""
+        all rows, gradients are produced only for this rank's rows -- see ``model.kw_glue.gather_loss_feats``.  When the
+        rows are this rank's equal share of a ``torch.distributed`` group, the forward is sharded as well: each rank
+        computes the denominators of its own rows / columns and one small all-gather completes the loss."""
         assert feat_A.shape == feat_B.shape, (feat_A.shape, feat_B.shape)  # losses.py:199
         N = feat_A.shape[0]
         begin, end = (0, N) if local_rows is None else local_rows
+        sharded = _use_sharded_forward(N, begin, end, group)
+        margin = self.margin if self.margin > 0 else 0.0  # losses.py:227: the margin applies only when positive
         if self.temperature_trainable:
-            return _MaskedNceFn.apply(feat_A, feat_B, self.temperature, index, 0.0, self.margin, self.dcl,
-                                      self.a2b, self.b2a, begin, end)
-        return _MaskedNceFn.apply(feat_A, feat_B, None, index, float(self.temperature), self.margin, self.dcl,
-                                  self.a2b, self.b2a, begin, end)
+            return _MaskedNceFn.apply(feat_A, feat_B, self.temperature, index, 0.0, margin, self.dcl,
+                                      self.a2b, self.b2a, begin, end, group, sharded)
+        return _MaskedNceFn.apply(feat_A, feat_B, None, index, float(self.temperature), margin, self.dcl,
+                                  self.a2b, self.b2a, begin, end, group, sharded)

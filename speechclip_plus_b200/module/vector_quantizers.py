@@ -17,6 +17,7 @@ from __future__ import annotations
 import ast
 import ctypes
 import logging
+import threading
 from typing import Dict, Optional, Sequence, Tuple
 
 import torch
@@ -40,48 +41,60 @@ def _masked_array(prob_msk: Sequence[int], V: int):
     return arr, len(cols)
 
 
+class TableEntry:
+    """Immutable per-device snapshot of the prepared token table (what one fused VQ call needs)."""
+    __slots__ = ("key", "table", "hat", "hat_t", "norm", "mean", "V", "D", "Vp")
+
+    def __init__(self, key, table, hat, hat_t, norm, mean, V, D, Vp):
+        self.key, self.table, self.hat, self.hat_t, self.norm, self.mean = key, table, hat, hat_t, norm, mean
+        self.V, self.D, self.Vp = V, D, Vp
+
+
 class TokenTableCache:
     """fp16 unit-norm copy of the frozen CLIP token table (+ transpose, norms, mean), rebuilt only when the table
     tensor changes (data pointer / version counter / shape).  The table is frozen in the reference
-    (kw_branches.py:194 asserts requires_grad == False), so in steady state this costs nothing per step."""
+    (kw_branches.py:194 asserts requires_grad == False), so in steady state this costs nothing per step.
+
+    One entry PER DEVICE behind a lock: ``nn.DataParallel`` replicas are shallow copies that share this object and call
+    ``get`` concurrently from one thread per GPU (SURVEY.md section 8(b) "Threading"); ``get`` returns an immutable
+    :class:`TableEntry`, so a replica can never observe another device's pointers."""
 
     def __init__(self):
-        self._key = None
-        self.table = None
-        self.hat = self.hat_t = self.norm = self.mean = None
-        self.V = self.D = self.Vp = 0
+        self._entries = {}
+        self._lock = threading.Lock()
 
-    def get(self, table: torch.Tensor) -> "TokenTableCache":
+    def get(self, table: torch.Tensor) -> TableEntry:
         _lib.require_cuda(table, "token table")
         key = (table.data_ptr(), table._version, tuple(table.shape), table.dtype, table.device)
-        if key == self._key:
-            return self
-        lib = _lib.load()
-        src = table.detach()
-        if src.dtype != torch.float32 or not src.is_contiguous():
-            src = src.float().contiguous()
-        V, D = src.shape
-        Vp = int(lib.scp_vq_padded_vocab(V))
-        dev = src.device
-        self.hat = torch.empty((Vp, D), dtype=torch.float16, device=dev)
-        self.hat_t = torch.empty((D, Vp), dtype=torch.float16, device=dev)
-        self.norm = torch.empty(Vp, dtype=torch.float32, device=dev)
-        self.mean = torch.empty(D + 1, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            st = lib.scp_vq_prepare_table(_lib.ptr(src), V, D, _lib.ptr(self.hat), _lib.ptr(self.hat_t),
-                                          _lib.ptr(self.norm), _lib.ptr(self.mean), _lib.stream_ptr(dev))
-        _lib.check(st, "scp_vq_prepare_table")
-        self.table = src
-        self.V, self.D, self.Vp = V, D, Vp
-        self._key = key
-        return self
+        with self._lock:
+            entry = self._entries.get(table.device)
+            if entry is not None and entry.key == key:
+                return entry
+            lib = _lib.load()
+            src = table.detach()
+            if src.dtype != torch.float32 or not src.is_contiguous():
+                src = src.float().contiguous()
+            V, D = src.shape
+            Vp = int(lib.scp_vq_padded_vocab(V))
+            dev = src.device
+            hat = torch.empty((Vp, D), dtype=torch.float16, device=dev)
+            hat_t = torch.empty((D, Vp), dtype=torch.float16, device=dev)
+            norm = torch.empty(Vp, dtype=torch.float32, device=dev)
+            mean = torch.empty(D + 1, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                st = lib.scp_vq_prepare_table(_lib.ptr(src), V, D, _lib.ptr(hat), _lib.ptr(hat_t), _lib.ptr(norm),
+                                              _lib.ptr(mean), _lib.stream_ptr(dev))
+            _lib.check(st, "scp_vq_prepare_table")
+            entry = TableEntry(key, src, hat, hat_t, norm, mean, V, D, Vp)
+            self._entries[table.device] = entry
+            return entry
 
 
 class _FusedVQFn(torch.autograd.Function):
     """keywords_out, idx, metrics, avg_probs, code_hist = f(keywords_in, tau)."""
 
     @staticmethod
-    def forward(ctx, kw: torch.Tensor, tau: torch.Tensor, cache: TokenTableCache, prob_msk, training: bool,
+    def forward(ctx, kw: torch.Tensor, tau: torch.Tensor, cache: TableEntry, prob_msk, training: bool,
                 want_avg_probs: bool):
         lib = _lib.load()
         B, K, D = kw.shape
@@ -244,8 +257,7 @@ class SimpleVectorQuantizer(nn.Module):
         if self.groundTruthPerplexity is not None:
             self.perplexity_criteria = nn.MSELoss()
         self._table_cache = TokenTableCache()
-        self._temp_float_key = None
-        self._temp_float = None
+        self._temp_float_cache = {}  # device -> (key, value); DataParallel replicas share this dict
 
     def set_num_updates(self, num_updates):
         if self.temp_type == "scheduled":  # :58-62
@@ -258,10 +270,11 @@ class SimpleVectorQuantizer(nn.Module):
         fixed / scheduled temperature the value is cached per tensor version, so no sync happens in steady state."""
         t = self.curr_temp
         key = (t.data_ptr(), t._version)
-        if self.temp_type == "learnable" or key != self._temp_float_key:
-            self._temp_float = float(t.detach().reshape(-1)[0].item())
-            self._temp_float_key = key
-        return self._temp_float
+        hit = self._temp_float_cache.get(t.device)
+        if self.temp_type == "learnable" or hit is None or hit[0] != key:
+            hit = (key, float(t.detach().reshape(-1)[0].item()))
+            self._temp_float_cache[t.device] = hit  # one atomic dict store: safe across replica threads
+        return hit[1]
 
     def _finish(self, result: Dict, metrics: torch.Tensor, K: int) -> Dict:
         result["code_perplexity"] = metrics[0]

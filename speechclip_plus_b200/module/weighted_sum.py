@@ -49,6 +49,7 @@ class _WeightedSumFn(torch.autograd.Function):
         _lib.require_cuda(x0, "WeightedSumLayer")
         lead_shape = x0.shape[:-1]
         D = x0.shape[-1]
+        in_shapes = [l.shape for l in layers]  # the callers' shapes: layer gradients are returned in them
         if x0.dim() != 3:  # (..., D) -> (1, R, D)
             layers = tuple(l.reshape(1, -1, D) for l in layers)
         views = _uniform_views(layers)
@@ -72,7 +73,7 @@ class _WeightedSumFn(torch.autograd.Function):
         ctx.utt_scale = utt_scale
         ctx.save_for_backward(w, *views)
         ctx.lead_shape = lead_shape
-        ctx.in_shapes = [l.shape for l in layers]
+        ctx.in_shapes = in_shapes
         return y.reshape(*lead_shape, D)
 
     @staticmethod

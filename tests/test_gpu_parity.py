@@ -619,6 +619,56 @@ def test_vq_full_size_properties(scp, cfg):
     assert torch.isfinite(gk).all()
 
 
+@pytest.mark.parametrize("cfg", [(256, 8, 49408, 512), (128, 8, 49408, 768), (128, 12, 49408, 512)],
+                         ids=["c3_base_M2048_D512", "c5_large_M1024_D768", "c4_dynamicK_M1536_D512"])
+def test_vq_full_size_vs_fp64_oracle(scp, cfg):
+    """BASELINE configs 3 / 5 / 4 at their per-GPU sizes against the oracle itself (not properties): the oracle's
+    restatement of my_vector_quantizer.py:64-165 + kw_branches.py:158-197 is evaluated in fp64 ON THE GPU (the (M,V)
+    fp64 matrices of the reference algorithm need ~6 GB, which no CPU test box should be asked for): all indices
+    (tie-tolerant), code / prob perplexity, ent_per_t, diversity_loss, avg_probs, the looked-up keywords and the
+    keyword gradient.  The fp16 e^c scratch, the closed-form prob_perplexity renormalisation and the depth of the
+    split-K / pipeline partial sums all change with M and V: this is where they are verified."""
+    B, K, V, D = cfg
+    dev = torch.device("cuda")
+    gen = torch.Generator(device=dev).manual_seed(V + B * K + D)
+    table = torch.randn(V, D, device=dev, generator=gen) * 0.02 + 0.003 * torch.randn(1, D, device=dev, generator=gen)
+    kw = torch.randn(B, K, D, device=dev, generator=gen) * table.std(0) + table.mean(0)
+    flat = kw.view(-1, D)
+    n_peak = flat[::7].shape[0]    # a seventh of the rows sit on a table row: sharply peaked softmax_tau rows
+    flat[::7] = table[torch.randint(4, V, (n_peak,), device=dev, generator=gen)] * 1.7 + 0.002 * torch.randn(
+        n_peak, D, device=dev, generator=gen)
+    gout = torch.randn(B, K, D, device=dev, generator=gen)
+    tau = 0.1
+    vq = _make_vq(scp, f"fixed={tau}", True)
+    kwd = kw.clone().requires_grad_(True)
+    res, out = vq.quantize_keywords(kwd, table)
+    (gk,) = torch.autograd.grad(out, [kwd], grad_outputs=gout)
+    t64 = torch.tensor([tau], dtype=torch.float64, device=dev)
+    ref, out_ref = oracle.vq_audio_features(kw.double(), table.double(), t64, training=True)
+    # indices: bit-exact except ties below fp32 summation noise (judged on the oracle's own fp64 scores)
+    idx = res["targets"].view(-1)
+    ridx = ref["targets"].view(-1)
+    bad = (idx != ridx).nonzero().flatten()
+    scores = ref["masked_scores"].view(-1, V)
+    for m in bad.tolist():
+        gap = (scores[m, ridx[m]] - scores[m, idx[m]]).item()
+        assert gap < 3e-7, f"row {m}: picked {idx[m].item()} instead of {ridx[m].item()}, cosine gap {gap:.3e}"
+    assert bad.numel() <= 2
+    assert rel_err(out, out_ref) < TOL if bad.numel() == 0 else True
+    for key in ("code_perplexity", "prob_perplexity", "ent_per_t", "diversity_loss"):
+        assert rel_err(res[key], ref[key]) < TOL, key
+    assert rel_err(res["avg_probs"], ref["avg_probs"]) < TOL
+    assert norm_err(res["avg_probs"], ref["avg_probs"]) < TOL
+    del ref, out_ref, scores
+    g_ref, _ = oracle.vq_keyword_grad(kw.double(), table.double(), t64.reshape(()), gout.double())
+    assert norm_err(gk, g_ref) < TOL
+    # row-wise as well: a peaked row's gradient is orders of magnitude smaller than a diffuse row's and would hide in
+    # the global norm (floor: 1e-3 of the largest row norm)
+    gr = g_ref.view(-1, D)
+    row = (gk.view(-1, D).double() - gr).norm(dim=1) / (gr.norm(dim=1) + 1e-3 * gr.norm(dim=1).max())
+    assert row.max().item() < 5 * TOL, row.max().item()
+
+
 # =====================================================================================================================
 # S3 masked InfoNCE, N0 normalise + pack, C0 compute_loss
 # =====================================================================================================================
@@ -662,6 +712,41 @@ def test_nce_vs_oracle(scp, N, D):
     assert rel_err(loss, l_ref) < TOL
     assert norm_err(ga, da) < TOL and norm_err(gb, db) < TOL
     assert rel_err(gt, dl) < TOL
+
+
+@pytest.mark.parametrize("N,D,world", [(256, 512, 2), (1024, 512, 8), (2048, 512, 8), (512, 768, 4), (66, 64, 2)])
+def test_nce_sharded_forward_matches_full(scp, N, D, world):
+    """SURVEY section 8(e) option B on ONE device: every rank's shard call (scp_nce_fwd_local on rows [r n, (r+1) n)) is
+    issued in turn, the (3, n) statistics are concatenated as the all-gather would deliver them, and
+    scp_nce_loss_from_stats must reproduce the loss / lse_row / lse_col of the full forward (losses.py:224-243)."""
+    from speechclip_plus_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    gen = torch.Generator(device=dev).manual_seed(N + D)
+    a = torch.nn.functional.normalize(torch.randn(N, D, device=dev, generator=gen), dim=-1)
+    b = torch.nn.functional.normalize(torch.randn(N, D, device=dev, generator=gen), dim=-1)
+    ids = torch.randint(0, max(N // 5, 2), (N,), device=dev, generator=gen)
+    ls = torch.tensor([math.log(1 / 0.07)], device=dev)
+    n = N // world
+    stream = _lib.stream_ptr(dev)
+    ws_b = lib.scp_nce_workspace_bytes(N, D)
+    ws = torch.empty(ws_b, dtype=torch.uint8, device=dev)
+    loss_f = torch.empty(1, device=dev); lr_f = torch.empty(N, device=dev); lc_f = torch.empty(N, device=dev)
+    _lib.check(lib.scp_nce_fwd(_lib.ptr(a), _lib.ptr(b), _lib.ptr(ids), N, D, _lib.ptr(ls), 0.0, 0.0, 0, 1, 1, 0,
+                               _lib.ptr(loss_f), _lib.ptr(lr_f), _lib.ptr(lc_f), _lib.ptr(ws), ws_b, stream), "fwd")
+    stats_all = torch.empty((world, 3, n), device=dev)
+    for r in range(world):
+        _lib.check(lib.scp_nce_fwd_local(_lib.ptr(a), _lib.ptr(b), _lib.ptr(ids), N, D, _lib.ptr(ls), 0.0, 0.0, 0,
+                                         r * n, (r + 1) * n, 0, _lib.ptr(stats_all[r]), _lib.ptr(ws), ws_b, stream),
+                   "fwd_local")
+    loss_s = torch.empty(1, device=dev); lr_s = torch.empty(N, device=dev); lc_s = torch.empty(N, device=dev)
+    _lib.check(lib.scp_nce_loss_from_stats(_lib.ptr(stats_all), world, n, _lib.ptr(ls), 0.0, 0.0, 1, 1,
+                                           _lib.ptr(loss_s), _lib.ptr(lr_s), _lib.ptr(lc_s), stream), "loss_from_stats")
+    torch.cuda.synchronize()
+    ref = oracle.nce_forward(a.double().cpu(), b.double().cpu(), ids.cpu(), 1 / 0.07)
+    assert rel_err(loss_s, ref.reshape(1)) < 1e-5
+    assert rel_err(loss_s, loss_f) < 1e-6
+    assert rel_err(lr_s, lr_f) < 1e-6 and rel_err(lc_s, lc_f) < 1e-6
 
 
 def test_nce_local_rows_match_full(scp):

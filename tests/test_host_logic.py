@@ -157,6 +157,11 @@ def test_compute_loss_key_contract():
     out = scp.compute_loss(feats, fake_criterion, 1.5, 0.5)
     assert set(out) == {"loss", "c_cl_loss", "p_cl_loss"} and math.isclose(float(out["loss"]), 2.0)
     out = scp.compute_loss(feats, fake_criterion, 0.0, 1.0, local_rows=(0, 2))
-    assert set(out) == {"loss", "p_cl_loss"} and calls[-1][2] == {"local_rows": (0, 2)}
+    assert set(out) == {"loss", "p_cl_loss"} and calls[-1][2] == {"local_rows": (0, 2), "group": None}
+    # quantity loss (kwClip.py:1030-1038): single process -> plain sum with the weight
+    feats_q = dict(feats, cif_quantity_out=torch.tensor([1.0, 2.0]), cif_target_len=torch.tensor([2.0, 4.0]))
+    out = scp.compute_loss(feats_q, fake_criterion, 1.0, 0.0, quantity_loss_weight=0.5,
+                           quantity_loss_criteria=torch.nn.L1Loss())
+    assert set(out) == {"loss", "c_cl_loss", "quantity_loss"} and math.isclose(float(out["loss"]), 1.0 + 0.5 * 1.5)
     with pytest.raises(AssertionError):
         scp.compute_loss({"id": torch.arange(4)}, fake_criterion, 1.0, 0.0)        # kwClip.py:1006-1010

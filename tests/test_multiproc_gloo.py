@@ -68,6 +68,41 @@ def _worker(rank: int, world: int, port: int, result_dir: str):
         averaged_scaled = summed / world * kw_glue.ddp_grad_scale(world)
         p_ref = (g_all * audio).sum()
         assert abs(averaged_scaled.item() - p_ref.item()) < 1e-6 * max(1.0, abs(p_ref.item()))
+        # ---- sharded forward (SURVEY section 8(e) option B): each rank evaluates the denominators of its own rows and
+        #      columns (losses.py:224-243 per shard), the ranks exchange (3, n) statistics with the product's gather
+        from speechclip_plus_b200.module import losses as scp_losses
+        A, Bm = oracle.l2_normalise(audio), oracle.l2_normalise(image)
+        scale = 1 / 0.07
+        S = A @ Bm.t() * scale
+        mask = oracle.nce_mask(ids, N)
+        neg_inf = torch.full_like(S, float("-inf"))
+        lse_row_loc = torch.logsumexp(torch.where(mask, S, neg_inf)[r0:r1], dim=1)        # local rows of A vs all B
+        lse_col_loc = torch.logsumexp(torch.where(mask, S, neg_inf)[:, r0:r1], dim=0)     # local rows of B vs all A
+        pos_loc = (A[r0:r1] * Bm[r0:r1]).sum(-1)
+        stats = torch.stack([lse_row_loc, lse_col_loc, pos_loc]).float()
+        stats_all = scp_losses.all_gather_stats(stats, world)
+        assert stats_all.shape == (world, 3, n)
+        lr = stats_all[:, 0].reshape(-1).double()
+        lc = stats_all[:, 1].reshape(-1).double()
+        ps = stats_all[:, 2].reshape(-1).double() * scale
+        loss_sharded = 0.5 * ((lr - ps).mean() + (lc - ps).mean())
+        assert abs(loss_sharded.item() - ref.item()) < 1e-5
+        assert scp_losses._use_sharded_forward(N, r0, r1, None)
+        assert not scp_losses._use_sharded_forward(N, 0, N, None)
+        # ---- CIF quantity loss on the multi-rank path: value = global mean, gradient = reference's after the
+        #      ddp_grad_scale * mean-over-ranks recipe (kwClip.py:1031-1038)
+        w = torch.tensor(0.7, dtype=torch.float64, requires_grad=True)     # a parameter shared by every rank
+        xq = torch.randn(N, generator=gen, dtype=torch.float64)
+        tgt = torch.randn(N, generator=gen, dtype=torch.float64)
+        q_local = torch.nn.functional.l1_loss(w * xq[r0:r1], tgt[r0:r1])
+        q = kw_glue.global_mean_with_local_grad(q_local)
+        q_ref = torch.nn.functional.l1_loss(w * xq, tgt)
+        assert abs(q.item() - q_ref.item()) < 1e-12
+        (gw,) = torch.autograd.grad(q * kw_glue.ddp_grad_scale(world), [w])
+        dist.all_reduce(gw)
+        gw = gw / world                                                     # DDP averages
+        (gw_ref,) = torch.autograd.grad(q_ref, [w])
+        assert abs(gw.item() - gw_ref.item()) < 1e-12
         open(os.path.join(result_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
