@@ -7,6 +7,10 @@ The reference resolves the three hot-path classes by name on Python modules:
   * the cosine + lookup glue is a method of ``GeneralBranch``     avssl/model/kw_branches.py:158-197
   * ``Kw_BatchNorm`` / ``Kw_BatchNorm_dynamic`` imported by name  avssl/model/kw_branches.py:19, :95, :629
   * ``CIF`` imported by name                                      avssl/model/kw_branches.py:17, :617
+and, so that the glue between those modules is on the path too (model/kwclip_glue.py):
+  * ``KWClip_GeneralTransformer.compute_loss`` / ``.forward``     avssl/model/kwClip.py:999-1040, :839-960  (N0, G0, C0)
+  * ``FairseqSpeechEncoder_Hubert.forward`` / ``S3prlSpeechEncoderPlus.forward``  speech_encoder_plus.py:520-640, :240-311 (S1')
+  * ``ClipModel.__init__``                                        avssl/module/clip_official.py:30-108  (N2)
 
 ``install()`` must run after ``import avssl`` and before the model is constructed.
 """
@@ -16,8 +20,11 @@ import importlib
 import sys
 
 
-def install(avssl_package: str = "avssl", strict: bool = False) -> dict:
-    """Swap the reference classes for the CUDA-backed ones.  Returns {dotted name: replaced?}."""
+def install(avssl_package: str = "avssl", strict: bool = False, fuse_forward: bool = True) -> dict:
+    """Swap the reference classes for the CUDA-backed ones.  Returns {dotted name: replaced?}.
+
+    ``fuse_forward=False`` keeps the reference's own ``KWClip_GeneralTransformer.forward`` (its three feature
+    normalisations then run as torch ops and the pack kernel re-normalises unit rows, which is the identity)."""
     from .module.losses import MaskedContrastiveLoss
     from .module.vector_quantizers import SimpleVectorQuantizer, fused_vq_audio_features
     from .module.weighted_sum import WeightedSumLayer
@@ -72,4 +79,35 @@ def install(avssl_package: str = "avssl", strict: bool = False) -> dict:
         if strict:
             raise
         done[f"{p}.model.kw_branches.GeneralBranch.vq_audio_features"] = False
+
+    # ---- the glue around the modules: loss (N0 + G0 + C0), upstream tail (S1'), vocabulary reduction (N2)
+    from .model import kwclip_glue
+
+    def patch_method(mod_name: str, cls_name: str, attr: str, make) -> None:
+        key = f"{mod_name}.{cls_name}.{attr}"
+        try:
+            mod = sys.modules.get(mod_name) or importlib.import_module(mod_name)
+            cls = getattr(mod, cls_name)
+            current = cls.__dict__[attr] if attr in cls.__dict__ else getattr(cls, attr)
+            if getattr(current, "_scp_installed", False):  # install() twice: do not wrap the wrapper
+                done[key] = True
+                return
+            new = make(current)
+            new._scp_installed = True
+            new._scp_original = current
+            setattr(cls, attr, new)
+            done[key] = True
+        except Exception:
+            if strict:
+                raise
+            done[key] = False
+
+    patch_method(f"{p}.model.kwClip", "KWClip_GeneralTransformer", "compute_loss",
+                 lambda cur: (lambda self, inputDict: kwclip_glue.kwclip_compute_loss(self, inputDict)))
+    if fuse_forward:
+        patch_method(f"{p}.model.kwClip", "KWClip_GeneralTransformer", "forward",
+                     lambda cur: (lambda self, batch: kwclip_glue.kwclip_forward(self, batch)))
+    for cls_name in ("FairseqSpeechEncoder_Hubert", "S3prlSpeechEncoderPlus"):
+        patch_method(f"{p}.module.speech_encoder_plus", cls_name, "forward", kwclip_glue.fused_upstream_forward)
+    patch_method(f"{p}.module.clip_official", "ClipModel", "__init__", kwclip_glue.clipmodel_init)
     return done

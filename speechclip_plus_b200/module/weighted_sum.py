@@ -122,8 +122,16 @@ class WeightedSumLayer(nn.Module):
         self.normalize_features = normalize_features
         if self.normalize_features:
             logger.info("Normalize feature before weighted sum")
+        # set (transiently) by the wrapped upstream forward of install(): the caller's per-layer method1 / method2
+        # rescale (speech_encoder_plus.py:572-592) is applied by this layer's kernel instead of a Python loop
+        self.upstream_norm_mode = None
 
     def forward(self, x: List[torch.Tensor]) -> torch.Tensor:
         assert len(x) == self.n_weights, len(x)  # weighted_sum.py:36
         mode = NORM_MODES[self.normalize_type] if self.normalize_features else _lib.SCP_NORM_NONE
+        forced = getattr(self, "upstream_norm_mode", None)
+        if forced is not None:
+            if self.normalize_features:  # the reference builds the layer without the LayerNorm flag in this case (:472-476)
+                raise _lib.ScpError("normalize_type=method1/method2 excludes the LayerNorm flag of the WeightedSumLayer")
+            mode = forced
         return _WeightedSumFn.apply(self.weights, mode, *x)
