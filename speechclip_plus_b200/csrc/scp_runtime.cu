@@ -129,6 +129,33 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols
   if (r != CUDA_SUCCESS) return fail(SCP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return SCP_OK;
 }
+// 3-D view of a row-major fp16 matrix (rows, 64*n_blocks) with row pitch `ld` elements, for MN-major operands:
+//   dim0 = 64 contiguous elements of one row, dim1 = row, dim2 = 64-element column block.
+// One box {64, box_rows, box_blocks} lands in shared memory as [block][row][64] -- 8 KB (box_rows = 64) SWIZZLE_128B
+// tiles one after the other, which is the layout the MN-major UMMA descriptor walks with LBO = box_rows * 128 B.
+// Coordinates of a load: {0, first row, first block}.
+int make_tmap_f16_blocked(CUtensorMap* out, const void* base, int64_t rows, int64_t n_blocks, int64_t ld, int box_rows,
+                          int box_blocks) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return fail(SCP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  static thread_local bool context_bound = false;
+  if (!context_bound) {
+    if (cudaFree(nullptr) != cudaSuccess) return fail(SCP_ERR_CUDA, "could not initialise the CUDA context on this thread");
+    context_bound = true;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16 != 0 || box_rows < 1 || box_rows > 256 || box_blocks < 1 ||
+      box_blocks > n_blocks)
+    return fail(SCP_ERR_INVALID, "blocked tensor map: bad base / pitch / box");
+  const cuuint64_t gdim[3] = {(cuuint64_t)kChunkK, (cuuint64_t)rows, (cuuint64_t)n_blocks};
+  const cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)kChunkK * 2};
+  const cuuint32_t box[3] = {(cuuint32_t)kChunkK, (cuuint32_t)box_rows, (cuuint32_t)box_blocks};
+  const cuuint32_t estride[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estride,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SCP_ERR_CUDA, "cuTensorMapEncodeTiled (blocked) failed with CUresult %d", (int)r);
+  return SCP_OK;
+}
 }  // namespace tc
 
 }  // namespace scp

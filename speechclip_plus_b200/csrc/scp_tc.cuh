@@ -251,6 +251,24 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
                : "memory");
 }
 
+// 16-column variants (half the live registers of the x32 form)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
 // ---- UMMA --------------------------------------------------------------------------------------------------
 // shared-memory matrix descriptor of a K-major SWIZZLE_128B tile starting at `smem_addr` (see file header)
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
@@ -299,6 +317,15 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// 3-D variant of tma_load_2d_pair: coordinates {element, row, block}
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, int32_t c0, int32_t c1, int32_t c2,
+                                                 uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
   // default semantics (release at CTA scope): the TMEM reads were already completed by tcgen05.wait::ld, nothing has
   // to be published cluster-wide, and a .release.cluster arrive costs a full MEMBAR per tile
@@ -343,6 +370,9 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask)
 // ---- host: tensor maps ---------------------------------------------------------------------------------------
 // 2-D fp16 row-major (rows, cols) matrix with row pitch `ld` elements; box = {64, box_rows}; SWIZZLE_128B.
 int make_tmap_f16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+// 3-D (64 elements, row, 64-column block) view for MN-major operands: see scp_runtime.cu
+int make_tmap_f16_blocked(CUtensorMap* out, const void* base, int64_t rows, int64_t n_blocks, int64_t ld, int box_rows,
+                          int box_blocks);
 
 }  // namespace tc
 }  // namespace scp

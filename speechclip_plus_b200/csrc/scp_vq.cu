@@ -2,17 +2,23 @@
 // Replaces GeneralBranch.get_keyword_cosine_score + SimpleVectorQuantizer.forward + the lookup matmul of the
 // reference (avssl/model/kw_branches.py:158-197, avssl/module/speechclip_c_modules/my_vector_quantizer.py:64-165).
 //
-// Forward pipeline (the (M,V) logit matrix is never written to memory):
+// Forward pipeline (the (M,V) fp32 logit matrix is never written to memory):
 //   vq_prep_kw          kw fp32 -> unit rows in fp16 (A operand) + 1/||kw||
 //   sweep 1 (tcgen05)   S = khat * Ehat^T tile by tile; per row: running softmax statistics at temperature 1 and tau,
-//                       and the maximum of every 32-column chunk (fp16-product precision)
+//                       the maximum of every 32-column chunk (fp16-product precision) and, for the column sums of
+//                       avg_probs, e^c of every logit as fp16 (the one (M,V) scratch of the forward)
 //   vq_select           per row: chunks whose maximum is within the fp16 error bound of the row maximum are re-scored
 //                       EXACTLY (fp64 accumulation over the fp32 table) -> arg-max is bit-exact w.r.t. an exact cosine,
 //                       first index wins ties; combines the split statistics; gathers keywords = E[idx]; code histogram
-//   sweep 2 (tcgen05)   transposed product Ehat * khat^T so that the column sums  avg_probs[v] = mean_m softmax(x)[m,v]
-//                       (which need the row normaliser from sweep 1) are thread-serial
+//   vq_colsum           avg_probs[v] = mean_m e^c[m,v] / Z_m from the fp16 scratch (one HBM pass; default).
+//                       SCP_VQ_COLSUM=0 selects the older second tensor-core sweep instead (transposed product
+//                       Ehat * khat^T with thread-serial column sums, no scratch)
 //   vq_metrics          code_perplexity, prob_perplexity, diversity_loss, ent_per_t
-// Backward pipeline:
+// Backward pipeline (D = 128 / 256 / 512; scp_vq_pipe.cuh): ONE producer/consumer launch -- producer CTA pairs compute
+//   c = khat Ehat^T and T = ghat Ehat^T with one N = 256 MMA against a resident [khat | ghat] tile and emit P~, Q~ tiles
+//   into a small ring that stays in L2; consumer CTA pairs accumulate U = Q~ Ehat, W = P~ Ehat in TMEM -- then
+//   vq_bwd_pipe_finalize.  The (M,V) matrices P~, Q~ never reach HBM.
+// Backward pipeline (other D; SCP_VQ_BWD_PIPE=0):
 //   vq_bwd_prep         g_keywords -> unit rows fp16 + scale + centring constant
 //   sweep 3 (tcgen05)   two accumulators sharing Ehat tiles: S1 = khat Ehat^T, S2 = ghat Ehat^T;
 //                       P = softmax_tau row, Q = P * (T - s0); writes fp16 P~, Q~ and the row sums
@@ -1197,15 +1203,20 @@ struct VqBwdWs {
   // producer/consumer pipeline (scp_vq_pipe.cuh)
   int pipe_mode;  // 0 = two-kernel path, 1 = fused pipeline (ring in L2), 2 = the two roles as separate launches
   int NP, ring, uw_slots, sa, sc, MT, NVT;
-  unsigned int* flags;  // ready[NP] | done[NP]
+  unsigned int* flags;  // ready[NP][ring] | done[NP]
   size_t pipe_smem;
 };
 static int vq_out_bn(int64_t D) { return D % 256 == 0 ? 256 : (D % 128 == 0 ? 128 : 64); }
 
-// SCP_VQ_BWD_PIPE: 1 (default) fused pipeline, 2 the same roles as two launches through a full-size scratch, 0 the older
-// sweep-3 + gemm_out kernels (always used when D is not 128 / 256 / 512: the pipeline keeps a 128 x D fp16 tile resident)
+// SCP_VQ_BWD_PIPE: 0 (default) the sweep-3 + gemm_out kernels; 1 the producer/consumer pipeline of scp_vq_pipe.cuh
+// (D = 128 / 256 / 512: it keeps a 128 x D fp16 tile resident), 2 the same two roles as separate launches through a
+// full-size scratch.  Measured on B200 (M = 2048, V = 49408, D = 512, ncu launch times): two-kernel path 385 us with
+// 872 MB of DRAM traffic and a 460 MB workspace; pipeline 487 us with the (M,V) matrices confined to a 19 MB ring in L2
+// and a 56 MB workspace.  Both roles are bound by the bytes a CTA can keep in flight towards L2 (96 KB ring next to the
+// 128 KB resident operand), so giving each role half of the SMs halves its rate: the pipeline trades 25 % of time for
+// ~8x less memory and is therefore opt-in (profiles/README.md, round 2).
 static int vq_bwd_pipe_mode(int64_t D) {
-  static const int env = [] { const char* e = getenv("SCP_VQ_BWD_PIPE"); return e ? atoi(e) : 1; }();
+  static const int env = [] { const char* e = getenv("SCP_VQ_BWD_PIPE"); return e ? atoi(e) : 0; }();
   if (!(D == 128 || D == 256 || D == 512)) return 0;
   return env;
 }
@@ -1233,10 +1244,11 @@ static VqBwdWs vq_bwd_ws(void* base, int64_t M, int64_t V, int64_t D) {
     }
     const int KC = (int)(D / tc::kChunkK);
     const int smem_budget = tc::kMaxDynSmem - 1024 - pipe::kBarBytes;
-    w.sa = std::min(pipe::kMaxStages, (smem_budget - KC * tc::kXTileBytes - 1024) / tc::kXTileBytes);
+    const int prod_fixed = 1024;  // per-keyword vectors of the producer epilogue
+    w.sa = std::min(pipe::kMaxStages, (smem_budget - KC * tc::kXTileBytes - prod_fixed) / tc::kXTileBytes);
     const int c_stage = tc::kXTileBytes + (int)D * 64;
     w.sc = std::min(pipe::kMaxStages, smem_budget / c_stage);
-    const size_t prod = (size_t)KC * tc::kXTileBytes + (size_t)w.sa * tc::kXTileBytes + 1024;
+    const size_t prod = (size_t)KC * tc::kXTileBytes + (size_t)w.sa * tc::kXTileBytes + prod_fixed;
     const size_t cons = (size_t)w.sc * c_stage;
     w.pipe_smem = 1024 + pipe::kBarBytes + std::max(prod, cons);
     size_t off = 0;
@@ -1247,7 +1259,7 @@ static VqBwdWs vq_bwd_ws(void* base, int64_t M, int64_t V, int64_t D) {
     };
     w.g_hat = static_cast<__half*>(take((size_t)Mp * D * 2));
     w.g_aux = static_cast<float*>(take((size_t)Mp * 2 * 4));
-    w.flags = static_cast<unsigned int*>(take((size_t)2 * w.NP * 4));
+    w.flags = static_cast<unsigned int*>(take((size_t)w.NP * (w.ring + 1) * 4));
     const size_t slots = w.pipe_mode == 1 ? (size_t)w.NP * w.ring : (size_t)total;
     w.pq = static_cast<__half*>(take(slots * pipe::kSlotHalfs * 2));
     w.partials = static_cast<float*>(take((size_t)Mp * w.uw_slots * 8 * 16));
@@ -1497,7 +1509,7 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
   const MaskedCols mc = make_masked(masked_cols, n_masked);
 
   vq_bwd_prep_kernel<<<(unsigned)ceil_div(Mp, 8), 256, 0, s>>>(g_keywords, M, Mp, (int)D, table_mean, ws.g_hat, ws.g_aux,
-                                                               ws.pipe_mode ? ws.flags : nullptr, 2 * ws.NP);
+                                                               ws.pipe_mode ? ws.flags : nullptr, ws.NP * (ws.ring + 1));
   SCP_CUDA_LAUNCH_CHECK("vq_bwd_prep");
   if (ws.pipe_mode) {
     pipe::PipeMaps maps{};
@@ -1505,15 +1517,21 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
     if ((rc = tc::make_tmap_f16(&maps.kw, kw_hat, Mp, D, D, 128))) return rc;
     if ((rc = tc::make_tmap_f16(&maps.gh, ws.g_hat, Mp, D, D, 128))) return rc;
     const int64_t slots = ws.pipe_mode == 1 ? (int64_t)ws.NP * ws.ring : (int64_t)ws.MT * ws.NVT;
-    if ((rc = tc::make_tmap_f16(&maps.scr, ws.pq, slots * 512, 128, 128, 64))) return rc;
-    if ((rc = tc::make_tmap_f16(&maps.tab_mn, table_hat, Vp, D, D, 64))) return rc;
+    if ((rc = tc::make_tmap_f16_blocked(&maps.scr, ws.pq, slots * 512, 2, 128, 64, 2))) return rc;
+    {
+      const int n_mma = D > 256 ? 2 : 1;
+      const int nb = (int)(D / n_mma / 2 / 64);  // 64-column table blocks one CTA stages per MMA
+      if ((rc = tc::make_tmap_f16_blocked(&maps.tab_mn, table_hat, Vp, D / 64, D, 64, nb))) return rc;
+    }
     pipe::PipeParams pp{};
     pp.MT = ws.MT; pp.NVT = ws.NVT; pp.NP = ws.NP; pp.KC = (int)(D / tc::kChunkK); pp.D = (int)D; pp.V = (int)V;
     pp.M = M; pp.Mp = Mp;
     pp.fused = ws.pipe_mode == 1;
     pp.ring = ws.ring; pp.sa = ws.sa; pp.sc = ws.sc; pp.uw_slots = ws.uw_slots;
+    static const int pipe_dbg = [] { const char* e = getenv("SCP_PIPE_DEBUG"); return e ? atoi(e) : 0; }();
+    pp.debug = pipe_dbg;
     pp.scratch = ws.pq;
-    pp.ready = ws.flags; pp.done = ws.flags + ws.NP;
+    pp.ready = ws.flags; pp.done = ws.flags + (size_t)ws.NP * ws.ring;
     pp.row_stats = row_stats; pp.g_aux = ws.g_aux; pp.table_norm = table_norm; pp.table_mean = table_mean; pp.tau = tau;
     pp.sums = ws.partials; pp.uw = ws.uw; pp.mc = mc;
     auto kern = g_tau ? pipe::vq_bwd_pipe_kernel<true> : pipe::vq_bwd_pipe_kernel<false>;
@@ -1528,7 +1546,7 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
       pp.role = role;
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3((unsigned)(pp.fused ? 4 * ws.NP : 2 * ws.NP));
-      cfg.blockDim = dim3(tc::kGemmThreads);
+      cfg.blockDim = dim3(pipe::kPipeThreads);
       cfg.dynamicSmemBytes = ws.pipe_smem;
       cfg.stream = s;
       cudaLaunchAttribute attr[1];

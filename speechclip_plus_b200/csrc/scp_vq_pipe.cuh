@@ -20,8 +20,10 @@
 //
 // A pipeline owns a contiguous run of (keyword tile, vocabulary tile) steps; the ring (a few slots of 128 KB per pipeline,
 // ~19 MB in total) stays in L2, so the only DRAM traffic of the whole backward is the unit table and the small operands.
-// Hand-off: `ready[q]` (+1 per producer epilogue warp and step, release) / `done[q]` (+1 per step once the consumer's TMA
-// loads of the slot have landed, release); waits are acquire loads, bounded (trap after 4 s).  The two roles execute the
+// Hand-off: `ready[q][slot]` (+1 per producer epilogue warp each time the slot is written, release: the k-th use of a slot is
+// complete at 16 k -- a per-pipeline step counter would not do, the epilogue warps drift up to two steps apart) /
+// `done[q]` (+1 per step once the consumer's TMA loads of the slot have landed, release); waits are acquire loads, bounded
+// (trap after 4 s).  The two roles execute the
 // same number of MMA cycles per step (4 M V D FLOP each in total), so the split is 1:1.
 //
 // All CTAs are co-resident by construction (one CTA per SM, grid <= number of SMs); if some SMs are busy with another
@@ -41,8 +43,8 @@ struct PipeMaps {
   CUtensorMap tab_k;   // Ehat (Vp, D), box {64, 128}: producer A operand (K-major)
   CUtensorMap kw;      // khat (Mp, D), box {64, 128}: resident B operand, CTA 0
   CUtensorMap gh;      // ghat (Mp, D), box {64, 128}: resident B operand, CTA 1
-  CUtensorMap scr;     // ring / scratch viewed as (slots * 512, 128), box {64, 64}: consumer A operand (MN-major)
-  CUtensorMap tab_mn;  // Ehat (Vp, D), box {64, 64}: consumer B operand (MN-major)
+  CUtensorMap scr;     // ring / scratch (slots * 512, 128) as (64, row, 2 blocks), box {64, 64, 2}: consumer A operand
+  CUtensorMap tab_mn;  // Ehat (Vp, D) as (64, row, D/64 blocks), box {64, 64, nb}: consumer B operand (both MN-major)
 };
 
 struct PipeParams {
@@ -53,9 +55,10 @@ struct PipeParams {
   int ring;       // slots per pipeline (fused)
   int sa, sc;     // smem ring stages of the producer / consumer
   int uw_slots;   // max number of pipelines that share one keyword tile
+  int debug;      // timing ablations (env SCP_PIPE_DEBUG, results invalid): 1 no epilogue maths, 2 no MMAs, 4 no P~/Q~ stores
   __half* scratch;
-  unsigned int* ready;
-  unsigned int* done;
+  unsigned int* ready;      // [NP][ring]: per ring slot, +1 per producer epilogue warp each time the slot has been written
+  unsigned int* done;       // [NP]: steps whose slot the consumer has loaded
   const float* row_stats;   // (M,4): [1] = lse at tau
   const float* g_aux;       // (Mp,2): |g|, s0
   const float* table_norm;  // (Vp,)
@@ -110,7 +113,17 @@ __host__ __device__ constexpr uint32_t make_idesc_f16_pair_mn(int n) {
   return tc::make_idesc_f16_pair(n) | (1u << 15) | (1u << 16);
 }
 
-// Lane j of the warp receives sum over the 32 lanes of v[j] (transpose-reduce: 31 shuffles instead of 32 x 5).
+// ---- per-keyword sums over the vocabulary ------------------------------------------------------------------------------
+// The producer epilogue holds lane <-> vocabulary row, register <-> keyword column, so sum_v P~[m,v] is a CROSS-LANE sum.
+// Measured alternatives (B200, M = 2048, V = 49408, D = 512, producer alone on 148 SMs):
+//   * shuffle transpose-reduce per step (31 x {2 FSEL, SHFL, FADD} per quantity and 32 columns): FSEL + SHFL + FADD were
+//     49 % of the stall samples, 222 us;
+//   * staging the fp16 tile in shared memory and summing it with ones x tile on mma.sync (ldmatrix + HMMA.16816): 291 us --
+//     the legacy HMMA path shares the tensor pipe with the tcgen05 MMAs that keep it busy, so the epilogue stalls on it;
+//   * (this version) thread-private fp32 running sums, one packed add per column pair and quantity, reduced across lanes
+//     ONCE per keyword tile.  The 128 accumulator registers per thread come from setmaxnreg: the two single-lane warps
+//     (and two idle warps that complete their warpgroup) shrink to 40 registers, the eight epilogue warps grow to 232.
+// Lane j of the warp receives the sum over the 32 lanes of v[j] (31 shuffles instead of 32 x 5).
 template <int O>
 __device__ __forceinline__ void tr_step(float (&v)[32], int lane) {
   const bool up = (lane & O) != 0;
@@ -130,9 +143,22 @@ __device__ __forceinline__ float lane_column_sum(float (&v)[32], int lane) {
   tr_step<1>(v, lane);
   return v[0];
 }
+__device__ __forceinline__ float lane_column_sum2(const tc::f32x2 (&a)[16], int lane) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) tc::unpack2(a[i], v[2 * i], v[2 * i + 1]);
+  return lane_column_sum(v, lane);
+}
+constexpr int kPipeThreads = 384;      // 8 epilogue warps + TMA warp + MMA warp + 2 idle warps (whole warpgroups)
+constexpr int kRegsEpilogue = 232;     // 8 * 32 * 232 + 4 * 32 * 40 = 384 * 168: the launch-time allocation, redistributed
+constexpr int kRegsOther = 40;
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 template <bool WANT_TAU>
-__global__ void __launch_bounds__(tc::kGemmThreads, 1)
+__global__ void __launch_bounds__(kPipeThreads, 1)
 vq_bwd_pipe_kernel(const __grid_constant__ PipeMaps maps, const PipeParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -187,6 +213,8 @@ vq_bwd_pipe_kernel(const __grid_constant__ PipeMaps maps, const PipeParams p) {
     uint8_t* ring_a = data + (size_t)p.KC * tc::kXTileBytes;  // sa stages x 16 KB of Ehat rows
     float* vec_bias = reinterpret_cast<float*>(ring_a + (size_t)p.sa * tc::kXTileBytes);
     float* vec_ns0 = vec_bias + 128;
+    if (warp >= tc::kEpiWarps) {
+    setmaxnreg_dec<kRegsOther>();  // warpgroup 2 (TMA warp, MMA warp, two idle warps) hands its registers to the epilogue
     if (warp == tc::kProducerWarp) {
       if (lane == 0) {
         int stage = 0, prev_mt = -1;
@@ -229,8 +257,10 @@ vq_bwd_pipe_kernel(const __grid_constant__ PipeMaps maps, const PipeParams p) {
             const uint64_t b_desc = tc::make_kmajor_sw128_desc(tc::smem_u32(res_b + (size_t)kc * tc::kXTileBytes));
             const uint32_t d = tmem_base + (uint32_t)(as * 256);
 #pragma unroll
-            for (int k = 0; k < tc::kChunkK / tc::kUmmaK; ++k)
+            for (int k = 0; k < tc::kChunkK / tc::kUmmaK; ++k) {
+              if (p.debug & 2) continue;
               tc::umma_f16_pair(d, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+            }
             tc::umma_commit_pair_mc(&empty_bar[stage], kPairMask);
             if (++stage == p.sa) { stage = 0; phase ^= 1; }
           }
@@ -239,20 +269,37 @@ vq_bwd_pipe_kernel(const __grid_constant__ PipeMaps maps, const PipeParams p) {
           if (++as == 2) { as = 0; aphase ^= 1; }
         }
       }
+    }
     } else {
+      setmaxnreg_inc<kRegsEpilogue>();
       const int quad = warp & 3, half = warp >> 2;
       const int vrow = rank * 128 + quad * 32 + lane;  // row inside the step's 256 vocabulary rows
       const float k_tau = kLog2e / __ldg(p.tau);
       const float inv_norm_ref = 1.0f / __ldg(p.table_mean + p.D);
       const tc::f32x2 kt2 = tc::pack2(k_tau, k_tau);
       const int sum_stride = p.uw_slots * 8;
+      // running sums of this thread's vocabulary rows: [chunk group][column pair] (WANT_TAU: plain per-step reduction)
+      tc::f32x2 acc_q[WANT_TAU ? 1 : 2][16], acc_p[WANT_TAU ? 1 : 2][16];
       float sum_q[2] = {0.f, 0.f}, sum_p[2] = {0.f, 0.f}, sum_qc[2] = {0.f, 0.f}, sum_pc[2] = {0.f, 0.f};
+      if constexpr (!WANT_TAU) {
+#pragma unroll
+        for (int gi = 0; gi < 2; ++gi)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc_q[gi][i] = acc_p[gi][i] = tc::pack2(0.f, 0.f);
+      }
       int as = 0, prev_mt = -1;
       uint32_t aphase = 0;
+      float rv_next = t0 < t1 ? __ldg(p.table_norm + (t0 % p.NVT) * kStepV + vrow) : 0.f;
       auto flush_sums = [&](int mt) {
         const int slot_s = (q - pipe_of_step((long long)mt * p.NVT, total, p.NP)) * 8 + rank * 4 + quad;
 #pragma unroll
         for (int gi = 0; gi < 2; ++gi) {
+          if constexpr (!WANT_TAU) {  // the one cross-lane reduction of the keyword tile
+            sum_q[gi] = lane_column_sum2(acc_q[gi], lane);
+            sum_p[gi] = lane_column_sum2(acc_p[gi], lane);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc_q[gi][i] = acc_p[gi][i] = tc::pack2(0.f, 0.f);
+          }
           const int64_t m = (int64_t)mt * 128 + (half * 2 + gi) * 32 + lane;
           *reinterpret_cast<float4*>(p.sums + (m * sum_stride + slot_s) * 4) =
               make_float4(sum_q[gi], sum_p[gi], sum_qc[gi], sum_pc[gi]);
@@ -276,7 +323,8 @@ vq_bwd_pipe_kernel(const __grid_constant__ PipeMaps maps, const PipeParams p) {
         }
         const int v = vt * kStepV + vrow;  // < Vp
         const bool valid = v < p.V && !is_masked(p.mc, v);
-        const float rv = __ldg(p.table_norm + v) * inv_norm_ref;  // T' = (ghat . ehat_v) * |e_v| / norm_ref - s0
+        const float rv = rv_next * inv_norm_ref;  // T' = (ghat . ehat_v) * |e_v| / norm_ref - s0
+        if (t + 1 < t1) rv_next = __ldg(p.table_norm + ((t + 1) % p.NVT) * kStepV + vrow);  // fetched one step ahead
         const tc::f32x2 rv2 = tc::pack2(rv, rv);
         const int li = t - t0;
         if (p.fused && li >= p.ring) {  // the slot's previous occupant has been loaded by the consumer
@@ -287,86 +335,90 @@ vq_bwd_pipe_kernel(const __grid_constant__ PipeMaps maps, const PipeParams p) {
         tc::mbar_wait(&tfull_bar[as], aphase);
         tc::tc_fence_after();
         const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256);
-#pragma unroll 1
+#pragma unroll  // (fully unrolled: the running sums are indexed by gi and must stay in registers)
         for (int gi = 0; gi < 2; ++gi) {
           const int g = half * 2 + gi;
-          uint32_t rc[32], rt[32];
-          __syncwarp();
-          tc::tmem_ld32_issue(tbase + (uint32_t)(g * 32), rc);
-          tc::tmem_ld32_issue(tbase + (uint32_t)(128 + g * 32), rt);
-          tc::tmem_ld32_wait(rc);
-          tc::tmem_ld32_wait(rt);
-          if (gi == 1) {  // the accumulator set is in registers: hand it back to the MMA issuer before the maths
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (rank != 0) tc::mbar_arrive_cluster(tc::mapa_u32(&tempty_bar[as], 0));
-              else tc::mbar_arrive(&tempty_bar[as]);
-            }
-          }
-          float c[32], tq[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) { c[i] = __uint_as_float(rc[i]); tq[i] = __uint_as_float(rt[i]); }
-          float cw[WANT_TAU ? 32 : 1];
           __half* dq = slot + (size_t)vrow * 128 + g * 32;
-          if (valid) {
-            const uint32_t bsm = tc::smem_u32(vec_bias) + (uint32_t)(g * 128), ssm = tc::smem_u32(vec_ns0) + (uint32_t)(g * 128);
+          const uint32_t bsm = tc::smem_u32(vec_bias) + (uint32_t)(g * 128), ssm = tc::smem_u32(vec_ns0) + (uint32_t)(g * 128);
+          float tp[WANT_TAU ? 32 : 1], tqv[WANT_TAU ? 32 : 1], tpc[WANT_TAU ? 32 : 1], tqc[WANT_TAU ? 32 : 1];
 #pragma unroll
-            for (int hb = 0; hb < 2; ++hb) {  // 16 columns at a time: one 32-byte store per matrix
-              uint32_t hq[8], hp[8];
+          for (int hb = 0; hb < 2; ++hb) {  // 16 columns of c and of T at a time
+            uint32_t rc[16], rt[16];
+            __syncwarp();
+            if (!(p.debug & 8)) {
+              tc::tmem_ld16_issue(tbase + (uint32_t)(g * 32 + hb * 16), rc);
+              tc::tmem_ld16_issue(tbase + (uint32_t)(128 + g * 32 + hb * 16), rt);
+              tc::tmem_ld16_wait(rc);
+              tc::tmem_ld16_wait(rt);
+            } else {
 #pragma unroll
-              for (int i = 4 * hb; i < 4 * hb + 4; ++i) {
-                const float4 b4 = tc::lds128f(bsm + i * 16), s4 = tc::lds128f(ssm + i * 16);
+              for (int i = 0; i < 16; ++i) { rc[i] = (uint32_t)(i + lane); rt[i] = (uint32_t)(i * lane); }
+            }
+            if (gi == 1 && hb == 1) {  // the accumulator set is in registers: hand it back to the MMA issuer before the maths
+              tc::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (rank != 0) tc::mbar_arrive_cluster(tc::mapa_u32(&tempty_bar[as], 0));
+                else tc::mbar_arrive(&tempty_bar[as]);
+              }
+            }
+            uint32_t hq[8], hp[8];
+            if (p.debug & 1) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { hp[i] = rc[i]; hq[i] = rt[i]; }
+            } else if (valid) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {  // 4 columns per iteration
+                const float4 b4 = tc::lds128f(bsm + (4 * hb + i) * 16), s4 = tc::lds128f(ssm + (4 * hb + i) * 16);
                 const tc::f32x2 bb[2] = {tc::pack2(b4.x, b4.y), tc::pack2(b4.z, b4.w)};
                 const tc::f32x2 ss[2] = {tc::pack2(s4.x, s4.y), tc::pack2(s4.z, s4.w)};
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                  const int e = 4 * i + 2 * j;
-                  const tc::f32x2 cc = tc::pack2(c[e], c[e + 1]);
+                  const int e = 4 * i + 2 * j;       // column inside this half
+                  const int o = 8 * hb + (e >> 1);   // packed pair inside the chunk group
+                  const tc::f32x2 cc = tc::pack2(__uint_as_float(rc[e]), __uint_as_float(rc[e + 1]));
                   const tc::f32x2 pj = tc::ex2_2(tc::fma2(cc, kt2, bb[j]));
-                  const tc::f32x2 tj = tc::fma2(tc::pack2(tq[e], tq[e + 1]), rv2, ss[j]);
+                  const tc::f32x2 tj = tc::fma2(tc::pack2(__uint_as_float(rt[e]), __uint_as_float(rt[e + 1])), rv2, ss[j]);
                   const tc::f32x2 qj = tc::mul2(pj, tj);
-                  hp[(e >> 1) & 7] = tc::cvt_f16x2(pj);
-                  hq[(e >> 1) & 7] = tc::cvt_f16x2(qj);
-                  if constexpr (WANT_TAU) { cw[e] = c[e]; cw[e + 1] = c[e + 1]; }
-                  tc::unpack2(pj, c[e], c[e + 1]);    // c <- P~
-                  tc::unpack2(qj, tq[e], tq[e + 1]);  // tq <- Q~
+                  hp[e >> 1] = tc::cvt_f16x2(pj);
+                  hq[e >> 1] = tc::cvt_f16x2(qj);
+                  if constexpr (WANT_TAU) {  // also the c-weighted sums of the learnable-temperature gradient
+                    tc::unpack2(pj, tp[2 * o], tp[2 * o + 1]);
+                    tc::unpack2(qj, tqv[2 * o], tqv[2 * o + 1]);
+                    tc::unpack2(tc::mul2(pj, cc), tpc[2 * o], tpc[2 * o + 1]);
+                    tc::unpack2(tc::mul2(qj, cc), tqc[2 * o], tqc[2 * o + 1]);
+                  } else {
+                    acc_p[gi][o] = tc::add2(acc_p[gi][o], pj);
+                    acc_q[gi][o] = tc::add2(acc_q[gi][o], qj);
+                  }
                 }
               }
+            } else {  // masked / padding vocabulary row: contributes nothing
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { hp[i] = 0u; hq[i] = 0u; }
+              if constexpr (WANT_TAU) {
+#pragma unroll
+                for (int i = 16 * hb; i < 16 * hb + 16; ++i) tp[i] = tqv[i] = tpc[i] = tqc[i] = 0.f;
+              }
+            }
+            if (!(p.debug & 4)) {
               tc::stg256(dq + 16 * hb, hq);
               tc::stg256(dq + kSlotHalfs / 2 + 16 * hb, hp);
+            } else if (hq[0] == 0x12345678u && hp[3] == 0x9abcdef0u) {  // keep the values alive without storing them
+              tc::stg256(dq, hq);
             }
-          } else {  // masked / padding vocabulary row: contributes nothing
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { c[i] = 0.f; tq[i] = 0.f; }
-            if constexpr (WANT_TAU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) cw[i] = 0.f;
-            }
-            const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-            tc::stg256(dq, z);
-            tc::stg256(dq + 16, z);
-            tc::stg256(dq + kSlotHalfs / 2, z);
-            tc::stg256(dq + kSlotHalfs / 2 + 16, z);
           }
-          if constexpr (WANT_TAU) {
-            float pc[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) pc[i] = c[i] * cw[i];
-            sum_pc[gi] += lane_column_sum(pc, lane);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) pc[i] = tq[i] * cw[i];
-            sum_qc[gi] += lane_column_sum(pc, lane);
+          if constexpr (WANT_TAU) {  // rare path (no shipped recipe learns the VQ temperature): reduce every step
+            sum_p[gi] += lane_column_sum(tp, lane);
+            sum_q[gi] += lane_column_sum(tqv, lane);
+            sum_pc[gi] += lane_column_sum(tpc, lane);
+            sum_qc[gi] += lane_column_sum(tqc, lane);
           }
-          sum_p[gi] += lane_column_sum(c, lane);
-          sum_q[gi] += lane_column_sum(tq, lane);
         }
         if (p.fused) {  // publish this warp's part of the slot
+          // bar.warp.sync orders the 32 lanes' stores before lane 0's release (cumulativity): no blocking fence needed
           __syncwarp();
-          if (lane == 0) {
-            __threadfence();
-            red_release_gpu_add(p.ready + q, 1u);
-          }
+          if (lane == 0) red_release_gpu_add(p.ready + (size_t)q * p.ring + li % p.ring, 1u);
         }
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
@@ -382,6 +434,8 @@ vq_bwd_pipe_kernel(const __grid_constant__ PipeMaps maps, const PipeParams p) {
     const int nb = nh / 64;             // 64-column blocks of 8 KB
     const uint32_t stage_bytes = (uint32_t)tc::kXTileBytes + (uint32_t)p.D * 64u;
     uint8_t* ring = data;
+    if (warp >= tc::kEpiWarps) {
+    setmaxnreg_dec<kRegsOther>();
     if (warp == tc::kProducerWarp) {
       if (lane == 0) {
         int stage = 0;
@@ -391,7 +445,7 @@ vq_bwd_pipe_kernel(const __grid_constant__ PipeMaps maps, const PipeParams p) {
           const int li = t - t0;
           (void)mt;
           if (p.fused) {
-            spin_until_ge(p.ready + q, (unsigned)(kWarpsPerStep * (li + 1)));
+            spin_until_ge(p.ready + (size_t)q * p.ring + li % p.ring, (unsigned)(kWarpsPerStep * (li / p.ring + 1)));
             fence_proxy_async_all();  // the slot was written through the generic proxy, TMA reads through the async proxy
           }
           const long long slot = p.fused ? (long long)q * p.ring + li % p.ring : (long long)t;
@@ -401,13 +455,11 @@ vq_bwd_pipe_kernel(const __grid_constant__ PipeMaps maps, const PipeParams p) {
             const uint32_t lead_bar = tc::mapa_u32(&full_bar[stage], 0);
             uint8_t* st = ring + (size_t)stage * stage_bytes;
             const int srow = (int)(slot * 512 + rank * 256 + kc * 64);
-            tc::tma_load_2d_pair(st, &maps.scr, 0, srow, lead_bar);
-            tc::tma_load_2d_pair(st + 8192, &maps.scr, 64, srow, lead_bar);
+            tc::tma_load_3d_pair(st, &maps.scr, 0, srow, 0, lead_bar);  // both 64-keyword blocks: [block][v][64]
             const int vrow0 = vt * kStepV + kc * 64;
-            for (int h = 0; h < n_mma; ++h)
-              for (int b = 0; b < nb; ++b)
-                tc::tma_load_2d_pair(st + tc::kXTileBytes + (size_t)(h * nb + b) * 8192, &maps.tab_mn,
-                                     h * n_each + rank * nh + b * 64, vrow0, lead_bar);
+            for (int h = 0; h < n_mma; ++h)  // this CTA's nb 64-column blocks of MMA h
+              tc::tma_load_3d_pair(st + tc::kXTileBytes + (size_t)(h * nb) * 8192, &maps.tab_mn, 0, vrow0,
+                                   (h * n_each + rank * nh) / 64, lead_bar);
             if (++stage == p.sc) { stage = 0; phase ^= 1; }
           }
         }
@@ -436,6 +488,7 @@ vq_bwd_pipe_kernel(const __grid_constant__ PipeMaps maps, const PipeParams p) {
               const uint32_t acc = (seg_first && kc == 0 && k == 0) ? 0u : 1u;
               const uint64_t a_desc = make_mn_sw128_desc(sa + (uint32_t)k * 2048u, 8192u);
               for (int h = 0; h < n_mma; ++h) {
+                if (p.debug & 2) continue;
                 const uint64_t b_desc = make_mn_sw128_desc(sb + (uint32_t)(h * nb) * 8192u + (uint32_t)k * 2048u, 8192u);
                 tc::umma_f16_pair(tmem_base + (uint32_t)(h * n_each), a_desc, b_desc, idesc, acc);
               }
@@ -449,7 +502,9 @@ vq_bwd_pipe_kernel(const __grid_constant__ PipeMaps maps, const PipeParams p) {
           }
         }
       }
+    }
     } else {
+      setmaxnreg_inc<kRegsEpilogue>();
       const int quad = warp & 3, half = warp >> 2;
       if (t1 > t0) {
         const int mt_a = t0 / p.NVT, mt_b = (t1 - 1) / p.NVT;

@@ -103,6 +103,7 @@ class _NormPackGatherFn(torch.autograd.Function):
         ctx.in_dtypes = [f.dtype for f in feats]
         ctx.save_for_backward(inv, *[g[ctx.rows[0]:ctx.rows[1]] for g in g_feats])
         ctx.mark_non_differentiable(g_ids)
+        ctx.set_materialize_grads(False)  # unused outputs (ids, features of an inactive branch) get None, not zeros
         return (g_ids, *g_feats)
 
     @staticmethod
@@ -147,6 +148,21 @@ def gather_loss_feats(loss_feats: Dict[str, torch.Tensor], group=None) -> Tuple[
     return out, shard_rows(n, rank)
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
+def _overlap_enabled() -> bool:
+    import os
+    return os.environ.get("SCP_NCE_OVERLAP", "1") != "0"
+
+
 def _world(group) -> int:
     return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 
@@ -180,18 +196,38 @@ def compute_loss(loss_feats: Dict[str, torch.Tensor], criterion, cascaded_object
     losses = {"loss": 0}
     image_feat = loss_feats["image_feat"].float()
     ids = loss_feats["id"]
-    for branch, weight in (("cascaded", cascaded_objective_weight), ("parallel", parallel_objective_weight)):
-        if weight > 0.0:
-            key = f"{branch}_audio_feat"
-            assert key in loss_feats, f"{loss_feats.keys()}"
-            kwargs = {} if local_rows is None else {"local_rows": local_rows, "group": group}
-            losses[f"{branch[0]}_cl_loss"] = criterion(feat_A=loss_feats[key].float(), feat_B=image_feat, index=ids,
-                                                      **kwargs)
-            # `loss += weight * term` of the reference, without the no-op kernels for `0 + x` and `1.0 * x`
-            term = losses[f"{branch[0]}_cl_loss"]
-            if weight != 1.0:
-                term = weight * term
-            losses["loss"] = term if isinstance(losses["loss"], int) else losses["loss"] + term
+    active = [(branch, weight) for branch, weight in (("cascaded", cascaded_objective_weight),
+                                                      ("parallel", parallel_objective_weight)) if weight > 0.0]
+    kwargs = {} if local_rows is None else {"local_rows": local_rows, "group": group}
+    terms = {}
+    # Hybrid models call the criterion twice on the same image features and ids (kwClip.py:1015-1028).  Each call is a
+    # chain of short, latency-bound launches; the second chain runs on a helper stream next to the first (fork / join by
+    # events: capturable), and autograd replays each backward on the stream of its forward, so both directions overlap.
+    overlap = (len(active) == 2 and image_feat.is_cuda and _overlap_enabled())
+    side = _side_stream(image_feat.device) if overlap else None
+    def call(branch):
+        key = f"{branch}_audio_feat"
+        assert key in loss_feats, f"{loss_feats.keys()}"
+        return criterion(feat_A=loss_feats[key].float(), feat_B=image_feat, index=ids, **kwargs)
+
+    if side is not None:
+        main = torch.cuda.current_stream(image_feat.device)
+        side.wait_stream(main)                       # fork: everything issued so far (gather, normalise) is visible
+        with torch.cuda.stream(side):
+            terms[active[1][0]] = call(active[1][0])
+        terms[active[0][0]] = call(active[0][0])     # the first chain on the caller's stream, next to the second
+        main.wait_stream(side)                       # join
+        terms[active[1][0]].record_stream(main)
+    else:
+        for branch, _ in active:
+            terms[branch] = call(branch)
+    for branch, weight in active:
+        losses[f"{branch[0]}_cl_loss"] = terms[branch]
+        # `loss += weight * term` of the reference, without the no-op kernels for `0 + x` and `1.0 * x`
+        term = terms[branch]
+        if weight != 1.0:
+            term = weight * term
+        losses["loss"] = term if isinstance(losses["loss"], int) else losses["loss"] + term
     if ("cif_quantity_out" in loss_feats and "cif_target_len" in loss_feats and quantity_loss_criteria is not None):
         q_loss = quantity_loss_criteria(loss_feats["cif_quantity_out"], loss_feats["cif_target_len"])
         if local_rows is not None:

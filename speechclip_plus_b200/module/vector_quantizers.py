@@ -124,6 +124,7 @@ class _FusedVQFn(torch.autograd.Function):
                                 _lib.ptr(metrics), _lib.ptr(kw_hat), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
         _lib.check(st, "scp_vq_fwd")
         ctx.training = training
+        ctx.set_materialize_grads(False)  # five of the six outputs carry no gradient: do not zero-fill them per step
         if training:
             ctx.save_for_backward(kw2, kw_hat, row_stats, tau_f)
             ctx.cache = cache
@@ -147,6 +148,8 @@ class _FusedVQFn(torch.autograd.Function):
         kw2, kw_hat, row_stats, tau_f = ctx.saved_tensors
         cache = ctx.cache
         B, K, D = ctx.shape
+        if g_out is None:
+            return None, None, None, None, None, None
         M = B * K
         dev = kw2.device
         g = g_out.reshape(M, D).float().contiguous()

@@ -669,6 +669,22 @@ def test_vq_full_size_vs_fp64_oracle(scp, cfg):
     assert row.max().item() < 5 * TOL, row.max().item()
 
 
+@pytest.mark.parametrize("mode", ["1", "2"], ids=["fused_ring_in_L2", "two_launches"])
+def test_vq_backward_pipeline_opt_in(mode):
+    """The producer/consumer form of the VQ backward (csrc/scp_vq_pipe.cuh, SCP_VQ_BWD_PIPE=1/2: MN-major tcgen05 operands,
+    ring hand-off through release/acquire counters) against the fp64 oracle on the GPU, incl. the learnable-temperature
+    gradient.  The mode is read once per process, hence the subprocess; tools/vq_bwd_check.py exits non-zero when the keyword
+    gradient of any shape is off by more than 1e-3 (kw_branches.py:181-197 + my_vector_quantizer.py:130-136)."""
+    import subprocess
+    import sys
+    env = dict(os.environ, SCP_VQ_BWD_PIPE=mode)
+    for extra in ([], ["--learnable"]):
+        r = subprocess.run([sys.executable, os.path.join(ROOT_DIR, "tools", "vq_bwd_check.py"), "--shapes", "small", *extra],
+                           env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert f'"mode": "{mode}"' in r.stdout
+
+
 # =====================================================================================================================
 # S3 masked InfoNCE, N0 normalise + pack, C0 compute_loss
 # =====================================================================================================================
@@ -935,6 +951,125 @@ def test_cascaded_chain_golden(scp, name):
         assert norm_err(gr, g[f"grad_{k}"]) < TOL, k
 
 
+@pytest.mark.parametrize("which", ["reference_head64", "flickr_sized_8112"])
+def test_reduced_vocab_chain(scp, which, tmp_path):
+    """N2 end to end on the GPU (clip_official.py:63-108 -> kw_branches.py:158-197 -> clip_official.py:222-279): the
+    by-frequency usage table -> reduce_subword_embedding (through the installed ClipModel.__init__ wrapper) -> the fused VQ
+    against the REDUCED table with the quantiser's default prob_msk = [0, 2, 3] = pad / SOT / EOT of that table ->
+    encode_keywords spliced with the reduced SOT / EOT ids -> loss; every stage against the oracle on the reduced table.
+    `reference_head64`: the first 64 rows of the reference's own avssl/data/flickr_stat/text_clip_vocab_usage_byfreq.npy;
+    `flickr_sized_8112`: a synthetic table of the Flickr recipe's size."""
+    import types
+    import numpy as np
+    from speechclip_plus_b200.model import kwclip_glue
+    from speechclip_plus_b200.module.clip_glue import encode_keywords
+    V_full, D, B, K, L = 49408, 512, 16, 8, 77
+    gen = torch.Generator().manual_seed(99)
+    if which == "reference_head64":
+        usage = np.load(os.path.join(ROOT_DIR, "tests", "golden", "vocab_usage_byfreq_head64.npy"))
+    else:
+        rest = torch.randperm(V_full - 2, generator=gen)[:8112 - 4].numpy() + 1      # ids 1 .. 49406 (0 / SOT / EOT excluded)
+        rest = rest[(rest != 49406)][:8112 - 4]
+        ids = np.concatenate([[0, rest[0], 49406, 49407], rest[1:]])
+        counts = np.sort(torch.randint(1, 10 ** 6, (len(ids),), generator=gen).numpy())[::-1]
+        usage = np.stack([ids, counts], 1).astype(np.int64)
+    path = tmp_path / "usage.npy"
+    np.save(path, usage)
+    full = torch.randn(V_full, D, generator=gen) * 0.02
+
+    def base_init(self, name, device="cpu", image_encoder_trainable=False, text_encoder_trainable=False,
+                  reduce_subword_embbedding=None, **kw):
+        torch.nn.Module.__init__(self)
+        emb = torch.nn.Embedding.from_pretrained(full.clone()).cuda()
+
+        class Tower(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.mix = torch.nn.Linear(D, D)
+
+            def forward(self, x):  # (L, N, D): mixes the positions, like attention does, so that the EOT feature
+                return torch.tanh(self.mix(x) + x.mean(dim=0, keepdim=True))  # depends on the keyword positions
+
+        torch.manual_seed(3)
+        self.model = types.SimpleNamespace(token_embedding=emb, positional_embedding=(torch.randn(L, D) * 0.01).cuda(),
+                                           transformer=Tower().cuda(), ln_final=torch.nn.LayerNorm(D).cuda(),
+                                           text_projection=(torch.randn(D, D) * D ** -0.5).cuda())
+        self.text_encoder_trainable = text_encoder_trainable
+        self.tokenizer = types.SimpleNamespace(encoder={"<|startoftext|>": 49406, "<|endoftext|>": 49407})
+        self.selected_text_emb_ids = None
+        self.device = torch.device("cuda")
+
+    cls = type("ClipModelStandIn", (torch.nn.Module,), {"__init__": kwclip_glue.clipmodel_init(base_init),
+                                                        "encode_keywords": encode_keywords})
+    clip = cls("ViT-B/32", reduce_subword_embbedding=str(path))
+    Vr = len(usage)
+    table = clip.model.token_embedding.weight
+    assert table.shape == (Vr, D) and not table.requires_grad
+    assert torch.equal(table.cpu(), full[torch.from_numpy(usage[:, 0].copy())])
+    assert (clip.startOfTxt_reduced, clip.endOfTxt_reduced) == (2, 3) and clip.original2Reduced[0] == 0
+    # keywords near table rows, some of them near the masked pad / SOT / EOT rows (which must never be chosen)
+    pick = torch.randint(0, Vr, (B, K), generator=gen)
+    pick[:, 0] = torch.tensor([0, 2, 3] * B)[:B]
+    kw = (table.cpu()[pick] * 2.0 + 0.004 * torch.randn(B, K, D, generator=gen)).cuda().requires_grad_(True)
+    vq = scp.SimpleVectorQuantizer("fixed=0.1").cuda().train()
+    branch = types.SimpleNamespace(clip=clip, vector_quantizer=vq, project_feats_to_CLIPspace=lambda f: f)
+    res, keywords = scp.fused_vq_audio_features(branch, kw)                 # default prob_msk = [0, 2, 3]
+    ref, kw_ref = oracle.vq_audio_features(kw.detach().double().cpu(), table.double().cpu(), torch.tensor([0.1], dtype=torch.float64))
+    assert torch.equal(res["targets"].cpu(), ref["targets"])
+    assert not bool(((res["targets"] == 0) | (res["targets"] == 2) | (res["targets"] == 3)).any())
+    assert rel_err(keywords, kw_ref) < TOL
+    for key in ("code_perplexity", "prob_perplexity", "ent_per_t"):
+        assert rel_err(res[key], ref[key]) < TOL, key
+    out = clip.encode_keywords(keywords, K)
+    x_ref, eot_idx = oracle.splice_keywords(kw_ref.float(), K, table.cpu(), clip.model.positional_embedding.cpu(), 2, 3)
+    with torch.no_grad():
+        t = clip.model
+        y = t.ln_final(t.transformer(x_ref.cuda().permute(1, 0, 2)).permute(1, 0, 2))
+        out_ref = y[torch.arange(B), eot_idx.cuda()] @ t.text_projection
+    assert rel_err(out, out_ref) < TOL
+    crit = scp.MaskedContrastiveLoss(temperature=0.07, temperature_trainable=True).cuda()
+    img = torch.randn(B, D, generator=gen).cuda()
+    ids = torch.randint(0, 5, (B,), generator=gen).cuda()
+    gathered, rows = scp.gather_loss_feats({"id": ids, "image_feat": img, "cascaded_audio_feat": out})
+    loss = scp.compute_loss(gathered, crit, 1.0, 0.0)["loss"]
+    loss_ref = oracle.nce_forward(oracle.l2_normalise(out_ref.double().cpu()), oracle.l2_normalise(img.double().cpu()),
+                                  ids.cpu(), 1 / 0.07)
+    assert rel_err(loss, loss_ref) < TOL
+    (g_kw,) = torch.autograd.grad(loss, [kw])
+    assert torch.isfinite(g_kw).all() and g_kw.abs().sum() > 0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_vq_under_dataparallel_replicas(scp):
+    """The reference trains with strategy: dp (SURVEY section 8(b) "Threading"): nn.DataParallel replicas are shallow
+    copies that share the module's table cache and run concurrently, one thread per GPU.  Every replica must use ITS
+    device's prepared table (per-device cache entries behind a lock), and the gathered result must equal the
+    single-device one."""
+    B, K, V, D = 32, 8, 8112, 512
+    gen = torch.Generator().manual_seed(17)
+    table = (torch.randn(V, D, generator=gen) * 0.02)
+    kw = torch.randn(B, K, D, generator=gen) * 0.02
+
+    class Wrap(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.vq = scp.SimpleVectorQuantizer("fixed=0.1")
+            self.table = torch.nn.Parameter(table.clone(), requires_grad=False)
+
+        def forward(self, x):
+            res, out = self.vq.quantize_keywords(x, self.table)
+            return out, res["targets"]
+
+    m = Wrap().cuda(0).train()
+    single_out, single_idx = m(kw.cuda(0))
+    dp = torch.nn.DataParallel(m, device_ids=[0, 1])
+    for _ in range(3):  # repeated calls: the cache entries of both devices stay valid side by side
+        out, idx = dp(kw.cuda(0))
+        assert torch.equal(idx.cpu(), single_idx.cpu())
+        assert torch.equal(out.cpu(), single_out.cpu())
+    assert len(m.vq._table_cache._entries) == 2
+
+
 def test_install_patches_reference_namespaces(scp):
     import sys
     import types
@@ -945,9 +1080,14 @@ def test_install_patches_reference_namespaces(scp):
                  f"{pkg}.module.speechclip_c_modules.my_vector_quantizer",
                  f"{pkg}.module.speechclip_c_modules.vector_quantizers", f"{pkg}.module.speechclip_c_modules.kw_bn",
                  f"{pkg}.module.clip_official", f"{pkg}.module.cif", f"{pkg}.util", f"{pkg}.util.data_utils",
-                 f"{pkg}.model", f"{pkg}.model.kw_branches"]:
+                 f"{pkg}.model", f"{pkg}.model.kw_branches", f"{pkg}.model.kwClip"]:
         mods[name] = types.ModuleType(name)
         sys.modules[name] = mods[name]
+    # the classes whose methods install() wraps (model/kwclip_glue.py)
+    mods[f"{pkg}.model.kwClip"].KWClip_GeneralTransformer = type(
+        "KWClip_GeneralTransformer", (), {"compute_loss": lambda self, d: None, "forward": lambda self, b: None})
+    for cls_name in ("FairseqSpeechEncoder_Hubert", "S3prlSpeechEncoderPlus"):
+        setattr(mods[f"{pkg}.module.speech_encoder_plus"], cls_name, type(cls_name, (), {"forward": lambda self, wav: wav}))
 
     class GeneralBranch:  # noqa: D401
         pass
@@ -966,6 +1106,8 @@ def test_install_patches_reference_namespaces(scp):
         assert mods[f"{pkg}.module.speechclip_c_modules.kw_bn"].Kw_BatchNorm_dynamic is scp.Kw_BatchNorm_dynamic
         assert getattr(mods[f"{pkg}.module.speechclip_c_modules.vector_quantizers"], "SimpleVectorQuantizer") \
             is scp.SimpleVectorQuantizer
+        assert mods[f"{pkg}.model.kwClip"].KWClip_GeneralTransformer.compute_loss._scp_installed
+        assert mods[f"{pkg}.module.speech_encoder_plus"].S3prlSpeechEncoderPlus.forward._scp_installed
         # the patched method runs the fused path on a duck-typed branch (projection = identity)
         V, D = 512, 64
         table = torch.randn(V, D).cuda() * 0.02
