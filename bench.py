@@ -32,6 +32,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+LOCAL_GROUP = "local"  # speechclip_plus_b200.model.kw_glue.LOCAL: no collective even inside an initialised process group
 METRIC = "train pairs/sec (hot path: layer weighted-sum + keyword VQ + masked InfoNCE, fwd+bwd+optimiser)"
 UNIT = "pairs/s"
 SEED = 7122
@@ -305,7 +306,7 @@ class HotPath:
             out = scp.compute_loss(gathered, self.crit, cfg["cascaded_weight"], cfg["parallel_weight"], local_rows=rows,
                                    group=self.group)                                    # S3 fwd (sharded)
         else:
-            gathered, _ = scp.gather_loss_feats(feats, None)
+            gathered, _ = scp.gather_loss_feats(feats, LOCAL_GROUP)  # purely local even inside an initialised group
             out = scp.compute_loss(gathered, self.crit, cfg["cascaded_weight"], cfg["parallel_weight"])
         torch.autograd.backward([out["loss"], y], [None, self.grad_y])                 # S3 bwd, V bwd, S1 bwd
         return out["loss"].detach(), res
@@ -532,7 +533,7 @@ def kernel_breakdown(hp: "HotPath", timer: GraphTimer):
             o = scp.compute_loss(gathered, hp.crit, hp.cfg["cascaded_weight"], hp.cfg["parallel_weight"], local_rows=rows,
                                  group=hp.group)
         else:
-            gathered, _ = scp.gather_loss_feats(feats, None)
+            gathered, _ = scp.gather_loss_feats(feats, LOCAL_GROUP)
             o = scp.compute_loss(gathered, hp.crit, hp.cfg["cascaded_weight"], hp.cfg["parallel_weight"])
         torch.autograd.grad(o["loss"], wrt, allow_unused=True)
     t = timer.time(nce_fb)

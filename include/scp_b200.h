@@ -282,9 +282,22 @@ int scp_grad_pack(const float* const* grads, const int64_t* sizes, int n, float 
  * registered tensor; g = grad_scale * packed.  step: device int64 counter, read and incremented by the kernel (a
  * replayed CUDA graph therefore advances it).  lr_device (nullable): device f32 learning rate written by the caller's
  * scheduler; otherwise `lr`. */
-int scp_adam_packed(float* const* params, const int64_t* sizes, int n, const float* packed_grads, float grad_scale,
+int scp_adam_packed(float* const* params, const int64_t* sizes, int n, const float* packed_grads,
+                    int n_shards /* packed_grads holds n_shards buffers (one per rank, as gathered), summed in rank order */,
+                    int64_t shard_stride /* elements between them */, float grad_scale,
                     float* exp_avg, float* exp_avg_sq, int64_t* step, const float* lr_device, float lr, float beta1,
                     float beta2, float eps, float weight_decay, scp_stream_t stream);
+
+/* ---- one-shot all-gather over NVLink peer memory for the path's small exchanges (G0 and friends): every rank pushes its
+ *      payload into the gather buffer of every peer with plain stores on peer-mapped pointers, raises a flag there and
+ *      waits for the flags of all peers -- one launch + one collect launch instead of an NCCL collective (25-50 us of
+ *      latency each at 8 ranks inside a CUDA graph).  The caller allocates the same buffer of scp_p2p_buffer_bytes() on
+ *      every rank as peer-accessible (symmetric) memory, zeroes it once, and passes the DEVICE array of the world base
+ *      pointers (peer_bufs_device[r] = rank r's buffer as mapped into this process).  state: 2 x u32, zero-initialised,
+ *      private to this rank.  out: (world, nbytes) local result.  nbytes: multiple of 16, <= nbytes_capacity. ---------- */
+size_t scp_p2p_buffer_bytes(int world, size_t nbytes_capacity);
+int scp_p2p_allgather(const void* src, size_t nbytes, void* const* peer_bufs_device, void* local_buf, int rank, int world,
+                      size_t nbytes_capacity, uint32_t* state, void* out, scp_stream_t stream);
 
 #ifdef __cplusplus
 }

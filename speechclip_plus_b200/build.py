@@ -19,7 +19,7 @@ INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libscp_b200.so")
 OBJ_DIR = os.path.join(PKG_DIR, "build")
 
-SOURCES = ["scp_runtime.cu", "scp_wsum.cu", "scp_kwbn.cu", "scp_splice.cu", "scp_cif.cu", "scp_vq.cu", "scp_nce.cu", "scp_optim.cu"]
+SOURCES = ["scp_runtime.cu", "scp_wsum.cu", "scp_kwbn.cu", "scp_splice.cu", "scp_cif.cu", "scp_vq.cu", "scp_nce.cu", "scp_optim.cu", "scp_p2p.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

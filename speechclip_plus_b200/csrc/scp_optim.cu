@@ -38,7 +38,8 @@ __global__ void grad_pack_kernel(PackList pl, float scale, float* __restrict__ p
 // torch.optim.Adam (no amsgrad, L2 weight decay): g += wd p ; m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ;
 // p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps).  `step` is read, and advanced by thread 0 of block 0 after
 // every block has read it (single launch, grid of one block for the sizes this path has).
-__global__ void adam_packed_kernel(PackList pl, const float* __restrict__ packed, float grad_scale,
+__global__ void adam_packed_kernel(PackList pl, const float* __restrict__ packed, int n_shards, int64_t shard_stride,
+                                   float grad_scale,
                                    float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
                                    int64_t* __restrict__ step, const float* __restrict__ lr_ptr, float lr, float beta1,
                                    float beta2, float eps, float weight_decay) {
@@ -52,7 +53,9 @@ __global__ void adam_packed_kernel(PackList pl, const float* __restrict__ packed
   for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
     const int t = pack_find(pl, e);
     float* p = pl.dst[t] + (e - pl.offset[t]);
-    float g = packed[e] * grad_scale;
+    float g = 0.f;
+    for (int r = 0; r < n_shards; ++r) g += packed[(int64_t)r * shard_stride + e];  // fixed order: every rank identical
+    g *= grad_scale;
     const float w = *p;
     g = fmaf(weight_decay, w, g);
     const float m = beta1 * exp_avg[e] + (1.0f - beta1) * g;
@@ -100,17 +103,21 @@ extern "C" int scp_grad_pack(const float* const* grads, const int64_t* sizes, in
 }
 
 extern "C" int scp_adam_packed(float* const* params, const int64_t* sizes, int n, const float* packed_grads,
-                               float grad_scale, float* exp_avg, float* exp_avg_sq, int64_t* step,
+                               int n_shards, int64_t shard_stride, float grad_scale, float* exp_avg, float* exp_avg_sq,
+                               int64_t* step,
                                const float* lr_device, float lr, float beta1, float beta2, float eps,
                                float weight_decay, scp_stream_t stream) {
   SCP_CHECK_ARG(params && packed_grads && exp_avg && exp_avg_sq && step, "adam_packed: null pointer");
+  SCP_CHECK_ARG(n_shards >= 1 && n_shards <= 1024, "adam_packed: n_shards %d", n_shards);
   PackList pl;
   int rc = make_pack_list(&pl, nullptr, params, sizes, n);
   if (rc) return rc;
   for (int i = 0; i < n; ++i) SCP_CHECK_ARG(params[i], "adam_packed: params[%d] null", i);
   SCP_CHECK_ARG(pl.offset[n] <= (1 << 20), "adam_packed: %lld elements (this entry point is for the path's small tensors)",
                 (long long)pl.offset[n]);
-  adam_packed_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pl, packed_grads, grad_scale, exp_avg,
+  SCP_CHECK_ARG(n_shards == 1 || shard_stride >= pl.offset[n], "adam_packed: shard stride %lld < %lld elements",
+                (long long)shard_stride, (long long)pl.offset[n]);
+  adam_packed_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pl, packed_grads, n_shards, shard_stride, grad_scale, exp_avg,
                                                                              exp_avg_sq, step, lr_device, lr, beta1, beta2,
                                                                              eps, weight_decay);
   SCP_CUDA_LAUNCH_CHECK("adam_packed");

@@ -21,6 +21,16 @@ from .. import _lib
 
 FEAT_KEYS = ("image_feat", "cascaded_audio_feat", "parallel_audio_feat")
 
+# pass as `group` to keep a call purely local even though torch.distributed is initialised (e.g. a single-process
+# reference evaluation of the concatenated batch on rank 0)
+LOCAL = "local"
+
+
+def group_world_size(group) -> int:
+    if group is LOCAL or not (dist.is_available() and dist.is_initialized()):
+        return 1
+    return dist.get_world_size(group)
+
 
 # ---------------------------------------------------------------------------------------------------------------
 # device-agnostic plumbing (exercised on CPU with gloo in tests/test_multiproc_gloo.py)
@@ -36,9 +46,14 @@ def pack_nbytes(n_feats: int, n: int, D: int) -> int:
 
 def all_gather_packed(packed: torch.Tensor, group=None) -> torch.Tensor:
     """All-gather one packed uint8 buffer per rank -> (world, nbytes).  Works for NCCL (device) and gloo (host)."""
-    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    world = group_world_size(group)
     if world == 1:
         return packed.reshape(1, -1)
+    if packed.is_cuda and packed.numel() * packed.element_size() % 16 == 0:
+        from . import peer_gather  # one push + one collect launch over NVLink peer memory instead of an NCCL collective
+        ctx = peer_gather.get(packed.numel() * packed.element_size(), packed.device, group, tag="feats")
+        if ctx is not None:
+            return ctx.all_gather(packed).view(packed.dtype).reshape(world, -1)
     out = torch.empty(world * packed.numel(), dtype=packed.dtype, device=packed.device)
     dist.all_gather_into_tensor(out, packed.reshape(-1), group=group)  # flat output: accepted by NCCL and gloo
     return out.reshape(world, -1)
@@ -164,7 +179,7 @@ def _overlap_enabled() -> bool:
 
 
 def _world(group) -> int:
-    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    return group_world_size(group)
 
 
 def global_mean_with_local_grad(local_mean: torch.Tensor, group=None) -> torch.Tensor:
@@ -216,8 +231,7 @@ def compute_loss(loss_feats: Dict[str, torch.Tensor], criterion, cascaded_object
         with torch.cuda.stream(side):
             terms[active[1][0]] = call(active[1][0])
         terms[active[0][0]] = call(active[0][0])     # the first chain on the caller's stream, next to the second
-        main.wait_stream(side)                       # join
-        terms[active[1][0]].record_stream(main)
+        main.wait_stream(side)                       # join (the next fork orders any reuse of the side stream's blocks)
     else:
         for branch, _ in active:
             terms[branch] = call(branch)

@@ -39,10 +39,12 @@ class PackedAdam:
         self.all_reduce = all_reduce  # False: a purely local optimiser even inside an initialised process group
         self.sizes = [p.numel() for p in self.params]
         total = sum(self.sizes)
+        self.total = total
+        self.padded = (total + 3) // 4 * 4  # the peer-memory exchange moves 16-byte units
         dev = p0.device
-        self.packed = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.packed = torch.zeros(self.padded, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(self.padded, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(self.padded, dtype=torch.float32, device=dev)
         self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
         self.lr_device: Optional[torch.Tensor] = None  # set to a device scalar to drive the rate from a scheduler
         self._sizes_arr = (ctypes.c_int64 * len(self.sizes))(*self.sizes)
@@ -79,11 +81,19 @@ class PackedAdam:
         """Pack this rank's gradients, SUM them over the group, apply Adam in place."""
         lib = _lib.load()
         self.pack_grads(grads)
+        src, n_shards, stride = self.packed, 1, 0
         if self.world() > 1:
-            dist.all_reduce(self.packed, op=dist.ReduceOp.SUM, group=self.group)
+            from . import peer_gather
+            ctx = peer_gather.get(self.padded * 4, self.packed.device, self.group, tag="grads")
+            if ctx is not None:  # every rank receives every rank's packed gradients and sums them in rank order
+                src = ctx.all_gather(self.packed).view(torch.float32)
+                n_shards, stride = self.world(), self.padded
+                self.gathered = src
+            else:
+                dist.all_reduce(self.packed, op=dist.ReduceOp.SUM, group=self.group)
         dev = self.packed.device
         with torch.cuda.device(dev):
-            st = lib.scp_adam_packed(self._param_ptrs, self._sizes_arr, len(self.params), _lib.ptr(self.packed),
+            st = lib.scp_adam_packed(self._param_ptrs, self._sizes_arr, len(self.params), _lib.ptr(src), n_shards, stride,
                                      float(grad_scale), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
                                      _lib.ptr(self.step_count), _lib.ptr(self.lr_device), self.lr, float(self.betas[0]),
                                      float(self.betas[1]), self.eps, self.weight_decay, _lib.stream_ptr(dev))

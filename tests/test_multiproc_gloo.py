@@ -87,8 +87,12 @@ def _worker(rank: int, world: int, port: int, result_dir: str):
         ps = stats_all[:, 2].reshape(-1).double() * scale
         loss_sharded = 0.5 * ((lr - ps).mean() + (lc - ps).mean())
         assert abs(loss_sharded.item() - ref.item()) < 1e-5
+        os.environ["SCP_NCE_SHARD_MIN_N"] = "0"
         assert scp_losses._use_sharded_forward(N, r0, r1, None)
         assert not scp_losses._use_sharded_forward(N, 0, N, None)
+        assert not scp_losses._use_sharded_forward(N, r0, r1, kw_glue.LOCAL)
+        os.environ["SCP_NCE_SHARD_MIN_N"] = "2048"
+        assert not scp_losses._use_sharded_forward(N, r0, r1, None)       # small global batches stay redundant
         # ---- CIF quantity loss on the multi-rank path: value = global mean, gradient = reference's after the
         #      ddp_grad_scale * mean-over-ranks recipe (kwClip.py:1031-1038)
         w = torch.tensor(0.7, dtype=torch.float64, requires_grad=True)     # a parameter shared by every rank
