@@ -767,6 +767,15 @@ def run_gpu_arm(args):
         e2e_fp16["note"] = ("same step with the upstream hidden states handed over as fp16 (the reference trains with "
                             "precision: 16; the S1 kernels read fp16 layers directly): half the host bytes. NOT the headline.")
 
+    if args.no_breakdown:  # profiling runs (ncu): the timed steps only
+        clocks = sampler.stop() if rank == 0 else None
+        if rank == 0:
+            emit_json(dict(metric=METRIC, value=pairs_per_s, unit=UNIT, n_gpus=world, steps=args.steps,
+                           ms_per_step=ms / args.steps, gpu_launches=int(launches), clocks=clocks,
+                           config=make_config(args.workload, args.scaling, world),
+                           note="profiling run: no roofline / e2e / configs legs"))
+        _finish(torch, world)
+        return
     timer = GraphTimer(torch, dev)
     kb = kernel_breakdown(hp, timer)
     clocks = sampler.stop() if rank == 0 else None
@@ -872,6 +881,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end legs (profiling runs)")
     ap.add_argument("--no-configs", action="store_true", help="skip the table of the other BASELINE configs")
+    ap.add_argument("--no-breakdown", action="store_true", help="skip the per-kernel timing legs (profiling runs under ncu)")
     ap.add_argument("--no-check", action="store_true", help="skip the N-rank vs single-process value check (N > 1)")
     ap.add_argument("--check-only", action="store_true", help="run only the N-rank vs single-process check")
     args = ap.parse_args()

@@ -25,6 +25,6 @@ from .module.speech_encoder_plus import fuse_upstream_features, upstream_feat_le
 from .module.cif import CIF  # noqa: F401
 from .model.kw_glue import compute_loss, gather_loss_feats, ddp_grad_scale  # noqa: F401
 from .model.packed_optim import PackedAdam  # noqa: F401
-from .install import install  # noqa: F401
+from .install import install, uninstall  # noqa: F401
 
 __version__ = "0.2.0"

@@ -12,12 +12,39 @@ and, so that the glue between those modules is on the path too (model/kwclip_glu
   * ``FairseqSpeechEncoder_Hubert.forward`` / ``S3prlSpeechEncoderPlus.forward``  speech_encoder_plus.py:520-640, :240-311 (S1')
   * ``ClipModel.__init__``                                        avssl/module/clip_official.py:30-108  (N2)
 
-``install()`` must run after ``import avssl`` and before the model is constructed.
+``install()`` must run after ``import avssl`` and before the model is constructed; ``uninstall()`` restores the reference.
 """
 from __future__ import annotations
 
 import importlib
 import sys
+
+_MISSING = object()
+_UNDO: list = []          # (owner, attribute, value before the first install()) in patch order
+_UNDO_KEYS: set = set()
+
+
+def _remember(owner, attr: str) -> None:
+    key = (id(owner), attr)
+    if key in _UNDO_KEYS:
+        return
+    _UNDO_KEYS.add(key)
+    _UNDO.append((owner, attr, owner.__dict__.get(attr, _MISSING) if isinstance(owner, type) else getattr(owner, attr, _MISSING)))
+
+
+def uninstall() -> int:
+    """Put back everything ``install()`` replaced (classes, methods, wrappers); returns the number of restored names."""
+    n = 0
+    while _UNDO:
+        owner, attr, old = _UNDO.pop()
+        if old is _MISSING:
+            if attr in getattr(owner, "__dict__", {}):
+                delattr(owner, attr)
+        else:
+            setattr(owner, attr, old)
+        n += 1
+    _UNDO_KEYS.clear()
+    return n
 
 
 def install(avssl_package: str = "avssl", strict: bool = False, fuse_forward: bool = True) -> dict:
@@ -42,6 +69,7 @@ def install(avssl_package: str = "avssl", strict: bool = False, fuse_forward: bo
                 raise
             done[key] = False
             return
+        _remember(mod, attr)
         setattr(mod, attr, value)
         done[key] = True
 
@@ -62,6 +90,7 @@ def install(avssl_package: str = "avssl", strict: bool = False, fuse_forward: bo
     try:
         from .module.clip_glue import encode_keywords, get_keypadding_mask
         co = sys.modules.get(f"{p}.module.clip_official") or importlib.import_module(f"{p}.module.clip_official")
+        _remember(co.ClipModel, "encode_keywords")
         co.ClipModel.encode_keywords = encode_keywords
         done[f"{p}.module.clip_official.ClipModel.encode_keywords"] = True
         patch(f"{p}.util.data_utils", "get_keypadding_mask", get_keypadding_mask)
@@ -73,6 +102,7 @@ def install(avssl_package: str = "avssl", strict: bool = False, fuse_forward: bo
     # the fused cosine + quantise + lookup replaces the method body on the shared base class of all branches
     try:
         kb = sys.modules.get(f"{p}.model.kw_branches") or importlib.import_module(f"{p}.model.kw_branches")
+        _remember(kb.GeneralBranch, "vq_audio_features")
         kb.GeneralBranch.vq_audio_features = lambda self, audio_feat: fused_vq_audio_features(self, audio_feat)
         done[f"{p}.model.kw_branches.GeneralBranch.vq_audio_features"] = True
     except Exception:
@@ -95,6 +125,7 @@ def install(avssl_package: str = "avssl", strict: bool = False, fuse_forward: bo
             new = make(current)
             new._scp_installed = True
             new._scp_original = current
+            _remember(cls, attr)
             setattr(cls, attr, new)
             done[key] = True
         except Exception:

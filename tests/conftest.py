@@ -25,6 +25,16 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+@pytest.fixture(autouse=True)
+def _restore_reference_after_install():
+    """install() patches the reference package process-wide; every test leaves the reference as it found it (the live
+    differential suites compare against the UNPATCHED reference)."""
+    yield
+    mod = sys.modules.get("speechclip_plus_b200.install")
+    if mod is not None:
+        mod.uninstall()
+
+
 def load_golden(name: str):
     """Load tests/golden/<name>.npz as a dict of torch tensors / python scalars."""
     out = {}

@@ -287,3 +287,26 @@ def test_clipmodel_init_wrapper_builds_the_reduced_vocabulary(tmp_path):
     with pytest.raises(SystemExit):
         cls("ViT-B/32", reduce_subword_embbedding=str(tmp_path / "missing.npy"))
     assert hasattr(co.ClipModel, "encode_keywords")
+
+
+def test_uninstall_restores_the_reference():
+    """install() -> uninstall() leaves every patched name of the reference package exactly as it was (classes looked up
+    by name, the two method bodies, the five wrapped glue methods), and a second install() starts from the originals."""
+    import speechclip_plus_b200 as scp
+    ref.import_avssl()
+    import importlib
+    kb = importlib.import_module("avssl.model.kw_branches")
+    losses = importlib.import_module("avssl.module.losses")
+    co = importlib.import_module("avssl.module.clip_official")
+    before = (kb.GeneralBranch.__dict__["vq_audio_features"], co.ClipModel.__dict__["encode_keywords"],
+              losses.MaskedContrastiveLoss, kb.CIF, kb.Kw_BatchNorm, [fn for _, _, fn in _save_glue_methods()])
+    done = scp.install("avssl", strict=True)
+    assert losses.MaskedContrastiveLoss is scp.MaskedContrastiveLoss
+    assert scp.uninstall() >= len(done) - 2          # package-level aliases may share a module object
+    after = (kb.GeneralBranch.__dict__["vq_audio_features"], co.ClipModel.__dict__["encode_keywords"],
+             losses.MaskedContrastiveLoss, kb.CIF, kb.Kw_BatchNorm, [fn for _, _, fn in _save_glue_methods()])
+    assert all(a is b for a, b in zip(before[:5], after[:5]))
+    assert all(a is b for a, b in zip(before[5], after[5]))
+    assert scp.uninstall() == 0
+    scp.install("avssl", strict=True)
+    assert co.ClipModel.__init__._scp_original is before[5][4]

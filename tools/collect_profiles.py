@@ -29,17 +29,19 @@ for r in rows[2:]:
     print(f"{float(r[h.index('gpu__time_duration.sum')]):8.1f} us  dram {per[k] / 1e6:8.1f} MB  tensor {r[t][:5]}%  {k[:80]}")
 g = lambda *names: int(sum(v for k, v in per.items() if any(n in k for n in names)))
 json.dump({"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch (bytes) from the ncu --set full capture of `python bench.py "
-           "--steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-breakdown --no-graph` (profiles/%s_ncu_full_hot_kernels.csv, "
+           "--steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-configs --no-breakdown --no-graph` (profiles/%s_ncu_full_hot_kernels.csv, "
            "tools/profile_round.sh); keyed like bench.py's kernel groups (group = sum of its kernels)" % tag,
            "wsum_fwd": g('wsum_fwd'), "wsum_bwd": g('wsum_bwd'), "vq_fwd": g('Sweep1', 'Sweep2', 'vq_select', 'vq_colsum'),
            "vq_bwd": g('Sweep3', 'StoreEpi<2>'), "nce_fwd_bwd": g('Nce')}, open(f"{pr}/traffic.json", "w"), indent=2)
 shutil.copy(f"{go}/{tag}_bench.json", f"{pr}/{tag}_bench.json")
 shutil.copy(f"{go}/{tag}_launches.csv", f"{pr}/{tag}_launches_bench_steps2.csv")
-for extra in ("aux_kernels", "config_kernels"):
+for extra in ("aux_kernels",):
     if os.path.exists(f"{go}/{tag}_{extra}.json"):
         shutil.copy(f"{go}/{tag}_{extra}.json", f"{pr}/{tag}_{extra}.json")
 d = json.load(open(f"{pr}/{tag}_bench.json"))
 print(d["value"], d["ms_per_step"], d["roofline"]["kernel"], round(d["roofline"]["frac"], 3), d["clocks"]["reasons"])
 for k, v in d["kernels"].items():
-    print(" ", k, round(v["ms"], 4), round(v["frac"], 3))
+    print(" ", k, round(v["ms"], 4), None if v["frac"] is None else round(v["frac"], 3))
 print(" e2e", d["e2e"]["value"], "cpu", d["cpu_baseline"]["value"], d["cpu_baseline"]["cores"])
+for k, v in (d.get("configs") or {}).items():
+    print(" ", k, v.get("ms_per_step"), v.get("error"))

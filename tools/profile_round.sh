@@ -9,7 +9,7 @@ set -u
 cd "$(dirname "$0")/.."
 tag=${1:-r01}
 mkdir -p gpurun_out
-SHORT="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-breakdown --no-graph"
+SHORT="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-configs --no-breakdown --no-graph"
 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err || { echo "bench failed"; tail -5 gpurun_out/${tag}_bench.err; exit 1; }
 $SHORT > gpurun_out/${tag}_short.json 2> gpurun_out/${tag}_short.err || { echo "short bench failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
@@ -23,7 +23,5 @@ ncu -i gpurun_out/${tag}_full.ncu-rep --page raw --csv > gpurun_out/${tag}_full_
 python tools/aux_kernel_times.py > gpurun_out/${tag}_aux_kernels.json 2> gpurun_out/${tag}_aux_kernels.err
 
 
-# the three kernel groups at the per-GPU sizes of every BASELINE config (the bench line is config 3 only)
-python tools/config_kernel_times.py > gpurun_out/${tag}_config_kernels.json 2> gpurun_out/${tag}_config_kernels.err
 tail -2 gpurun_out/${tag}_ncu_full.log
 cat gpurun_out/${tag}_bench.json
