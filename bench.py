@@ -789,12 +789,22 @@ def run_gpu_arm(args):
         for name, scaling in (("c2", "weak"), ("c3", "strong"), ("c4", "strong"), ("c5", "strong")):
             if (name, scaling) == (args.workload, args.scaling):
                 continue
-            try:
-                configs[f"{name}_{scaling}"] = measure_config(torch, dist, name, scaling, dev, rank, world, 10, peaks, timer,
-                                                              graph=not args.no_graph)
-            except Exception as exc:  # a config that does not fit must not take the headline down
-                configs[f"{name}_{scaling}"] = dict(error=repr(exc)[:300])
-                torch.cuda.empty_cache()
+            # one retry (single process only: a lone rank retrying would desynchronise the collectives): a stream capture
+            # invalidated by an unrelated asynchronous error is transient
+            for attempt in ((0, 1) if world == 1 else (0,)):
+                try:
+                    configs[f"{name}_{scaling}"] = measure_config(torch, dist, name, scaling, dev, rank, world, 10, peaks,
+                                                                  timer, graph=not args.no_graph)
+                    break
+                except Exception as exc:  # a config that does not fit must not take the headline down
+                    import traceback
+                    traceback.print_exc(file=sys.stderr)
+                    configs[f"{name}_{scaling}"] = dict(error=repr(exc)[:300], attempts=attempt + 1)
+                    try:
+                        torch.cuda.synchronize()
+                    except Exception:
+                        pass
+                    torch.cuda.empty_cache()
             _trace(f"config {name}/{scaling} done")
 
     if rank == 0:

@@ -146,6 +146,25 @@ int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int64_t D,
                float* metrics, void* kw_hat,
                void* workspace, size_t workspace_bytes, scp_stream_t stream);
 
+/* Forward that keeps what the backward pass would otherwise recompute.  saved_probs (nullable -> exactly scp_vq_fwd),
+ * (Mp, Vp) fp16, scp_vq_saved_probs_bytes(M, V) bytes, takes the place of the (M,V) scratch inside the workspace (use
+ * scp_vq_fwd_save_workspace_bytes) and receives the soft-max numerators at temperature tau,
+ *   P''[m,v] = exp((cos[m,v] - 1)/tau + 10)      (= e^{cos/tau} at tau = 0.1; in [e^-10, e^10] for every tau; 0 for masked /
+ *   padding columns),
+ * i.e. softmax_tau(cos[m,:]) up to the row's normaliser (kw_branches.py:158-179 + my_vector_quantizer.py:130-136); avg_probs
+ * and the exact arg-max are derived from the same buffer (e^cos = P''^tau e^{1 - 10 tau}).  Outputs are identical to
+ * scp_vq_fwd within the stated tolerances.  The buffer must stay untouched until scp_vq_bwd_saved has consumed it.  Meant for
+ * tau >= 0.07: below that the numerators far from the row maximum fall into fp16 subnormals (the Python wrapper selects the
+ * recompute path then). */
+size_t scp_vq_saved_probs_bytes(int64_t M, int64_t V);
+size_t scp_vq_fwd_save_workspace_bytes(int64_t M, int64_t V, int64_t D);   /* saved_probs != NULL: no (M,V) scratch inside */
+int scp_vq_fwd_save(const float* kw, int64_t M, int64_t K, int64_t V, int64_t D,
+                    const void* table_hat, const float* table_norm, const float* table,
+                    const int32_t* masked_cols, int n_masked, const float* tau,
+                    int64_t* idx, float* keywords, float* row_stats, float* code_hist, float* avg_probs,
+                    float* metrics, void* kw_hat, void* saved_probs,
+                    void* workspace, size_t workspace_bytes, scp_stream_t stream);
+
 size_t scp_vq_bwd_workspace_bytes(int64_t M, int64_t V, int64_t D);
 
 /* Backward of the straight-through estimator (training mode):
@@ -158,6 +177,21 @@ int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, int64_t V, i
                const int32_t* masked_cols, int n_masked, const float* tau,
                float* g_kw, float* g_tau,
                void* workspace, size_t workspace_bytes, scp_stream_t stream);
+
+/* Same gradient from the numerators saved by scp_vq_fwd_save (saved_probs nullable -> scp_vq_bwd): only g . E^T is formed
+ * on the tensor cores (no k . E^T product, no exponentials: 6 instead of 8 M V D executed FLOP over forward + backward ... 4
+ * instead of 8 in this call) and the output GEMM reads P'' in place.  Falls back to the recompute path when g_tau is
+ * requested (a learnable temperature needs the logits), for single-tile problems and for D > 512. */
+/* 1 when scp_vq_bwd_saved would use the saved numerators for this shape (at least two 128-row tiles, D <= 512): callers
+ * that cannot profit should call scp_vq_fwd (its avg_probs pass is cheaper than the one of scp_vq_fwd_save). */
+int scp_vq_bwd_saved_available(int64_t M, int64_t V, int64_t D);
+size_t scp_vq_bwd_saved_workspace_bytes(int64_t M, int64_t V, int64_t D, int want_tau);   /* want_tau: g_tau != NULL */
+int scp_vq_bwd_saved(const float* g_keywords, const float* kw, int64_t M, int64_t V, int64_t D,
+                     const void* kw_hat, const void* table_hat, const void* table_hat_t,
+                     const float* table_norm, const float* table_mean, const float* row_stats,
+                     const int32_t* masked_cols, int n_masked, const float* tau, const void* saved_probs,
+                     float* g_kw, float* g_tau,
+                     void* workspace, size_t workspace_bytes, scp_stream_t stream);
 
 /* Dense-input form of SimpleVectorQuantizer.forward (my_vector_quantizer.py:64-165) for callers that already hold the
  * (M,V) score matrix x (fp32, row pitch ldx).  Masks x IN PLACE like the reference (:78-79).  subword_prob (nullable,

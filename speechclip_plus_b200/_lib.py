@@ -53,6 +53,16 @@ SIGNATURES = {
     "scp_vq_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                            POINTER(c_int32), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "scp_vq_saved_probs_bytes": (c_size_t, [c_int64, c_int64]),
+    "scp_vq_fwd_save_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "scp_vq_bwd_saved_available": (c_int, [c_int64, c_int64, c_int64]),
+    "scp_vq_bwd_saved_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
+    "scp_vq_fwd_save": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                POINTER(c_int32), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "scp_vq_bwd_saved": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, POINTER(c_int32), c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_size_t, c_void_p]),
     "scp_vq_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "scp_vq_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_void_p, c_void_p, POINTER(c_int32), c_int, c_void_p, c_void_p, c_void_p,

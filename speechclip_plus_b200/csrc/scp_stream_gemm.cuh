@@ -59,7 +59,8 @@ enum { MC_NONE = 0, MC_X = 1, MC_Y = 2, MC_PAIR = 3 };
 
 struct EpiCtx {
   int row_in_tile;  // 0..127: TMEM lane == X row inside the CTA tile
-  int half;         // 0/1: which half of every tile's column chunks this warp consumes
+  int half;         // 0 .. parts-1: which share of every tile's column chunks this warp consumes
+  int parts;        // epilogue warps per lane quadrant (EW / 4): 2 by default, 4 with sixteen epilogue warps
   int tid;          // 0..255 inside the epilogue group
   uint8_t* smem;    // Epi::kSmemBytes bytes, 1024-byte aligned, shared by the epilogue group
   const GemmMaps* maps;
@@ -176,6 +177,14 @@ struct GemmCfg {
   static_assert(STAGES * kStageBytes <= 220 * 1024, "smem ring too large");
 };
 
+// An epilogue that declares `static constexpr bool kUnrollTile = true` gets its tile's chunk loop fully unrolled and is
+// called as chunk_k(k, col0, v) with k = 0 .. chunks-per-warp-1 a compile-time constant after unrolling (it can keep
+// per-chunk state, e.g. prefetched operands, in registers).
+template <class E, class = void>
+struct epi_unroll { static constexpr bool value = false; };
+template <class E>
+struct epi_unroll<E, decltype((void)E::kUnrollTile)> { static constexpr bool value = E::kUnrollTile; };
+
 // Epi interface (all __device__ __forceinline__):
 //   struct Params;                      POD passed by value to the kernel
 //   static constexpr int kSmemBytes;    extra shared memory (shared by the 8 epilogue warps)
@@ -186,8 +195,11 @@ struct GemmCfg {
 //   void finish();
 // Per-row state lives in the two warps ("halves") that own the row; epilogues combine the halves themselves
 // (separate partial slots, or through ctx.smem + named_bar_sync(kEpiBarrierId, kEpiThreads)).
-template <int BN, int NX, int STAGES, class Epi, int CL, int MC, int NRES>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// EW = epilogue warps (8 or 16).  Sixteen put four warps on every SM sub-partition: the row-wise epilogues are
+// latency-bound with two (ncu: ~40 % issue utilisation, `wait` + scoreboard stalls dominate), at the price of a
+// 112-register budget per thread ((16 + 2) * 32 threads).  The TMA / MMA warps keep the two highest warp ids.
+template <int BN, int NX, int STAGES, class Epi, int CL, int MC, int NRES, int EW>
+__global__ void __launch_bounds__((EW + 2) * 32, 1)
 stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, const typename Epi::Params ep) {
   constexpr bool kPair = MC == MC_PAIR;
   constexpr bool XRES = NRES > 0;
@@ -198,6 +210,9 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
   static_assert((CL == 1) == (MC == MC_NONE), "clusters exist to share operands");
   static_assert(MC != MC_X || (kTileM / CL) % 8 == 0, "X slice must be whole swizzle atoms");
   static_assert(MC != MC_Y || (BN / CL) % 8 == 0, "Y slice must be whole swizzle atoms");
+  static_assert(EW == 8 || EW == 16, "epilogue warps");
+  static_assert((BN / 32) % (EW / 4) == 0, "every epilogue warp of a quadrant takes the same number of 32-column chunks");
+  constexpr int kProducerWarp = EW, kMmaWarp = EW + 1;  // shadow the namespace-level defaults (EW = 8)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem_x = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // resident X region (XRES): operand x, chunk j at smem_x + (x * k_res + j) * 16 KB; the ring follows it
@@ -227,7 +242,7 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull_bar[a], 1);
-        mbar_init(&tempty_bar[a], kPair ? 2 * kEpiWarps : kEpiWarps);  // one arrive per epilogue warp (of both CTAs)
+        mbar_init(&tempty_bar[a], kPair ? 2 * EW : EW);  // one arrive per epilogue warp (of both CTAs)
       }
       fence_barrier_init();
     }
@@ -347,11 +362,12 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
       EpiCtx ctx;
       ctx.row_in_tile = quad * 32 + lane;
       ctx.half = warp >> 2;
+      ctx.parts = EW / 4;
       ctx.tid = threadIdx.x;
       ctx.smem = epi_smem;
       ctx.maps = &maps;
       Epi epi(ep, work, ctx);
-      constexpr int kChunksPerHalf = BN / 64;
+      constexpr int kChunksPerHalf = BN / 32 / (EW / 4);
       for (int it = 0; it < work.iters; ++it) {
         const int nt = work.nt_first + it * work.nt_stride;
         const bool real = nt < work.nt_end;
@@ -368,7 +384,7 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
             __syncwarp();
             const int c0 = ctx.half * kChunksPerHalf;
             tmem_ld32_issue(tbase + (uint32_t)(c0 * 32), raw[0]);
-            if constexpr (kChunksPerHalf % 2 == 0) {
+            if constexpr (kChunksPerHalf % 2 == 0 && !epi_unroll<Epi>::value) {
 #pragma unroll 1
               for (int cc = 0; cc < kChunksPerHalf; cc += 2) {
                 const int c = c0 + cc;
@@ -395,7 +411,11 @@ stream_gemm_kernel(const __grid_constant__ GemmMaps maps, const Sched sched, con
                 float v[1][32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[0][i] = __uint_as_float(raw[cc & 1][i]);
-                if (!(sched.debug & 1)) epi.chunk(nt * BN + c * 32, v);
+                if constexpr (epi_unroll<Epi>::value) {
+                  if (!(sched.debug & 1)) epi.chunk_k(cc, nt * BN + c * 32, v);
+                } else {
+                  if (!(sched.debug & 1)) epi.chunk(nt * BN + c * 32, v);
+                }
                 __syncwarp();
               }
             }
@@ -456,12 +476,12 @@ constexpr int resident_smem_bytes(int k_chunks_per_split) {
 }
 
 // NRES: number of resident X operands (0 = all streamed; `true` at old call sites means 1)
-template <int BN, int NX, int STAGES, class Epi, int CL = 1, int MC = MC_NONE, int NRES = 0>
+template <int BN, int NX, int STAGES, class Epi, int CL = 1, int MC = MC_NONE, int NRES = 0, int EW = kEpiWarps>
 int launch_stream_gemm(const GemmMaps& maps, const Sched& sched, const typename Epi::Params& ep, cudaStream_t stream,
                        const char* name) {
   constexpr bool XRES = NRES > 0;
   using Cfg = GemmCfg<BN, NX, STAGES, MC == MC_PAIR, NRES>;
-  auto kern = stream_gemm_kernel<BN, NX, STAGES, Epi, CL, MC, NRES>;
+  auto kern = stream_gemm_kernel<BN, NX, STAGES, Epi, CL, MC, NRES, EW>;
   const int k_res = XRES ? (sched.k_chunks + sched.k_splits - 1) / sched.k_splits : 0;
   const int smem = Cfg::smem_bytes(Epi::kSmemBytes, k_res);
   if (smem > kMaxDynSmem) return fail(SCP_ERR_UNSUPPORTED, "%s: %d B of shared memory needed (K too large for a resident X tile)", name, smem);
@@ -484,7 +504,7 @@ int launch_stream_gemm(const GemmMaps& maps, const Sched& sched, const typename 
     return fail(SCP_ERR_INVALID, "%s: two-direction schedules do not support clusters", name);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3((EW + 2) * 32);
   cfg.dynamicSmemBytes = (size_t)smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

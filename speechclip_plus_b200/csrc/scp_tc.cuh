@@ -172,6 +172,17 @@ __device__ __forceinline__ void stg256(void* gptr, const uint32_t* r) {
                "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+// 32-byte read-only global load that does not allocate in L1 (streamed once)
+__device__ __forceinline__ void ldg256_stream(const void* gptr, uint32_t* r) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(gptr));
+}
+// packed fp16 pair -> packed fp32 pair (low half first)
+__device__ __forceinline__ f32x2 cvt_f32x2_f16x2(uint32_t h) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
+  return pack2(f.x, f.y);
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -370,6 +381,7 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask)
 // ---- host: tensor maps ---------------------------------------------------------------------------------------
 // 2-D fp16 row-major (rows, cols) matrix with row pitch `ld` elements; box = {64, box_rows}; SWIZZLE_128B.
 int make_tmap_f16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+
 // 3-D (64 elements, row, 64-column block) view for MN-major operands: see scp_runtime.cu
 int make_tmap_f16_blocked(CUtensorMap* out, const void* base, int64_t rows, int64_t n_blocks, int64_t ld, int box_rows,
                           int box_blocks);

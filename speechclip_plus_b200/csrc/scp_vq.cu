@@ -175,24 +175,33 @@ __device__ __forceinline__ tc::f32x2 ipow2(tc::f32x2 x) {
   }
 }
 
-struct Sweep1Epi {
+// SAVE: the fp16 scratch holds the soft-max numerators at temperature tau INSTEAD of e^c,
+//     P''[m,v] = exp((c - 1)/tau + 10)      (= e^{c/tau} at tau = 0.1; in [e^-10, e^10] for every tau: fp16 range),
+// and is owned by the caller: the column sums and the arg-max filter recover e^c = P''^tau e^{1 - 10 tau} from it
+// (relative error tau x the fp16 rounding), and the backward pass (scp_vq_bwd_saved) needs neither the k . E^T product
+// nor an exponential -- SweepTEpi reads P'' back and the output GEMM consumes the same buffer.  One (M,V) fp16 matrix is
+// written per forward either way.
+template <bool SAVE>
+struct Sweep1EpiT {
   struct Params {
     float* chunk_max;   // (Mp, n_chunks): maximum of every 32-column chunk (scanned by the arg-max kernel)
     float* group_max;   // (Mp, n_chunks, 4): maximum of every 8-column group (read for candidate chunks only)
-    float* partials;    // (Mp, n_slots, 4): sum e^c, sum c e^c, running max, sum e^{(c-max)/tau};  n_slots = 2*n_groups
+    float* partials;    // (Mp, n_slots, 4): sum e^c, sum c e^c, running max, sum e^{(c-max)/tau};  n_slots = parts*n_groups
     const float* tau;   // device scalar
-    __half* e16;        // nullable (Mp, ldE) fp16: e^c of every logit, consumed by vq_colsum_kernel (avg_probs)
+    __half* e16;        // nullable (Mp, ldE) fp16: e^c of every logit (SAVE: P'', zeros for masked / padding columns),
+                        // consumed by vq_colsum_kernel (avg_probs), the arg-max filter and, SAVE, the backward pass
     int64_t ldE;
     int n_chunks;
     int n_groups;
     int V;
-    int dbg;            // timing ablations (env SCP_VQ_S1_DBG, results invalid): 1 = no chunk/group maxima stores
+    int dbg;            // timing ablations (env SCP_VQ_S1_DBG, results invalid): 1 = no chunk/group maxima stores,
+                        // 2 = no e^c / P'' stores (pow10 path)
     MaskedCols mc;
   };
   static constexpr int kSmemBytes = 0;
   const Params& p;
   int64_t row;
-  int slot;
+  int slot, n_slots;
   bool pow10;   // 1/tau == 10 (every shipped recipe: "fixed=0.1"): e^{c/tau} = (e^c)^10 by repeated squaring
   float k_tau;  // log2(e)/tau
   // running sums as packed pairs (even / odd columns), two independent sets to shorten the dependency chains:
@@ -200,8 +209,9 @@ struct Sweep1Epi {
   tc::f32x2 acc_e[2], acc_ce[2], acc_et[2];
   float run_max;
 
-  __device__ __forceinline__ Sweep1Epi(const Params& p_, const WorkInfo& w, const tc::EpiCtx& ctx)
-      : p(p_), row((int64_t)w.m_tile * tc::kTileM + ctx.row_in_tile), slot(w.n_group * 2 + ctx.half) {
+  __device__ __forceinline__ Sweep1EpiT(const Params& p_, const WorkInfo& w, const tc::EpiCtx& ctx)
+      : p(p_), row((int64_t)w.m_tile * tc::kTileM + ctx.row_in_tile), slot(w.n_group * ctx.parts + ctx.half),
+        n_slots(ctx.parts * p_.n_groups) {
     const float inv_tau = 1.0f / __ldg(p.tau);
     k_tau = kLog2e * inv_tau;
     pow10 = fabsf(inv_tau - 10.0f) <= 1e-4f;
@@ -221,8 +231,9 @@ struct Sweep1Epi {
       const tc::f32x2 e1 = tc::ex2_2(tc::mul2(cc, kl));
       acc_e[a] = tc::add2(acc_e[a], e1);
       acc_ce[a] = tc::fma2(cc, e1, acc_ce[a]);
-      acc_et[a] = tc::add2(acc_et[a], ipow2<N>(e1));
-      h[i >> 1] = tc::cvt_f16x2(e1);
+      const tc::f32x2 et = ipow2<N>(e1);
+      acc_et[a] = tc::add2(acc_et[a], et);
+      h[i >> 1] = tc::cvt_f16x2(SAVE ? et : e1);
     }
   }
   // e^c of the chunk's 32 columns as fp16: 64 contiguous bytes of this thread's row, two full-sector stores.  e^c lies in
@@ -256,7 +267,13 @@ struct Sweep1Epi {
       if (!p.e16)
         *reinterpret_cast<float4*>(p.group_max + (row * p.n_chunks + (col0 >> 5)) * 4) = make_float4(gm[0], gm[1], gm[2], gm[3]);
     }
-    if (cmax <= kNegBig) return;  // fully masked / padding chunk: contributes nothing (and has no finite maximum)
+    if (cmax <= kNegBig) {  // fully masked / padding chunk: contributes nothing (and has no finite maximum)
+      if (SAVE && p.e16) {  // the output GEMM of the backward pass reads every column of the buffer
+        const uint32_t z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        store_e(col0, z);
+      }
+      return;
+    }
     if (pow10) {
       // |c| <= 1 and 1/tau = 10: e^{c/tau} = (e^c)^10 cannot overflow, so no running maximum is needed and the
       // second exponential becomes four packed multiplies -- ONE SFU op per logit instead of two.  Only this one
@@ -264,7 +281,7 @@ struct Sweep1Epi {
       run_max = 0.f;  // the partial sum is relative to a shift of 0
       uint32_t h[16];
       pow_chunk<10>(c, h);
-      if (p.e16) store_e(col0, h);
+      if (p.e16 && !(p.dbg & 2)) store_e(col0, h);
       return;
     }
     if (cmax > run_max) {  // rescale the temperature-tau sum to the new running maximum
@@ -276,6 +293,8 @@ struct Sweep1Epi {
     }
     const float shift = -run_max * k_tau;
     const tc::f32x2 kl = tc::pack2(kLog2e, kLog2e), kt = tc::pack2(k_tau, k_tau), sh = tc::pack2(shift, shift);
+    const float shift_p = 10.0f * kLog2e - k_tau;  // P'' = 2^(c k_tau + shift_p) = exp((c - 1)/tau + 10)
+    const tc::f32x2 shp = tc::pack2(shift_p, shift_p);
     uint32_t h[16];
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
@@ -285,16 +304,18 @@ struct Sweep1Epi {
       acc_e[a] = tc::add2(acc_e[a], e1);
       acc_ce[a] = tc::fma2(cc, e1, acc_ce[a]);
       acc_et[a] = tc::add2(acc_et[a], tc::ex2_2(tc::fma2(cc, kt, sh)));
-      h[i >> 1] = tc::cvt_f16x2(e1);
+      h[i >> 1] = tc::cvt_f16x2(SAVE ? tc::ex2_2(tc::fma2(cc, kt, shp)) : e1);
     }
     if (p.e16) store_e(col0, h);
   }
   __device__ __forceinline__ void finish() {
     float4 o = make_float4(tc::hsum2(tc::add2(acc_e[0], acc_e[1])), tc::hsum2(tc::add2(acc_ce[0], acc_ce[1])), run_max,
                            tc::hsum2(tc::add2(acc_et[0], acc_et[1])));
-    *reinterpret_cast<float4*>(p.partials + (row * (2 * p.n_groups) + slot) * 4) = o;
+    *reinterpret_cast<float4*>(p.partials + (row * n_slots + slot) * 4) = o;
   }
 };
+using Sweep1Epi = Sweep1EpiT<false>;
+using Sweep1SaveEpi = Sweep1EpiT<true>;
 
 // =====================================================================================================================
 // exact arg-max + statistics combine + keyword gather      (block of 128 threads <-> row)
@@ -442,7 +463,8 @@ vq_select_kernel(const float* __restrict__ kw, const float* __restrict__ table, 
                  const float* __restrict__ tau_ptr, MaskedCols mc, int64_t* __restrict__ idx_out,
                  float* __restrict__ keywords, float* __restrict__ row_stats, float* __restrict__ code_hist,
                  float* __restrict__ lse1_l2, int phases /* bit 0: row statistics, bit 1: arg-max + gather */,
-                 const __half* __restrict__ e16 /* nullable: (Mp, ldE) fp16 e^c, replaces group_max */, int64_t ldE) {
+                 const __half* __restrict__ e16 /* nullable: (Mp, ldE) fp16 e^c, replaces group_max */, int64_t ldE,
+                 int e16_is_p /* the scratch holds P'' = exp((c - 1)/tau + 10) instead of e^c (scp_vq_fwd_save) */) {
   const int lane = threadIdx.x & 31;
   const int64_t m = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (m >= M) return;  // whole warp
@@ -516,6 +538,11 @@ vq_select_kernel(const float* __restrict__ kw, const float* __restrict__ table, 
     // group filter from the e^c scratch: fp16(e^c) >= e^thr (1 - 1e-3) holds for every column with c >= thr (fp16 rounding
     // 4.9e-4 + ex2.approx 2^-22), i.e. the filter only ever admits MORE groups than the exact test c >= thr
     const float thr_e = expf(thr) * (1.0f - 1.0e-3f);
+    // the same filter on P'' (monotone in c; relative error of the stored value: fp16 rounding 4.9e-4 + the repeated-squaring
+    // chain ~3e-6, i.e. LESS than 1e-3 / tau in c).  Below the fp16 normal range the rounding is absolute (6e-8): a threshold
+    // that low (row maximum below about -0.8) admits every group of the candidate chunk instead.
+    const float thr_p = expf((thr - 1.0f) / *tau_ptr + 10.0f) * (1.0f - 1.0e-3f);
+    const bool p_all = e16_is_p && thr_p < 1.3e-4f;
     // every chunk whose maximum could hide the true arg-max is re-scored exactly (usually one or two per row), and
     // inside it only the 8-column groups whose own maximum qualifies
 #pragma unroll 1
@@ -529,7 +556,7 @@ vq_select_kernel(const float* __restrict__ kw, const float* __restrict__ table, 
         unsigned gq;  // bit g: group g of this chunk can hold the arg-max (warp-uniform)
         if (e16) {
           const float e = __half2float(e16[m * ldE + (int64_t)chunk * 32 + lane]);
-          const unsigned cols = __ballot_sync(0xffffffffu, e >= thr_e);
+          const unsigned cols = __ballot_sync(0xffffffffu, p_all || e >= (e16_is_p ? thr_p : thr_e));
           gq = ((cols & 0xffu) ? 1u : 0u) | ((cols & 0xff00u) ? 2u : 0u) | ((cols & 0xff0000u) ? 4u : 0u) |
                ((cols & 0xff000000u) ? 8u : 0u);
         } else {
@@ -625,15 +652,39 @@ struct Sweep2Epi {
 // row segment per warp load, eight loads in flight per lane); the eight warps are combined through shared memory in a
 // fixed order, so the result is deterministic.  Vp/64 = 772 blocks of 256 threads at the full vocabulary: all resident.
 constexpr int kColsumCols = 64;
+__device__ __forceinline__ float fast_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// PMODE: the scratch holds P'' = exp((c - 1)/tau + 10) (scp_vq_fwd_save):  e^c / Z_m = 2^(tau lg2 P'' + (1 - 10 tau) log2 e - log2 Z_m)
+// -- two SFU ops per element instead of a multiply, which makes the pass SFU-bound (72 us against 39 us at M = 2048,
+// V = 49408; an FMA-pipe polynomial for the 2^x half was issue-bound and slower: 102 us); the backward pass saves more than
+// that.  P'' = 0 (masked / padding columns) gives 2^-inf = 0.
+template <bool PMODE>
 __global__ void __launch_bounds__(256)
 vq_colsum_kernel(const __half* __restrict__ e16, int64_t ldE, const float* __restrict__ lse1_l2, int64_t M, int V,
-                 float inv_m, MaskedCols mc, float* __restrict__ avg_probs) {
+                 float inv_m, MaskedCols mc, const float* __restrict__ tau_ptr, float* __restrict__ avg_probs) {
   __shared__ float2 s_part[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t col = (int64_t)blockIdx.x * kColsumCols + 2 * lane;
   const uint32_t* src = reinterpret_cast<const uint32_t*>(e16 + col);
   const int64_t ld32 = ldE >> 1;
+  const float tau = PMODE ? __ldg(tau_ptr) : 1.0f;
+  const float shift = PMODE ? (1.0f - 10.0f * tau) * kLog2e : 0.f;
   float a0 = 0.f, a1 = 0.f;
+  auto add = [&](uint32_t hbits, float w) {
+    const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&hbits));
+    if (PMODE) {
+      const float c = w + shift;
+      a0 += tc::fast_ex2(fmaf(tau, fast_lg2(e.x), c));
+      a1 += tc::fast_ex2(fmaf(tau, fast_lg2(e.y), c));
+    } else {
+      const float wj = tc::fast_ex2(w);
+      a0 = fmaf(e.x, wj, a0);
+      a1 = fmaf(e.y, wj, a1);
+    }
+  };
   int64_t m = warp;
   for (; m + 56 < M; m += 64) {
     uint32_t h[8];
@@ -644,20 +695,9 @@ vq_colsum_kernel(const __half* __restrict__ e16, int64_t ldE, const float* __res
       w[j] = __ldg(lse1_l2 + m + 8 * j);
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
-      const float wj = tc::fast_ex2(w[j]);
-      a0 = fmaf(e.x, wj, a0);
-      a1 = fmaf(e.y, wj, a1);
-    }
+    for (int j = 0; j < 8; ++j) add(h[j], w[j]);
   }
-  for (; m < M; m += 8) {
-    const uint32_t hh = __ldcs(src + m * ld32);
-    const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&hh));
-    const float wj = tc::fast_ex2(__ldg(lse1_l2 + m));
-    a0 = fmaf(e.x, wj, a0);
-    a1 = fmaf(e.y, wj, a1);
-  }
+  for (; m < M; m += 8) add(__ldcs(src + m * ld32), __ldg(lse1_l2 + m));
   s_part[warp][lane] = make_float2(a0, a1);
   __syncthreads();
   if (warp == 0) {
@@ -920,6 +960,114 @@ struct Sweep3Epi {
   }
 };
 
+// Saved-numerator backward sweep (scp_vq_bwd_saved): X = ghat (resident), Y = Ehat, ONE N = 256 accumulator T = ghat . ehat_v.
+// Per logit the epilogue reads T from TMEM and the forward's fp16 P'' from global memory and writes
+//     Q''[m,v] = P''[m,v] (T r_v - s0)       r_v = ||e_v|| / norm_ref
+// as fp16 plus the row sums of Q'' and P''.  No exponential, one TMEM value and 2 + 2 bytes per logit.
+// The thread's row segment of P'' for one tile (4 chunks x 64 B) is kept in registers and refilled one tile ahead: the
+// load of chunk k of the NEXT tile is issued as soon as chunk k of this tile has been consumed (`kUnrollTile`: k is a
+// compile-time constant after unrolling, so the buffer stays in registers).
+struct SweepTEpi {
+  struct Params {
+    const __half* p16;        // (Mp, ld) fp16 P'' written by scp_vq_fwd_save
+    __half* q16;              // (Mp, ld) fp16 Q''
+    int64_t ld;               // = Vp
+    const float* g_aux;       // (Mp,2): |g|, s0
+    const float* table_norm;  // (Vp,)
+    const float* table_mean;  // [D] = norm_ref
+    float* partials;          // (Mp, 2*n_groups, 4): sum Q'', sum P'', 0, 0
+    int n_groups, D;
+  };
+  static constexpr bool kUnrollTile = true;
+  static constexpr int kChunks = kVqBN / 32 / 2;   // chunks per warp and tile (two warps share a lane quadrant)
+  static constexpr int kWarpVec = 32 * 4;          // r_v of the chunk being consumed (lane <-> column, read back broadcast)
+  static constexpr int kSmemBytes = tc::kEpiWarps * kWarpVec;
+  const Params& p;
+  int64_t row;
+  int slot, n_slots, lane, half, cur_nt, nt_stride, nt_end;
+  uint32_t wsm;
+  float pre;  // r_v of this lane's column of the NEXT chunk
+  float s0, inv_norm_ref;
+  uint32_t pbuf[kChunks][16];
+  tc::f32x2 acc_q[2], acc_p[2];
+  __device__ __forceinline__ float vec_load(int nt, int k) const {
+    return __ldg(p.table_norm + (int64_t)nt * kVqBN + (half * kChunks + k) * 32 + lane) * inv_norm_ref;
+  }
+  __device__ __forceinline__ const __half* p_src(int nt, int k) const {
+    return p.p16 + row * p.ld + (int64_t)nt * kVqBN + (half * kChunks + k) * 32;
+  }
+  __device__ __forceinline__ void fetch(int nt, int k) {
+    const __half* src = p_src(nt, k);
+    tc::ldg256_stream(src, pbuf[k]);
+    tc::ldg256_stream(src + 16, pbuf[k] + 8);
+  }
+  __device__ __forceinline__ SweepTEpi(const Params& p_, const WorkInfo& w, const tc::EpiCtx& ctx)
+      : p(p_), row((int64_t)w.m_tile * tc::kTileM + ctx.row_in_tile), slot(w.n_group * ctx.parts + ctx.half),
+        n_slots(ctx.parts * p_.n_groups), half(ctx.half), cur_nt(w.nt_first), nt_stride(w.nt_stride), nt_end(w.nt_end) {
+    lane = ctx.tid & 31;
+    wsm = tc::smem_u32(ctx.smem + (ctx.tid >> 5) * kWarpVec);
+    const bool any = w.nt_first < w.nt_end;
+    inv_norm_ref = 1.0f / p.table_mean[p.D];
+    pre = any ? vec_load(w.nt_first, 0) : 0.f;
+#pragma unroll
+    for (int k = 0; k < kChunks; ++k) {
+      if (any) fetch(w.nt_first, k);
+      else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pbuf[k][i] = 0u;
+      }
+    }
+    s0 = p.g_aux[row * 2 + 1];
+    acc_q[0] = acc_q[1] = acc_p[0] = acc_p[1] = tc::pack2(0.f, 0.f);
+  }
+  __device__ __forceinline__ void tile_begin(int nt) { cur_nt = nt; }
+  __device__ __forceinline__ void tile_end(int) {}
+  __device__ __forceinline__ void chunk_k(int k, int col0, float (&v)[1][32]) {
+    float(&t)[32] = v[0];
+    // r_v of the chunk's 32 columns: parked by lane <-> column, read back as broadcast vectors; the next chunk's value is
+    // fetched while this one is consumed
+    __syncwarp();  // the previous chunk's reads of the vector are complete
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(wsm + (uint32_t)lane * 4), "f"(pre) : "memory");
+    __syncwarp();
+    {
+      const int nk = k + 1 < kChunks ? k + 1 : 0;
+      const int nnt = k + 1 < kChunks ? cur_nt : cur_nt + nt_stride;
+      if (nnt < nt_end) pre = vec_load(nnt, nk);
+    }
+    const tc::f32x2 ns0 = tc::pack2(-s0, -s0);
+    uint32_t hq[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 rv = tc::lds128f(wsm + i * 16);
+      const tc::f32x2 rr[2] = {tc::pack2(rv.x, rv.y), tc::pack2(rv.z, rv.w)};
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int e = 4 * i + 2 * j;
+        const tc::f32x2 tj = tc::fma2(tc::pack2(t[e], t[e + 1]), rr[j], ns0);  // (g . e_v)/(|g| norm_ref) - s0
+        const tc::f32x2 pj = tc::cvt_f32x2_f16x2(pbuf[k][e >> 1]);
+        const tc::f32x2 qj = tc::mul2(pj, tj);
+        acc_p[j] = tc::add2(acc_p[j], pj);
+        acc_q[j] = tc::add2(acc_q[j], qj);
+        hq[e >> 1] = tc::cvt_f16x2(qj);
+      }
+    }
+    __half* dst = p.q16 + row * p.ld + col0;
+    tc::stg256(dst, hq);
+    tc::stg256(dst + 16, hq + 8);
+    const int next = cur_nt + nt_stride;
+    if (next < nt_end) fetch(next, k);  // this row's chunk k of the next tile: in flight for a whole tile
+  }
+  __device__ __forceinline__ void finish() {
+    *reinterpret_cast<float4*>(p.partials + (row * n_slots + slot) * 4) =
+        make_float4(tc::hsum2(tc::add2(acc_q[0], acc_q[1])), tc::hsum2(tc::add2(acc_p[0], acc_p[1])), 0.f, 0.f);
+  }
+};
+// bring-up switch: SCP_VQ_SAVED=0 makes scp_vq_bwd_saved ignore the saved numerators (A/B against the recompute path)
+static bool vq_saved_enabled() {
+  static const bool on = [] { const char* e = getenv("SCP_VQ_SAVED"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 // plain accumulator store: out[k_split][x][row][col]  (fp32)
 template <int NX>
 struct StoreEpi {
@@ -966,7 +1114,9 @@ vq_bwd_finalize_kernel(const float* __restrict__ uw /* (k_splits, 2, Mp, D) */, 
     sq += q.x; sp += q.y; sqc += q.z; spc += q.w;
   }
   const float s_adj = sp > 0.f ? sq / sp : 0.f;
-  const float scale = g_aux[m * 2] * table_mean[D] / (kPScale * tau);
+  // U, W carry the row's own normaliser sum P (2^14 on the recompute path, sum_v P'' on the saved-numerator path)
+  const float inv_sp = sp > 0.f ? 1.0f / sp : 0.f;
+  const float scale = g_aux[m * 2] * table_mean[D] * inv_sp / tau;
   const float inv_norm = row_stats[m * 4 + 3];
   float4 u = make_float4(0.f, 0.f, 0.f, 0.f), w = u;
   for (int ks = 0; ks < k_splits; ++ks) {
@@ -990,7 +1140,7 @@ vq_bwd_finalize_kernel(const float* __restrict__ uw /* (k_splits, 2, Mp, D) */, 
                   (gk[2] - proj * kh[2]) * inv_norm, (gk[3] - proj * kh[3]) * inv_norm);
   if (g_tau && threadIdx.x == 0) {
     // d/dtau = -(1/tau^2) sum_v P (T - s) c      (T in true units = T' * |g| * norm_ref)
-    const float contrib = -(g_aux[m * 2] * table_mean[D]) * (sqc - s_adj * spc) / (kPScale * tau * tau);
+    const float contrib = -(g_aux[m * 2] * table_mean[D]) * (sqc - s_adj * spc) * inv_sp / (tau * tau);
     atomicAdd(g_tau, contrib);
   }
 }
@@ -1171,7 +1321,7 @@ static int vq_sweep1_groups(int64_t Mp, int64_t Vp) {
   if (g > n_tiles) g = n_tiles;
   return g;
 }
-static VqFwdWs vq_fwd_ws(void* base, int64_t M, int64_t V) {
+static VqFwdWs vq_fwd_ws(void* base, int64_t M, int64_t V, bool with_scratch = true) {
   const int64_t Mp = round_up(M, tc::kTileM), Vp = scp_vq_padded_vocab(V);
   VqFwdWs w{};
   w.n_chunks = (int)(Vp / 32);
@@ -1184,10 +1334,11 @@ static VqFwdWs vq_fwd_ws(void* base, int64_t M, int64_t V) {
   };
   w.chunk_max = static_cast<float*>(take((size_t)Mp * w.n_chunks * 4));
   w.group_max = static_cast<float*>(take((size_t)Mp * w.n_chunks * 4 * 4));  // four 8-column group maxima per chunk
-  w.partials = static_cast<float*>(take((size_t)Mp * w.n_groups * 2 * 16));
+  w.partials = static_cast<float*>(take((size_t)Mp * w.n_groups * 4 * 16));  // up to 4 epilogue warps per lane quadrant
   w.lse1_l2 = static_cast<float*>(take((size_t)round_up(M, 256) * 4));
   w.metric_part = static_cast<float*>(take((size_t)(kMetricBlocks * 3 + 1) * 4));  // + the ticket counter
-  w.e16 = vq_colsum_enabled() ? static_cast<__half*>(take((size_t)Mp * Vp * 2)) : nullptr;
+  // (scp_vq_fwd_save: the caller's saved_probs buffer is the scratch)
+  w.e16 = with_scratch && vq_colsum_enabled() ? static_cast<__half*>(take((size_t)Mp * Vp * 2)) : nullptr;
   w.total = off;
   return w;
 }
@@ -1225,7 +1376,13 @@ static int vq_pipe_ring() {
   return r;
 }
 
-static VqBwdWs vq_bwd_ws(void* base, int64_t M, int64_t V, int64_t D) {
+// the saved-numerator path of scp_vq_bwd_saved is taken iff ... (one predicate for the launch and the workspace size)
+static bool vq_saved_path_ok(int64_t M, int64_t D, bool want_tau) {
+  const int64_t Mp = round_up(M, tc::kTileM);
+  return !want_tau && !vq_bwd_pipe_mode(D) && vq_use_pair((int)(Mp / tc::kTileM)) && vq_saved_enabled() &&
+         tc::resident_smem_bytes<kVqBN, 1, 5, SweepTEpi, tc::MC_PAIR>((int)(D / tc::kChunkK)) <= tc::kMaxDynSmem;
+}
+static VqBwdWs vq_bwd_ws(void* base, int64_t M, int64_t V, int64_t D, bool saved = false) {
   const int64_t Mp = round_up(M, tc::kTileM), Vp = scp_vq_padded_vocab(V);
   VqBwdWs w{};
   w.pipe_mode = vq_bwd_pipe_mode(D);
@@ -1282,11 +1439,36 @@ static VqBwdWs vq_bwd_ws(void* base, int64_t M, int64_t V, int64_t D) {
   };
   w.g_hat = static_cast<__half*>(take((size_t)Mp * D * 2));
   w.g_aux = static_cast<float*>(take((size_t)Mp * 2 * 4));
-  w.pq = static_cast<__half*>(take((size_t)2 * Mp * Vp * 2));
+  w.pq = static_cast<__half*>(take((size_t)(saved ? 1 : 2) * Mp * Vp * 2));  // saved: Q'' only, P'' is the forward's buffer
   w.partials = static_cast<float*>(take((size_t)Mp * w.n_groups * 2 * 16));
   w.uw = static_cast<float*>(take((size_t)w.k_splits * 2 * Mp * D * 4));
   w.total = off;
   return w;
+}
+
+template <bool SAVE>
+static int launch_sweep1(const GemmMaps& maps, const Sched& sc, const VqFwdWs& ws, const float* tau, __half* e16,
+                         int64_t Vp, int64_t V, const MaskedCols& mc, bool pair, cudaStream_t s) {
+  using Epi = Sweep1EpiT<SAVE>;
+  typename Epi::Params ep{};
+  ep.chunk_max = ws.chunk_max;
+  ep.group_max = ws.group_max;
+  ep.partials = ws.partials;
+  ep.tau = tau;
+  ep.e16 = e16;
+  ep.ldE = Vp;
+  static const int s1_dbg = [] { const char* e = getenv("SCP_VQ_S1_DBG"); return e ? atoi(e) : 0; }();
+  ep.dbg = s1_dbg;
+  ep.n_chunks = ws.n_chunks;
+  ep.n_groups = ws.n_groups;
+  ep.V = (int)V;
+  ep.mc = mc;
+  // resident keyword tile (128 x D fp16) when it fits next to a 6-stage ring of table half-tiles (D <= 512)
+  const bool xres = pair && vq_resident_enabled() &&
+                    tc::resident_smem_bytes<kVqBN, 1, 6, Epi, tc::MC_PAIR>(sc.k_chunks) <= tc::kMaxDynSmem;
+  if (xres) return tc::launch_stream_gemm<kVqBN, 1, 6, Epi, 2, tc::MC_PAIR, true>(maps, sc, ep, s, "vq_sweep1");
+  if (pair) return tc::launch_stream_gemm<kVqBN, 1, 6, Epi, 2, tc::MC_PAIR>(maps, sc, ep, s, "vq_sweep1");
+  return tc::launch_stream_gemm<kVqBN, 1, 4, Epi>(maps, sc, ep, s, "vq_sweep1");
 }
 
 static int check_vq_shape(int64_t M, int64_t V, int64_t D) {
@@ -1328,12 +1510,28 @@ extern "C" int scp_vq_prepare_table(const float* table, int64_t V, int64_t D, vo
 }
 
 extern "C" size_t scp_vq_fwd_workspace_bytes(int64_t M, int64_t V, int64_t) { return vq_fwd_ws(nullptr, M, V).total; }
+extern "C" size_t scp_vq_fwd_save_workspace_bytes(int64_t M, int64_t V, int64_t) {
+  return vq_fwd_ws(nullptr, M, V, false).total;
+}
+
+extern "C" size_t scp_vq_saved_probs_bytes(int64_t M, int64_t V) {
+  return (size_t)round_up(M, tc::kTileM) * (size_t)scp_vq_padded_vocab(V) * 2;
+}
 
 extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int64_t D, const void* table_hat,
                           const float* table_norm, const float* table, const int32_t* masked_cols, int n_masked,
                           const float* tau, int64_t* idx, float* keywords, float* row_stats, float* code_hist,
                           float* avg_probs, float* metrics, void* kw_hat, void* workspace, size_t workspace_bytes,
                           scp_stream_t stream) {
+  return scp_vq_fwd_save(kw, M, K, V, D, table_hat, table_norm, table, masked_cols, n_masked, tau, idx, keywords, row_stats,
+                         code_hist, avg_probs, metrics, kw_hat, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int scp_vq_fwd_save(const float* kw, int64_t M, int64_t K, int64_t V, int64_t D, const void* table_hat,
+                               const float* table_norm, const float* table, const int32_t* masked_cols, int n_masked,
+                               const float* tau, int64_t* idx, float* keywords, float* row_stats, float* code_hist,
+                               float* avg_probs, float* metrics, void* kw_hat, void* saved_probs, void* workspace,
+                               size_t workspace_bytes, scp_stream_t stream) {
   int rc = check_device_arch();
   if (rc) return rc;
   rc = check_vq_shape(M, V, D);
@@ -1343,7 +1541,7 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
                 "vq_fwd: null pointer");
   SCP_CHECK_ARG(K > 0 && M % K == 0, "vq_fwd: M=%lld is not a multiple of K=%lld", (long long)M, (long long)K);
   SCP_CHECK_ARG(n_masked >= 0 && n_masked <= SCP_MAX_MASKED && (n_masked == 0 || masked_cols), "vq_fwd: masked cols");
-  const VqFwdWs ws = vq_fwd_ws(workspace, M, V);
+  const VqFwdWs ws = vq_fwd_ws(workspace, M, V, saved_probs == nullptr);
   if (workspace_bytes < ws.total) return fail(SCP_ERR_WORKSPACE, "vq_fwd: workspace %zu < %zu", workspace_bytes, ws.total);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int64_t Mp = round_up(M, tc::kTileM), Vp = scp_vq_padded_vocab(V);
@@ -1355,6 +1553,7 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
   SCP_CUDA_LAUNCH_CHECK("vq_prep_kw");
 
   // ---- sweep 1
+  const int s1_parts = 2;  // partial-statistics slots per V group = epilogue warps per lane quadrant of the launched kernel
   {
     GemmMaps maps{};
     if ((rc = tc::make_tmap_f16(&maps.x[0], kw_hat, Mp, D, D, tc::kTileM))) return rc;
@@ -1369,27 +1568,15 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
     sc.k_splits = 1;
     sc.m_half = sc.m_tiles;
     sc.n_upper_off = 0;
-    Sweep1Epi::Params ep{};
-    ep.chunk_max = ws.chunk_max;
-    ep.group_max = ws.group_max;
-    ep.partials = ws.partials;
-    ep.tau = tau;
-    ep.e16 = avg_probs ? ws.e16 : nullptr;
-    ep.ldE = Vp;
-    static const int s1_dbg = [] { const char* e = getenv("SCP_VQ_S1_DBG"); return e ? atoi(e) : 0; }();
-    ep.dbg = s1_dbg;
-    ep.n_chunks = ws.n_chunks;
-    ep.n_groups = ws.n_groups;
-    ep.V = (int)V;
-    ep.mc = mc;
-    // resident keyword tile (128 x D fp16) when it fits next to a 6-stage ring of table half-tiles (D <= 512)
-    const bool xres = pair && vq_resident_enabled() &&
-                      tc::resident_smem_bytes<kVqBN, 1, 6, Sweep1Epi, tc::MC_PAIR>(sc.k_chunks) <= tc::kMaxDynSmem;
-    if (xres) rc = tc::launch_stream_gemm<kVqBN, 1, 6, Sweep1Epi, 2, tc::MC_PAIR, true>(maps, sc, ep, s, "vq_sweep1");
-    else if (pair) rc = tc::launch_stream_gemm<kVqBN, 1, 6, Sweep1Epi, 2, tc::MC_PAIR>(maps, sc, ep, s, "vq_sweep1");
-    else rc = tc::launch_stream_gemm<kVqBN, 1, 4, Sweep1Epi>(maps, sc, ep, s, "vq_sweep1");
+    // scp_vq_fwd_save: the caller's buffer takes the place of the workspace scratch and receives P'' (always written: the
+    // backward pass needs it even when prob_perplexity is not wanted)
+    __half* e16 = saved_probs ? static_cast<__half*>(saved_probs) : (avg_probs ? ws.e16 : nullptr);
+    rc = saved_probs ? launch_sweep1<true>(maps, sc, ws, tau, e16, Vp, V, mc, pair, s)
+                     : launch_sweep1<false>(maps, sc, ws, tau, e16, Vp, V, mc, pair, s);
     if (rc) return rc;
   }
+  // the (M,V) fp16 scratch sweep 1 has written: e^c in the workspace, or P'' in the caller's buffer (scp_vq_fwd_save)
+  const __half* scratch = saved_probs ? static_cast<const __half*>(saved_probs) : (avg_probs ? ws.e16 : nullptr);
   // ---- exact arg-max, statistics, gather
   const size_t sel_smem = (size_t)4 * ws.n_chunks * sizeof(float);  // one row of chunk maxima per warp
   if (sel_smem > 48 * 1024)
@@ -1401,8 +1588,8 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
 #define SCP_SELECT_LAUNCH(NVV, STREAM, PHASES)                                                                         \
   vq_select_kernel<NVV><<<(unsigned)ceil_div(M, 4), 128, sel_smem, STREAM>>>(                                          \
       kw, table, table_norm, reinterpret_cast<const __half*>(table_hat), reinterpret_cast<const __half*>(kw_hat), M,   \
-      (int)V, (int)D, ws.chunk_max, ws.group_max, ws.n_chunks, ws.partials, 2 * ws.n_groups, tau, mc, idx, keywords,   \
-      row_stats, code_hist, ws.lse1_l2, PHASES, avg_probs ? ws.e16 : nullptr, Vp)
+      (int)V, (int)D, ws.chunk_max, ws.group_max, ws.n_chunks, ws.partials, s1_parts * ws.n_groups, tau, mc, idx, keywords, \
+      row_stats, code_hist, ws.lse1_l2, PHASES, scratch, Vp, saved_probs ? 1 : 0)
 #define SCP_SELECT(STREAM, PHASES)                                                                                     \
   do {                                                                                                                 \
     if (D <= 128) SCP_SELECT_LAUNCH(1, STREAM, PHASES);                                                                \
@@ -1432,9 +1619,13 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
 #undef SCP_SELECT
 #undef SCP_SELECT_LAUNCH
   // ---- column sums -- skipped when the caller does not want prob_perplexity
-  if (avg_probs && ws.e16) {
-    vq_colsum_kernel<<<(unsigned)(Vp / kColsumCols), 256, 0, s>>>(ws.e16, Vp, ws.lse1_l2, M, (int)V, 1.0f / (float)M, mc,
-                                                                 avg_probs);
+  if (avg_probs && scratch) {
+    if (saved_probs)
+      vq_colsum_kernel<true><<<(unsigned)(Vp / kColsumCols), 256, 0, s>>>(scratch, Vp, ws.lse1_l2, M, (int)V, 1.0f / (float)M,
+                                                                         mc, tau, avg_probs);
+    else
+      vq_colsum_kernel<false><<<(unsigned)(Vp / kColsumCols), 256, 0, s>>>(scratch, Vp, ws.lse1_l2, M, (int)V, 1.0f / (float)M,
+                                                                          mc, tau, avg_probs);
     if (cudaGetLastError() != cudaSuccess) {
       if (forked) join_from_side(s);  // never leave the helper stream un-joined (stream capture would be invalidated)
       return fail(SCP_ERR_CUDA, "vq_colsum launch failed");
@@ -1480,6 +1671,13 @@ extern "C" int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int6
 extern "C" size_t scp_vq_bwd_workspace_bytes(int64_t M, int64_t V, int64_t D) {
   return vq_bwd_ws(nullptr, M, V, D).total;
 }
+extern "C" int scp_vq_bwd_saved_available(int64_t M, int64_t V, int64_t D) {
+  (void)V;
+  return vq_saved_path_ok(M, D, false) ? 1 : 0;
+}
+extern "C" size_t scp_vq_bwd_saved_workspace_bytes(int64_t M, int64_t V, int64_t D, int want_tau) {
+  return vq_bwd_ws(nullptr, M, V, D, vq_saved_path_ok(M, D, want_tau != 0)).total;
+}
 
 template <int BN>
 static int launch_gemm_out(const GemmMaps& maps, const Sched& sc, const StoreEpi<2>::Params& ep, bool pair, cudaStream_t s) {
@@ -1494,6 +1692,15 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
                           const float* table_norm, const float* table_mean, const float* row_stats,
                           const int32_t* masked_cols, int n_masked, const float* tau, float* g_kw, float* g_tau,
                           void* workspace, size_t workspace_bytes, scp_stream_t stream) {
+  return scp_vq_bwd_saved(g_keywords, kw, M, V, D, kw_hat, table_hat, table_hat_t, table_norm, table_mean, row_stats,
+                          masked_cols, n_masked, tau, nullptr, g_kw, g_tau, workspace, workspace_bytes, stream);
+}
+
+extern "C" int scp_vq_bwd_saved(const float* g_keywords, const float* kw, int64_t M, int64_t V, int64_t D,
+                                const void* kw_hat, const void* table_hat, const void* table_hat_t,
+                                const float* table_norm, const float* table_mean, const float* row_stats,
+                                const int32_t* masked_cols, int n_masked, const float* tau, const void* saved_probs,
+                                float* g_kw, float* g_tau, void* workspace, size_t workspace_bytes, scp_stream_t stream) {
   int rc = check_device_arch();
   if (rc) return rc;
   rc = check_vq_shape(M, V, D);
@@ -1502,7 +1709,8 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
                     tau && g_kw && workspace,
                 "vq_bwd: null pointer");
   SCP_CHECK_ARG(n_masked >= 0 && n_masked <= SCP_MAX_MASKED && (n_masked == 0 || masked_cols), "vq_bwd: masked cols");
-  const VqBwdWs ws = vq_bwd_ws(workspace, M, V, D);
+  const bool use_saved = saved_probs && vq_saved_path_ok(M, D, g_tau != nullptr);
+  const VqBwdWs ws = vq_bwd_ws(workspace, M, V, D, use_saved);
   if (workspace_bytes < ws.total) return fail(SCP_ERR_WORKSPACE, "vq_bwd: workspace %zu < %zu", workspace_bytes, ws.total);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int64_t Mp = round_up(M, tc::kTileM), Vp = scp_vq_padded_vocab(V);
@@ -1572,8 +1780,40 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
     SCP_CUDA_LAUNCH_CHECK("vq_bwd_pipe_finalize");
     return SCP_OK;
   }
+  // ---- saved-numerator path: T' = ghat . Ehat^T only (one N = 256 accumulator, resident ghat), Q'' = P''(T' - s0) from the
+  //      forward's P''; the output GEMM reads P'' straight from the forward's buffer.  4 M V D FLOP less than the recompute
+  //      path below, no exponentials, half the scratch.  A learnable temperature (g_tau) needs the logits: recompute path.
+  const __half* p_src = nullptr;  // W operand of the output GEMM (default: second half of the scratch)
+  int fin_groups = 2 * ws.n_groups;
+  if (use_saved) {
+    GemmMaps maps{};
+    if ((rc = tc::make_tmap_f16(&maps.x[0], ws.g_hat, Mp, D, D, tc::kTileM))) return rc;
+    maps.x[1] = maps.x[0];
+    if ((rc = tc::make_tmap_f16(&maps.y, table_hat, Vp, D, D, kVqBN / 2))) return rc;
+    Sched sc{};
+    sc.m_tiles = (int)(Mp / tc::kTileM);
+    sc.n_tiles = (int)(Vp / kVqBN);
+    sc.n_groups = vq_sweep1_groups(Mp, Vp);
+    sc.k_chunks = (int)(D / tc::kChunkK);
+    sc.k_splits = 1;
+    sc.m_half = sc.m_tiles;
+    sc.n_upper_off = 0;
+    SweepTEpi::Params ep{};
+    ep.p16 = static_cast<const __half*>(saved_probs);
+    ep.q16 = ws.pq;
+    ep.ld = Vp;
+    ep.g_aux = ws.g_aux;
+    ep.table_norm = table_norm;
+    ep.table_mean = table_mean;
+    ep.partials = ws.partials;
+    ep.n_groups = sc.n_groups;
+    ep.D = (int)D;
+    if ((rc = tc::launch_stream_gemm<kVqBN, 1, 5, SweepTEpi, 2, tc::MC_PAIR, 1>(maps, sc, ep, s, "vq_sweep_t"))) return rc;
+    p_src = static_cast<const __half*>(saved_probs);
+    fin_groups = 2 * sc.n_groups;
+  }
   // ---- sweep 3: P~, Q~ and row sums
-  {
+  if (!use_saved) {
     GemmMaps maps{};
     const bool pair = vq_use_pair((int)(Mp / tc::kTileM));
     if ((rc = tc::make_tmap_f16(&maps.x[0], kw_hat, Mp, D, D, tc::kTileM))) return rc;
@@ -1613,7 +1853,7 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
   {
     GemmMaps maps{};
     if ((rc = tc::make_tmap_f16(&maps.x[0], ws.pq, Mp, Vp, Vp, tc::kTileM))) return rc;
-    if ((rc = tc::make_tmap_f16(&maps.x[1], ws.pq + Mp * Vp, Mp, Vp, Vp, tc::kTileM))) return rc;
+    if ((rc = tc::make_tmap_f16(&maps.x[1], p_src ? p_src : ws.pq + Mp * Vp, Mp, Vp, Vp, tc::kTileM))) return rc;
     const bool pair = vq_use_pair((int)(Mp / tc::kTileM));
     if ((rc = tc::make_tmap_f16(&maps.y, table_hat_t, D, Vp, Vp, pair ? ws.bn_out / 2 : ws.bn_out))) return rc;
     Sched sc{};
@@ -1635,7 +1875,7 @@ extern "C" int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, i
   }
   if (g_tau && cudaMemsetAsync(g_tau, 0, 4, s) != cudaSuccess) return fail(SCP_ERR_CUDA, "memset g_tau");
   vq_bwd_finalize_kernel<<<(unsigned)M, (unsigned)(D / 4), 0, s>>>(ws.uw, ws.k_splits, M, Mp, (int)D, ws.partials,
-                                                                  2 * ws.n_groups, ws.g_aux, kw, row_stats, table_mean,
+                                                                  fin_groups, ws.g_aux, kw, row_stats, table_mean,
                                                                   tau, g_kw, g_tau);
   SCP_CUDA_LAUNCH_CHECK("vq_bwd_finalize");
   return SCP_OK;

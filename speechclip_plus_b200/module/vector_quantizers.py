@@ -95,7 +95,7 @@ class _FusedVQFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, kw: torch.Tensor, tau: torch.Tensor, cache: TableEntry, prob_msk, training: bool,
-                want_avg_probs: bool):
+                want_avg_probs: bool, save_probs: bool = False):
         lib = _lib.load()
         B, K, D = kw.shape
         M = B * K
@@ -115,17 +115,24 @@ class _FusedVQFn(torch.autograd.Function):
         avg_probs = torch.empty(Vp, dtype=torch.float32, device=dev) if want_avg_probs else None
         metrics = torch.empty(3 + K, dtype=torch.float32, device=dev)
         kw_hat = torch.empty((Mp, D), dtype=torch.float16, device=dev)
-        ws_bytes = lib.scp_vq_fwd_workspace_bytes(M, V, D)
+        # the soft-max numerators the backward pass would otherwise recompute take the place of the forward's (M,V) scratch;
+        # they are owned by this call (never a shared workspace: a second forward before the backward must not overwrite them)
+        saved = None
+        if training and save_probs and ctx.needs_input_grad[0] and lib.scp_vq_bwd_saved_available(M, V, D):
+            saved = torch.empty(lib.scp_vq_saved_probs_bytes(M, V), dtype=torch.uint8, device=dev)
+        ws_bytes = (lib.scp_vq_fwd_save_workspace_bytes if saved is not None else lib.scp_vq_fwd_workspace_bytes)(M, V, D)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            st = lib.scp_vq_fwd(_lib.ptr(kw2), M, K, V, D, _lib.ptr(cache.hat), _lib.ptr(cache.norm),
-                                _lib.ptr(cache.table), masked, n_masked, _lib.ptr(tau_f), _lib.ptr(idx),
-                                _lib.ptr(kw_out), _lib.ptr(row_stats), _lib.ptr(code_hist), _lib.ptr(avg_probs),
-                                _lib.ptr(metrics), _lib.ptr(kw_hat), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
-        _lib.check(st, "scp_vq_fwd")
+            st = lib.scp_vq_fwd_save(_lib.ptr(kw2), M, K, V, D, _lib.ptr(cache.hat), _lib.ptr(cache.norm),
+                                     _lib.ptr(cache.table), masked, n_masked, _lib.ptr(tau_f), _lib.ptr(idx),
+                                     _lib.ptr(kw_out), _lib.ptr(row_stats), _lib.ptr(code_hist), _lib.ptr(avg_probs),
+                                     _lib.ptr(metrics), _lib.ptr(kw_hat), _lib.ptr(saved), _lib.ptr(ws), ws_bytes,
+                                     _lib.stream_ptr(dev))
+        _lib.check(st, "scp_vq_fwd_save")
         ctx.training = training
         ctx.set_materialize_grads(False)  # five of the six outputs carry no gradient: do not zero-fill them per step
         if training:
+            ctx.saved_probs = saved
             ctx.save_for_backward(kw2, kw_hat, row_stats, tau_f)
             ctx.cache = cache
             ctx.prob_msk = list(prob_msk)
@@ -143,13 +150,13 @@ class _FusedVQFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_out, *unused):
         if not ctx.training:  # eval: subword_prob = hard one-hot, no gradient path (my_vector_quantizer.py:138-139)
-            return None, None, None, None, None, None
+            return None, None, None, None, None, None, None
         lib = _lib.load()
         kw2, kw_hat, row_stats, tau_f = ctx.saved_tensors
         cache = ctx.cache
         B, K, D = ctx.shape
         if g_out is None:
-            return None, None, None, None, None, None
+            return None, None, None, None, None, None, None
         M = B * K
         dev = kw2.device
         g = g_out.reshape(M, D).float().contiguous()
@@ -157,15 +164,18 @@ class _FusedVQFn(torch.autograd.Function):
         g_kw = torch.empty((M, D), dtype=torch.float32, device=dev)
         need_tau = ctx.needs_input_grad[1]
         g_tau = torch.empty(1, dtype=torch.float32, device=dev) if need_tau else None
-        ws_bytes = lib.scp_vq_bwd_workspace_bytes(M, cache.V, D)
+        saved = None if need_tau else ctx.saved_probs
+        ws_bytes = (lib.scp_vq_bwd_saved_workspace_bytes(M, cache.V, D, int(need_tau)) if saved is not None
+                    else lib.scp_vq_bwd_workspace_bytes(M, cache.V, D))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            st = lib.scp_vq_bwd(_lib.ptr(g), _lib.ptr(kw2), M, cache.V, D, _lib.ptr(kw_hat), _lib.ptr(cache.hat),
-                                _lib.ptr(cache.hat_t), _lib.ptr(cache.norm), _lib.ptr(cache.mean),
-                                _lib.ptr(row_stats), masked, n_masked, _lib.ptr(tau_f), _lib.ptr(g_kw),
-                                _lib.ptr(g_tau), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
-        _lib.check(st, "scp_vq_bwd")
-        return g_kw.view(B, K, D).to(ctx.in_dtype), g_tau, None, None, None, None
+            st = lib.scp_vq_bwd_saved(_lib.ptr(g), _lib.ptr(kw2), M, cache.V, D, _lib.ptr(kw_hat), _lib.ptr(cache.hat),
+                                      _lib.ptr(cache.hat_t), _lib.ptr(cache.norm), _lib.ptr(cache.mean),
+                                      _lib.ptr(row_stats), masked, n_masked, _lib.ptr(tau_f),
+                                      _lib.ptr(saved), _lib.ptr(g_kw),
+                                      _lib.ptr(g_tau), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
+        _lib.check(st, "scp_vq_bwd_saved")
+        return g_kw.view(B, K, D).to(ctx.in_dtype), g_tau, None, None, None, None, None
 
 
 class _DenseVQFn(torch.autograd.Function):
@@ -319,8 +329,13 @@ class SimpleVectorQuantizer(nn.Module):
         _lib.require_cuda(keywords, "quantize_keywords")
         cache = self._table_cache.get(table)
         B, K, _ = keywords.shape
+        # fixed / scheduled temperature >= 0.07 (every shipped recipe: 0.1): the forward keeps the fp16 soft-max numerators
+        # and the backward skips the k . E^T product and the exponentials (scp_vq_fwd_save / scp_vq_bwd_saved); a learnable
+        # temperature needs the logits for d/dtau and a smaller one the full dynamic range: recompute path
+        save_probs = (self.training and self.temp_type != "learnable" and torch.is_grad_enabled()
+                      and keywords.requires_grad and self._temp_as_float() >= 0.07)
         out, idx, metrics, row_stats, code_hist, avg_probs = _FusedVQFn.apply(
-            keywords, self.curr_temp, cache, tuple(prob_msk), self.training, compute_prob_perplexity)
+            keywords, self.curr_temp, cache, tuple(prob_msk), self.training, compute_prob_perplexity, save_probs)
         result = {"num_vars": cache.V}
         self._finish(result, metrics, K)
         result["subword_prob"] = None

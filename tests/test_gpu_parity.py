@@ -669,6 +669,41 @@ def test_vq_full_size_vs_fp64_oracle(scp, cfg):
     assert row.max().item() < 5 * TOL, row.max().item()
 
 
+@pytest.mark.parametrize("cfg", [(32, 8, 8112, 512, 0.1), (24, 12, 19787, 256, 0.5), (256, 8, 49408, 512, 0.1), (20, 8, 8112, 768, 0.1)],
+                         ids=["flickr_vocab", "generic_tau_D256", "bench_shape", "D768_falls_back"])
+def test_vq_saved_numerators_vs_recompute(scp, cfg):
+    """The two forms of the straight-through backward (kw_branches.py:181-197 + my_vector_quantizer.py:130-136) must agree:
+    `save_probs=True` (scp_vq_fwd_save / scp_vq_bwd_saved: the forward keeps P'' = exp((c-1)/tau + 10) as fp16, the column
+    sums and the arg-max filter read it, the backward forms only g . E^T) against `save_probs=False` (the backward recomputes
+    k . E^T and the soft-max).  Same indices, metrics within 1e-4 of each other, keyword gradients within 5e-4 of each other
+    and within the 1e-3 tolerance of the fp64 oracle.  D = 768 has no resident tile: the saved forward must still be
+    correct and the backward silently takes the recompute path."""
+    from speechclip_plus_b200.module.vector_quantizers import _FusedVQFn
+    B, K, V, D, tau = cfg
+    gen = torch.Generator().manual_seed(B * 7 + V)
+    table = (torch.randn(V, D, generator=gen) * 0.02 + 0.003 * torch.randn(1, D, generator=gen)).cuda()
+    kw = (torch.randn(B, K, D, generator=gen).cuda() * table.std(0) + table.mean(0))
+    pick = torch.randint(0, V, (B,), generator=gen).cuda()
+    kw[:, 0] = table[pick] * 1.5 + 0.002 * torch.randn(B, D, generator=gen).cuda()   # rows with a cosine close to 1
+    gout = torch.randn(B, K, D, generator=gen).cuda()
+    vq = _make_vq(scp, f"fixed={tau}", True)
+    cache = vq._table_cache.get(table)
+    outs = []
+    for save in (True, False):
+        kwd = kw.clone().requires_grad_(True)
+        out, idx, metrics, row_stats, code_hist, avg_probs = _FusedVQFn.apply(kwd, vq.curr_temp, cache, (0, 2, 3), True, True, save)
+        (g,) = torch.autograd.grad(out, [kwd], grad_outputs=gout)
+        outs.append((idx, metrics, avg_probs[:V], g))
+    (i1, m1, a1, g1), (i0, m0, a0, g0) = outs
+    assert torch.equal(i1, i0)
+    assert rel_err(m1, m0) < 1e-4 and rel_err(a1, a0) < 2e-4
+    assert norm_err(g1, g0) < 5e-4, norm_err(g1, g0)
+    if V <= 20000:
+        g_ref, _ = oracle.vq_keyword_grad(kw.double().cpu(), table.double().cpu(), torch.tensor(tau, dtype=torch.float64),
+                                          gout.double().cpu())
+        assert norm_err(g1, g_ref) < TOL and norm_err(g0, g_ref) < TOL
+
+
 @pytest.mark.parametrize("mode", ["1", "2"], ids=["fused_ring_in_L2", "two_launches"])
 def test_vq_backward_pipeline_opt_in(mode):
     """The producer/consumer form of the VQ backward (csrc/scp_vq_pipe.cuh, SCP_VQ_BWD_PIPE=1/2: MN-major tcgen05 operands,
