@@ -836,7 +836,7 @@ def run_gpu_arm(args):
                     data="synthetic", impl="b200", config=config,
                     launch="one CUDA graph per step" if not args.no_graph else "eager launches",
                     numerics="fp32 I/O; VQ tensor-core operands fp16 with fp32 accumulation and exact fp64 arg-max "
-                             "re-scoring, avg_probs reduced from an fp16 e^c scratch; InfoNCE split-fp16 (hi/lo) operands",
+                             "re-scoring, the forward keeps the fp16 soft-max numerators P'' = exp((c-1)/tau+10) for the backward (avg_probs and the arg-max filter are derived from them); InfoNCE split-fp16 (hi/lo) operands",
                     kernel_timing="every kernel group = one CUDA-graph replay after a 192 MB L2 flush, median of 7",
                     roofline=roofline, roofline_vq=roofline_vq, kernels=kernels, configs=configs,
                     multi_gpu_check=check, cpu_baseline=cpu_baseline, cpu_baseline_fair=cpu_fair, e2e=e2e,

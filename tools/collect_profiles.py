@@ -32,7 +32,7 @@ json.dump({"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch 
            "--steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-configs --no-breakdown --no-graph` (profiles/%s_ncu_full_hot_kernels.csv, "
            "tools/profile_round.sh); keyed like bench.py's kernel groups (group = sum of its kernels)" % tag,
            "wsum_fwd": g('wsum_fwd'), "wsum_bwd": g('wsum_bwd'), "vq_fwd": g('Sweep1', 'Sweep2', 'vq_select', 'vq_colsum'),
-           "vq_bwd": g('Sweep3', 'StoreEpi<2>'), "nce_fwd_bwd": g('Nce')}, open(f"{pr}/traffic.json", "w"), indent=2)
+           "vq_bwd": g('Sweep3', 'SweepT', 'StoreEpi<2>'), "nce_fwd_bwd": g('Nce')}, open(f"{pr}/traffic.json", "w"), indent=2)
 shutil.copy(f"{go}/{tag}_bench.json", f"{pr}/{tag}_bench.json")
 shutil.copy(f"{go}/{tag}_launches.csv", f"{pr}/{tag}_launches_bench_steps2.csv")
 for extra in ("aux_kernels",):
