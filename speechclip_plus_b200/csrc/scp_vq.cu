@@ -5,25 +5,29 @@
 // Forward pipeline (the (M,V) fp32 logit matrix is never written to memory):
 //   vq_prep_kw          kw fp32 -> unit rows in fp16 (A operand) + 1/||kw||
 //   sweep 1 (tcgen05)   S = khat * Ehat^T tile by tile; per row: running softmax statistics at temperature 1 and tau,
-//                       the maximum of every 32-column chunk (fp16-product precision) and, for the column sums of
-//                       avg_probs, e^c of every logit as fp16 (the one (M,V) scratch of the forward)
+//                       the maximum of every 32-column chunk (fp16-product precision) and ONE (M,V) fp16 matrix:
+//                       e^c of every logit (scp_vq_fwd: workspace scratch for the column sums) or the soft-max
+//                       numerators P'' = exp((c-1)/tau + 10) (scp_vq_fwd_save: the caller's buffer, kept for the backward)
 //   vq_select           per row: chunks whose maximum is within the fp16 error bound of the row maximum are re-scored
 //                       EXACTLY (fp64 accumulation over the fp32 table) -> arg-max is bit-exact w.r.t. an exact cosine,
 //                       first index wins ties; combines the split statistics; gathers keywords = E[idx]; code histogram
-//   vq_colsum           avg_probs[v] = mean_m e^c[m,v] / Z_m from the fp16 scratch (one HBM pass; default).
-//                       SCP_VQ_COLSUM=0 selects the older second tensor-core sweep instead (transposed product
+//   vq_colsum           avg_probs[v] = mean_m e^c[m,v] / Z_m from that matrix (one pass; HBM-bound from e^c, SFU-bound from
+//                       P'').  SCP_VQ_COLSUM=0 selects the older second tensor-core sweep instead (transposed product
 //                       Ehat * khat^T with thread-serial column sums, no scratch)
 //   vq_metrics          code_perplexity, prob_perplexity, diversity_loss, ent_per_t
-// Backward pipeline (D = 128 / 256 / 512; scp_vq_pipe.cuh): ONE producer/consumer launch -- producer CTA pairs compute
-//   c = khat Ehat^T and T = ghat Ehat^T with one N = 256 MMA against a resident [khat | ghat] tile and emit P~, Q~ tiles
-//   into a small ring that stays in L2; consumer CTA pairs accumulate U = Q~ Ehat, W = P~ Ehat in TMEM -- then
-//   vq_bwd_pipe_finalize.  The (M,V) matrices P~, Q~ never reach HBM.
-// Backward pipeline (other D; SCP_VQ_BWD_PIPE=0):
+// Backward, saved numerators (scp_vq_bwd_saved; default of the Python wrapper for a fixed / scheduled temperature):
 //   vq_bwd_prep         g_keywords -> unit rows fp16 + scale + centring constant
+//   sweep T (tcgen05)   ONE accumulator T = ghat Ehat^T (resident ghat); Q'' = P'' (T r_v - s0) from the forward's P'';
+//                       writes fp16 Q'' and the row sums of Q'', P''
+//   gemm_out (tcgen05)  U = Q'' * Ehat, W = P'' * Ehat  (K = V, split-K; P'' read in place from the forward's buffer)
+//   vq_bwd_finalize     g_khat = (U - s W)/(tau sum P''), projection through the normalisation
+// Backward, recompute (scp_vq_bwd; learnable temperature, single-tile problems, D > 512):
 //   sweep 3 (tcgen05)   two accumulators sharing Ehat tiles: S1 = khat Ehat^T, S2 = ghat Ehat^T;
 //                       P = softmax_tau row, Q = P * (T - s0); writes fp16 P~, Q~ and the row sums
-//   gemm_out (tcgen05)  U = Q~ * Ehat, W = P~ * Ehat  (K = V, split-K)
-//   vq_bwd_finalize     g_khat = (U - s W)/tau, projection through the normalisation, optional d/dtau
+//   gemm_out, vq_bwd_finalize as above (+ optional d/dtau)
+// Backward, opt-in low-memory mode (SCP_VQ_BWD_PIPE=1, D = 128 / 256 / 512; scp_vq_pipe.cuh): ONE producer/consumer launch --
+//   producer CTA pairs compute c and T with one N = 256 MMA against a resident [khat | ghat] tile and emit P~, Q~ tiles into
+//   a small ring that stays in L2; consumer CTA pairs accumulate U, W in TMEM.  Slower (487 vs 385 us), 8x less workspace.
 #include <cfloat>
 
 #include "scp_stream_gemm.cuh"

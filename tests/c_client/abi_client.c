@@ -297,6 +297,70 @@ static void check_nce(cudaStream_t st) {
   cudaFree(d_dA); cudaFree(d_dls); cudaFree(d_ws);
 }
 
+/* ------------------------------------------------------------------------------------------------------------ */
+/* S2 with saved soft-max numerators: scp_vq_fwd_save + scp_vq_bwd_saved must reproduce scp_vq_fwd + scp_vq_bwd          */
+static void check_vq_saved(cudaStream_t st) {
+  enum { M = 256, K = 8, V = 700, D = 64 };   /* two 128-row tiles: the saved path is available */
+  static float table[V * D], kw[M * D], g[M * D];
+  for (int i = 0; i < V * D; ++i) table[i] = 0.02f * gauss() + 0.003f;
+  for (int i = 0; i < M * D; ++i) { kw[i] = 0.02f * gauss() + 0.003f; g[i] = gauss(); }
+  for (int d = 0; d < D; ++d) kw[9 * D + d] = 2.0f * table[17 * D + d];   /* a row whose cosine with column 17 is 1 */
+  const int64_t Vp = scp_vq_padded_vocab(V), Mp = (M + 127) / 128 * 128;
+  EXPECT(scp_vq_bwd_saved_available(M, V, D) == 1 && scp_vq_bwd_saved_available(12, V, D) == 0 &&
+             scp_vq_bwd_saved_available(M, V, 768) == 0, "scp_vq_bwd_saved_available");
+  EXPECT(scp_vq_saved_probs_bytes(M, V) == (size_t)Mp * Vp * 2, "scp_vq_saved_probs_bytes");
+  EXPECT(scp_vq_fwd_save_workspace_bytes(M, V, D) + (size_t)Mp * Vp * 2 <= scp_vq_fwd_workspace_bytes(M, V, D) + 4096,
+         "the saved forward needs no (M,V) scratch inside its workspace");
+  float* d_table = (float*)to_dev(table, sizeof table);
+  float* d_kw = (float*)to_dev(kw, sizeof kw);
+  float* d_g = (float*)to_dev(g, sizeof g);
+  void* d_hat = dev_alloc((size_t)Vp * D * 2);
+  void* d_hat_t = dev_alloc((size_t)Vp * D * 2);
+  float* d_norm = (float*)dev_alloc((size_t)Vp * 4);
+  float* d_mean = (float*)dev_alloc((D + 1) * 4);
+  const float tau = 0.1f;
+  float* d_tau = (float*)to_dev(&tau, 4);
+  const int32_t masked[3] = {0, 2, 3};
+  int rc = scp_vq_prepare_table(d_table, V, D, d_hat, d_hat_t, d_norm, d_mean, st);
+  EXPECT(rc == SCP_OK, "scp_vq_prepare_table -> %d", rc);
+  static int64_t idx[2][M];
+  static float avg[2][V], gk[2][M * D];
+  for (int saved = 0; saved < 2; ++saved) {
+    int64_t* d_idx = (int64_t*)dev_alloc(M * 8);
+    float* d_out = (float*)dev_alloc(M * D * 4);
+    float* d_stats = (float*)dev_alloc(M * 4 * 4);
+    float* d_hist = (float*)dev_alloc((size_t)Vp * 4);
+    float* d_avg = (float*)dev_alloc((size_t)Vp * 4);
+    float* d_metrics = (float*)dev_alloc((3 + K) * 4);
+    void* d_kw_hat = dev_alloc((size_t)Mp * D * 2);
+    float* d_gk = (float*)dev_alloc(M * D * 4);
+    void* d_saved = saved ? dev_alloc(scp_vq_saved_probs_bytes(M, V)) : NULL;
+    const size_t fws = saved ? scp_vq_fwd_save_workspace_bytes(M, V, D) : scp_vq_fwd_workspace_bytes(M, V, D);
+    const size_t bws = saved ? scp_vq_bwd_saved_workspace_bytes(M, V, D, 0) : scp_vq_bwd_workspace_bytes(M, V, D);
+    void* d_fws = dev_alloc(fws);
+    void* d_bws = dev_alloc(bws);
+    rc = scp_vq_fwd_save(d_kw, M, K, V, D, d_hat, d_norm, d_table, masked, 3, d_tau, d_idx, d_out, d_stats, d_hist, d_avg,
+                         d_metrics, d_kw_hat, d_saved, d_fws, fws, st);
+    EXPECT(rc == SCP_OK, "scp_vq_fwd_save(saved=%d) -> %d (%s)", saved, rc, scp_last_error_string(rc));
+    rc = scp_vq_bwd_saved(d_g, d_kw, M, V, D, d_kw_hat, d_hat, d_hat_t, d_norm, d_mean, d_stats, masked, 3, d_tau, d_saved,
+                          d_gk, NULL, d_bws, bws, st);
+    EXPECT(rc == SCP_OK, "scp_vq_bwd_saved(saved=%d) -> %d (%s)", saved, rc, scp_last_error_string(rc));
+    CUDA_OK(cudaStreamSynchronize(st));
+    to_host(idx[saved], d_idx, sizeof idx[saved]);
+    to_host(avg[saved], d_avg, sizeof avg[saved]);
+    to_host(gk[saved], d_gk, sizeof gk[saved]);
+    cudaFree(d_idx); cudaFree(d_out); cudaFree(d_stats); cudaFree(d_hist); cudaFree(d_avg); cudaFree(d_metrics);
+    cudaFree(d_kw_hat); cudaFree(d_gk); cudaFree(d_fws); cudaFree(d_bws);
+    if (d_saved) cudaFree(d_saved);
+  }
+  EXPECT(memcmp(idx[0], idx[1], sizeof idx[0]) == 0 && idx[1][9] == 17, "saved forward: same arg-max codes");
+  double num = 0, den = 0;
+  for (int v = 0; v < V; ++v) EXPECT(fabs(avg[0][v] - avg[1][v]) < 1e-3 * (1.0 / V), "avg_probs[%d] %.6g vs %.6g", v, avg[1][v], avg[0][v]);
+  for (int i = 0; i < M * D; ++i) { num += ((double)gk[1][i] - gk[0][i]) * ((double)gk[1][i] - gk[0][i]); den += (double)gk[0][i] * gk[0][i]; }
+  EXPECT(den > 0 && sqrt(num / den) < 1e-3, "keyword gradient: saved vs recompute, relative error %.3e", sqrt(num / fmax(den, 1e-300)));
+  cudaFree(d_table); cudaFree(d_kw); cudaFree(d_g); cudaFree(d_hat); cudaFree(d_hat_t); cudaFree(d_norm); cudaFree(d_mean); cudaFree(d_tau);
+}
+
 int main(void) {
   int n_dev = 0;
   printf("libscp_b200 version %d\n", scp_version());
@@ -311,6 +375,7 @@ int main(void) {
   const int before = scp_num_launches();
   check_wsum(st);
   check_vq(st);
+  check_vq_saved(st);
   check_nce(st);
   CUDA_OK(cudaDeviceSynchronize());
   CUDA_OK(cudaGetLastError());
