@@ -654,8 +654,11 @@ struct Sweep2Epi {
 // e16 (Mp, ldE) fp16 = e^c from sweep 1, lse1_l2[m] = -log2(Z_m) from the statistics phase of vq_select.  Block <-> strip
 // of 64 columns x all M rows: warp w takes the rows m = w (mod 8), lane l the columns 2l, 2l+1 of the strip (one 128-byte
 // row segment per warp load, eight loads in flight per lane); the eight warps are combined through shared memory in a
-// fixed order, so the result is deterministic.  Vp/64 = 772 blocks of 256 threads at the full vocabulary: all resident.
+// fixed order, so the result is deterministic.  Vp/64 = 772 strips at the full vocabulary = 5.2 blocks per SM: the SMs that
+// draw six blocks set the time of this pipe-bound pass, so the rows are split over blockIdx.y as well (kColsumRowSplit row
+// ranges -> 3088 short blocks, dynamically scheduled) and vq_metrics_kernel adds the row-range partials in a fixed order.
 constexpr int kColsumCols = 64;
+constexpr int kColsumRowSplit = 4;   // row ranges of the column-sum pass (M >= 1024), 1 below
 __device__ __forceinline__ float fast_lg2(float x) {
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -667,10 +670,14 @@ __device__ __forceinline__ float fast_lg2(float x) {
 // that.  P'' = 0 (masked / padding columns) gives 2^-inf = 0.
 template <bool PMODE>
 __global__ void __launch_bounds__(256)
-vq_colsum_kernel(const __half* __restrict__ e16, int64_t ldE, const float* __restrict__ lse1_l2, int64_t M, int V,
-                 float inv_m, MaskedCols mc, const float* __restrict__ tau_ptr, float* __restrict__ avg_probs) {
+vq_colsum_kernel(const __half* __restrict__ e16, int64_t ldE, const float* __restrict__ lse1_l2, int64_t M_all, int V,
+                 float inv_m, MaskedCols mc, const float* __restrict__ tau_ptr, float* __restrict__ avg_probs,
+                 int64_t rows_per_block /* blockIdx.y selects a row range; its sums go to avg_probs + blockIdx.y * ldE */) {
   __shared__ float2 s_part[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t m_begin = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t M = m_begin + rows_per_block < M_all ? m_begin + rows_per_block : M_all;  // end of this block's rows
+  avg_probs += (int64_t)blockIdx.y * ldE;
   const int64_t col = (int64_t)blockIdx.x * kColsumCols + 2 * lane;
   const uint32_t* src = reinterpret_cast<const uint32_t*>(e16 + col);
   const int64_t ld32 = ldE >> 1;
@@ -689,7 +696,7 @@ vq_colsum_kernel(const __half* __restrict__ e16, int64_t ldE, const float* __res
       a1 = fmaf(e.y, wj, a1);
     }
   };
-  int64_t m = warp;
+  int64_t m = m_begin + warp;
   for (; m + 56 < M; m += 64) {
     uint32_t h[8];
     float w[8];
@@ -722,26 +729,35 @@ vq_colsum_kernel(const __half* __restrict__ e16, int64_t ldE, const float* __res
 // =====================================================================================================================
 // metrics: code_perplexity, prob_perplexity, diversity_loss, ent_per_t      (one block)
 // =====================================================================================================================
-constexpr int kMetricBlocks = 64;
+constexpr int kMetricBlocks = 128;
 
 // Stage 1 (all blocks): per-block partial sums of h log(h + 1e-7) over the code histogram and the average softmax.
 // Stage 2 (the block that draws the last ticket): fixed-order sum of the partials, perplexities, diversity loss,
 // ent_per_t.  `ticket` must be zero on entry (vq_prep_kw / a memset clears it) and is left at zero.
 __global__ void __launch_bounds__(256)
-vq_metrics_kernel(const float* __restrict__ code_hist, const float* __restrict__ avg_probs,
+vq_metrics_kernel(const float* __restrict__ code_hist, float* __restrict__ avg_probs,
                   const float* __restrict__ row_stats, int64_t M, int K, int V,
                   float* __restrict__ partial /* (kMetricBlocks, 2) | ticket | (kMetricBlocks,) */,
-                  unsigned int* __restrict__ ticket, float* __restrict__ metrics) {
+                  unsigned int* __restrict__ ticket, float* __restrict__ metrics,
+                  const float* __restrict__ avg_part = nullptr /* (n_part, Vp): row-range partials of the column sums */,
+                  int n_part = 0, int Vp = 0) {
   __shared__ float s_red[3][8];
   __shared__ bool s_last;
   const float inv_m = 1.0f / (float)M;
   float* partial_sum = partial + kMetricBlocks * 2 + 1;  // third partial (sum of avg_probs), behind the ticket word
   float hc = 0.f, hp = 0.f, sp = 0.f;
-  for (int v = blockIdx.x * 256 + threadIdx.x; v < V; v += kMetricBlocks * 256) {
+  for (int v = blockIdx.x * 256 + threadIdx.x; v < (avg_part ? Vp : V); v += kMetricBlocks * 256) {
+    float a = 0.f;
+    if (avg_part) {  // avg_probs = sum of the row-range partials, fixed order (also the zero padding of [V, Vp))
+      for (int y = 0; y < n_part; ++y) a += avg_part[(int64_t)y * Vp + v];
+      avg_probs[v] = a;
+    } else if (avg_probs) {
+      a = avg_probs[v];
+    }
+    if (v >= V) continue;
     const float h = code_hist[v] * inv_m;  // my_vector_quantizer.py:94-99
     hc += h * logf(h + 1e-7f);
-    if (avg_probs) {
-      const float a = avg_probs[v];  // :119-121
+    if (avg_probs) {  // :119-121
       hp += a * logf(a + 1e-7f);
       sp += a;
     }
@@ -1295,6 +1311,7 @@ struct VqFwdWs {
   float* partials;
   float* lse1_l2;
   float* metric_part;
+  float* avg_part;
   __half* e16;   // (Mp, Vp) fp16 e^c written by sweep 1 for the column sums (null in the two-sweep mode)
   size_t total;
   int n_chunks, n_groups;
@@ -1341,6 +1358,7 @@ static VqFwdWs vq_fwd_ws(void* base, int64_t M, int64_t V, bool with_scratch = t
   w.partials = static_cast<float*>(take((size_t)Mp * w.n_groups * 4 * 16));  // up to 4 epilogue warps per lane quadrant
   w.lse1_l2 = static_cast<float*>(take((size_t)round_up(M, 256) * 4));
   w.metric_part = static_cast<float*>(take((size_t)(kMetricBlocks * 3 + 1) * 4));  // + the ticket counter
+  w.avg_part = static_cast<float*>(take((size_t)kColsumRowSplit * Vp * 4));        // row-range partials of the column sums
   // (scp_vq_fwd_save: the caller's saved_probs buffer is the scratch)
   w.e16 = with_scratch && vq_colsum_enabled() ? static_cast<__half*>(take((size_t)Mp * Vp * 2)) : nullptr;
   w.total = off;
@@ -1623,13 +1641,15 @@ extern "C" int scp_vq_fwd_save(const float* kw, int64_t M, int64_t K, int64_t V,
 #undef SCP_SELECT
 #undef SCP_SELECT_LAUNCH
   // ---- column sums -- skipped when the caller does not want prob_perplexity
+  const int n_part = M >= 1024 ? kColsumRowSplit : 1;
   if (avg_probs && scratch) {
+    const int64_t rows_per_block = round_up(ceil_div(M, n_part), 64);
+    float* dst = n_part > 1 ? ws.avg_part : avg_probs;
+    const dim3 grid((unsigned)(Vp / kColsumCols), (unsigned)n_part);
     if (saved_probs)
-      vq_colsum_kernel<true><<<(unsigned)(Vp / kColsumCols), 256, 0, s>>>(scratch, Vp, ws.lse1_l2, M, (int)V, 1.0f / (float)M,
-                                                                         mc, tau, avg_probs);
+      vq_colsum_kernel<true><<<grid, 256, 0, s>>>(scratch, Vp, ws.lse1_l2, M, (int)V, 1.0f / (float)M, mc, tau, dst, rows_per_block);
     else
-      vq_colsum_kernel<false><<<(unsigned)(Vp / kColsumCols), 256, 0, s>>>(scratch, Vp, ws.lse1_l2, M, (int)V, 1.0f / (float)M,
-                                                                          mc, tau, avg_probs);
+      vq_colsum_kernel<false><<<grid, 256, 0, s>>>(scratch, Vp, ws.lse1_l2, M, (int)V, 1.0f / (float)M, mc, tau, dst, rows_per_block);
     if (cudaGetLastError() != cudaSuccess) {
       if (forked) join_from_side(s);  // never leave the helper stream un-joined (stream capture would be invalidated)
       return fail(SCP_ERR_CUDA, "vq_colsum launch failed");
@@ -1665,9 +1685,10 @@ extern "C" int scp_vq_fwd_save(const float* kw, int64_t M, int64_t K, int64_t V,
     }
   }
   if (forked && (rc = join_from_side(s))) return rc;  // the metrics need the code histogram of the arg-max phase
+  const bool parts = avg_probs && scratch && n_part > 1;
   vq_metrics_kernel<<<kMetricBlocks, 256, 0, s>>>(code_hist, avg_probs, row_stats, M, (int)K, (int)V, ws.metric_part,
                                                   reinterpret_cast<unsigned int*>(ws.metric_part + kMetricBlocks * 2),
-                                                  metrics);
+                                                  metrics, parts ? ws.avg_part : nullptr, parts ? n_part : 0, (int)Vp);
   SCP_CUDA_LAUNCH_CHECK("vq_metrics");
   return SCP_OK;
 }

@@ -73,3 +73,42 @@ def test_e16_group_filter_never_drops_a_column_at_or_above_the_threshold():
     # and it is a filter, not a pass-through: a column 2 * (MARGIN + slack) below the maximum is rejected
     far = np.exp(thr.astype(np.float64) - MARGIN - 2 * SLACK).astype(np.float32).astype(np.float16).astype(np.float32)
     assert (far < thr_e).all()
+
+
+SLACK_P = _const(r"const float thr_p = expf\(\(thr - 1\.0f\) / \*tau_ptr \+ 10\.0f\) \* \(1\.0f - ([0-9.e+-]+f?)\);")
+SUBNORMAL_GUARD = _const(r"const bool p_all = e16_is_p && thr_p < ([0-9.e+-]+f?);")
+
+
+@torch.no_grad()
+def test_saved_numerator_group_filter_never_drops_a_column_at_or_above_the_threshold():
+    """scp_vq_fwd_save stores P'' = exp((c - 1)/tau + 10) instead of e^c; the arg-max group filter tests
+    fp16(P'') >= float32(exp((thr - 1)/tau + 10)) * (1 - SLACK_P) and admits every group once that threshold falls below
+    SUBNORMAL_GUARD (fp16 subnormals round absolutely, not relatively).  Simulated like the kernel computes it: tau = 0.1
+    through the repeated-squaring chain ((e^c)^10 = ((x^2)^2 x)^2 in float32, every product rounded), any other tau
+    through one ex2.approx; worst-case ex2.approx error (2^-22 relative, both signs) applied to every exponential."""
+    assert 2.0 ** -11 < SLACK_P < 5e-3 and 6.2e-5 < SUBNORMAL_GUARD < 1e-3
+    mx = np.linspace(-1.0, 1.0, 2001, dtype=np.float64)[:, None]
+    thr = (mx.astype(np.float32) - np.float32(MARGIN)).astype(np.float32)
+    offs = np.concatenate([np.linspace(0.0, 1e-5, 101), np.linspace(1e-5, MARGIN, 300)])[None, :]
+    c = (thr.astype(np.float64) + offs).astype(np.float32)                                 # the tensor-core logit, float32
+    f32 = np.float32
+    for tau in (0.1, 0.07, 0.25, 1.0):
+        thr_p = (np.exp((thr.astype(np.float64) - 1.0) / tau + 10.0).astype(f32) * f32(1.0 - SLACK_P)).astype(f32)
+        checked = thr_p >= f32(SUBNORMAL_GUARD)                                            # below: every group is admitted
+        assert checked.any()
+        for approx_err in (-2.0 ** -22, 0.0, 2.0 ** -22):
+            if tau == 0.1:
+                e1 = (np.exp(c.astype(np.float64)) * (1.0 + approx_err)).astype(f32)        # ex2.approx(c * log2 e)
+                x2 = (e1 * e1).astype(f32)
+                x4 = (x2 * x2).astype(f32)
+                x5 = (x4 * e1).astype(f32)
+                p = (x5 * x5).astype(f32)                                                   # ipow2<10>
+            else:
+                p = (np.exp((c.astype(np.float64) - 1.0) / tau + 10.0) * (1.0 + approx_err)).astype(f32)
+            p16 = p.astype(np.float16).astype(f32)                                          # cvt.rn.f16x2.f32
+            ok = (p16 >= thr_p) | ~checked
+            assert ok.all(), (tau, approx_err)
+        # and it filters: two margins below the row maximum is rejected wherever the relative bound applies
+        far = np.exp((thr.astype(np.float64) - MARGIN - 2 * SLACK_P * tau - 1.0) / tau + 10.0).astype(f32)
+        far16 = far.astype(np.float16).astype(f32)
+        assert ((far16 < thr_p) | ~checked).all(), tau
