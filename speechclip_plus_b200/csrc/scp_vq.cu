@@ -997,6 +997,7 @@ struct SweepTEpi {
     const float* table_mean;  // [D] = norm_ref
     float* partials;          // (Mp, 2*n_groups, 4): sum Q'', sum P'', 0, 0
     int n_groups, D;
+    int dbg;                  // timing ablations (env SCP_VQ_ST_DBG, results invalid): 1 = no Q'' stores, 2 = no P'' loads
   };
   static constexpr bool kUnrollTile = true;
   static constexpr int kChunks = kVqBN / 32 / 2;   // chunks per warp and tile (two warps share a lane quadrant)
@@ -1017,6 +1018,7 @@ struct SweepTEpi {
     return p.p16 + row * p.ld + (int64_t)nt * kVqBN + (half * kChunks + k) * 32;
   }
   __device__ __forceinline__ void fetch(int nt, int k) {
+    if (p.dbg & 2) return;
     const __half* src = p_src(nt, k);
     tc::ldg256_stream(src, pbuf[k]);
     tc::ldg256_stream(src + 16, pbuf[k] + 8);
@@ -1071,9 +1073,11 @@ struct SweepTEpi {
         hq[e >> 1] = tc::cvt_f16x2(qj);
       }
     }
-    __half* dst = p.q16 + row * p.ld + col0;
-    tc::stg256(dst, hq);
-    tc::stg256(dst + 16, hq + 8);
+    if (!(p.dbg & 1)) {
+      __half* dst = p.q16 + row * p.ld + col0;
+      tc::stg256(dst, hq);
+      tc::stg256(dst + 16, hq + 8);
+    }
     const int next = cur_nt + nt_stride;
     if (next < nt_end) fetch(next, k);  // this row's chunk k of the next tile: in flight for a whole tile
   }
@@ -1833,6 +1837,8 @@ extern "C" int scp_vq_bwd_saved(const float* g_keywords, const float* kw, int64_
     ep.partials = ws.partials;
     ep.n_groups = sc.n_groups;
     ep.D = (int)D;
+    static const int st_dbg = [] { const char* e = getenv("SCP_VQ_ST_DBG"); return e ? atoi(e) : 0; }();
+    ep.dbg = st_dbg;
     if ((rc = tc::launch_stream_gemm<kVqBN, 1, 5, SweepTEpi, 2, tc::MC_PAIR, 1>(maps, sc, ep, s, "vq_sweep_t"))) return rc;
     p_src = static_cast<const __half*>(saved_probs);
     fin_groups = 2 * sc.n_groups;
