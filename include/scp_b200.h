@@ -195,8 +195,10 @@ int scp_vq_bwd_saved(const float* g_keywords, const float* kw, int64_t M, int64_
 
 /* Dense-input form of SimpleVectorQuantizer.forward (my_vector_quantizer.py:64-165) for callers that already hold the
  * (M,V) score matrix x (fp32, row pitch ldx).  Masks x IN PLACE like the reference (:78-79).  subword_prob (nullable,
- * (M,V) f32 contiguous) receives the forward VALUE of `hard + p - p.detach()` / `hard`, i.e. the one-hot.  Outputs as in
- * scp_vq_fwd (row_stats[.,3] unused; code_hist / avg_probs have V entries). */
+ * (M,V) f32 contiguous) receives the forward VALUE of `hard + p - p.detach()` / `hard`, i.e. the one-hot; with
+ * `training` = 3 (bit 0: training mode, bit 1: the module's hard = False) it receives softmax(x / tau) itself (:130-131).
+ * scp_vq_dense_bwd is the backward of both (the straight-through estimator's gradient IS the soft-max gradient).  Outputs as
+ * in scp_vq_fwd (row_stats[.,3] unused; code_hist / avg_probs have V entries). */
 size_t scp_vq_dense_workspace_bytes(int64_t M, int64_t V);
 int scp_vq_dense_fwd(float* x, int64_t M, int64_t K, int64_t V, int64_t ldx,
                      const int32_t* masked_cols, int n_masked, const float* tau, int training,

@@ -279,12 +279,12 @@ def vq_forward(cos: torch.Tensor, curr_temp: torch.Tensor | float, training: boo
 #      oracle starts from its output, the keyword vectors in CLIP space)
 # ----------------------------------------------------------------------------------------
 def vq_audio_features(keywords_in: torch.Tensor, table: torch.Tensor, curr_temp, training: bool = True,
-                      prob_msk: Sequence[int] = (0, 2, 3), faithful_loop: bool = False
+                      prob_msk: Sequence[int] = (0, 2, 3), faithful_loop: bool = False, hard: bool = True
                       ) -> Tuple[Dict[str, object], torch.Tensor]:
     """cos = cosine(keywords, table) (:192); vq = quantiser(cos) (:193);
     keywords_out = subword_prob @ table (:195).  Returns (vq_results, keywords_out)."""
     cos = cosine_scores_loop(keywords_in, table) if faithful_loop else cosine_scores(keywords_in, table)
-    vq = vq_forward(cos, curr_temp, training=training, prob_msk=prob_msk)
+    vq = vq_forward(cos, curr_temp, training=training, prob_msk=prob_msk, hard=hard)
     kw_out = vq["subword_prob"] @ table
     return vq, kw_out
 

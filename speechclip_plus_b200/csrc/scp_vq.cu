@@ -1238,12 +1238,16 @@ vq_dense_row_kernel(float* __restrict__ x, int64_t M, int V, int64_t ldx, Masked
   z1 = block_sum_256(z1, s_red);
   zt = block_sum_256(zt, s_red);
   const float lse1 = mx + logf(z1);
+  const bool soft = (training & 3) == 3;
   // pass C: entropy exactly as the reference (:111) and the value of subword_prob (:130-139)
   float ent = 0.f;
   for (int v = tid; v < V; v += 256) {
     const float p = expf(row[v] - lse1);
     ent -= p * logf(p + 1e-9f);
-    if (subword_prob) subword_prob[m * (int64_t)V + v] = v == mi ? 1.f : 0.f;
+    // value of subword_prob: the one-hot (hard = True: `hard + p - p.detach()`, and eval), or, training with hard = False
+    // (`training` bit 1), softmax(x / tau) itself (:130-131)
+    if (subword_prob)
+      subword_prob[m * (int64_t)V + v] = soft ? expf((row[v] - mx) / tau) / zt : (v == mi ? 1.f : 0.f);
   }
   ent = block_sum_256(ent, s_red);
   if (tid == 0) {
@@ -1255,7 +1259,6 @@ vq_dense_row_kernel(float* __restrict__ x, int64_t M, int V, int64_t ldx, Masked
     rs[2] = ent;
     rs[3] = 0.f;
   }
-  (void)training;
 }
 
 // thread <-> column: avg_probs[v] = mean_m exp(x[m,v] - lse1[m])   (deterministic column sums)

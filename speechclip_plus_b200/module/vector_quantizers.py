@@ -182,7 +182,7 @@ class _DenseVQFn(torch.autograd.Function):
     """subword_prob, idx, metrics = f(x, tau) for a dense score tensor x (B,K,V); masks x in place."""
 
     @staticmethod
-    def forward(ctx, x: torch.Tensor, tau: torch.Tensor, prob_msk, training: bool):
+    def forward(ctx, x: torch.Tensor, tau: torch.Tensor, prob_msk, training: bool, hard: bool = True):
         lib = _lib.load()
         B, K, V = x.shape
         M = B * K
@@ -200,7 +200,7 @@ class _DenseVQFn(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             st = lib.scp_vq_dense_fwd(_lib.ptr(x2), M, K, V, x2.stride(0), masked, n_masked, _lib.ptr(tau_f),
-                                      int(training), _lib.ptr(idx), _lib.ptr(row_stats), _lib.ptr(code_hist),
+                                      int(training) | (0 if hard else 2), _lib.ptr(idx), _lib.ptr(row_stats), _lib.ptr(code_hist),
                                       _lib.ptr(avg_probs), _lib.ptr(metrics), _lib.ptr(sub), _lib.ptr(ws), ws_bytes,
                                       _lib.stream_ptr(dev))
         _lib.check(st, "scp_vq_dense_fwd")
@@ -214,7 +214,7 @@ class _DenseVQFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_sub, *unused):
         if not ctx.training:
-            return None, None, None, None
+            return None, None, None, None, None
         lib = _lib.load()
         x2, row_stats, tau_f = ctx.saved_tensors
         B, K, V = ctx.shape
@@ -228,7 +228,7 @@ class _DenseVQFn(torch.autograd.Function):
             st = lib.scp_vq_dense_bwd(_lib.ptr(x2), _lib.ptr(g), M, V, x2.stride(0), V, _lib.ptr(row_stats),
                                       _lib.ptr(tau_f), _lib.ptr(g_x), _lib.ptr(g_tau), _lib.stream_ptr(dev))
         _lib.check(st, "scp_vq_dense_bwd")
-        return g_x.view(B, K, V), g_tau, None, None
+        return g_x.view(B, K, V), g_tau, None, None, None
 
 
 class SimpleVectorQuantizer(nn.Module):
@@ -241,8 +241,7 @@ class SimpleVectorQuantizer(nn.Module):
         self.hard = hard
         if use_gumbel:
             raise NotImplementedError("use_gumbel=True is not used by any shipped recipe and has no CUDA path here")
-        if not hard:
-            raise NotImplementedError("hard=False has no CUDA path here (every shipped recipe uses hard=True)")
+
         if isinstance(temp, str):
             if temp.startswith("learnable="):
                 self.temp_type = "learnable"
@@ -311,7 +310,7 @@ class SimpleVectorQuantizer(nn.Module):
         result = {"num_vars": fsz}
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
-        sub, idx, metrics = _DenseVQFn.apply(x, self.curr_temp, tuple(prob_msk), self.training)
+        sub, idx, metrics = _DenseVQFn.apply(x, self.curr_temp, tuple(prob_msk), self.training, self.hard)
         self._finish(result, metrics, tsz)
         result["subword_prob"] = sub
         if produce_targets:
@@ -327,6 +326,9 @@ class SimpleVectorQuantizer(nn.Module):
         ``vq_results["subword_prob"]`` is ``None``: its only consumer in the reference is the lookup matmul
         (kw_branches.py:195), which is fused here."""
         _lib.require_cuda(keywords, "quantize_keywords")
+        if not self.hard:
+            raise NotImplementedError("hard=False: the soft lookup softmax(x / tau) @ E has no fused kernel (no shipped recipe "
+                                      "uses it); call forward() on the dense cosine scores -- fused_vq_audio_features does")
         cache = self._table_cache.get(table)
         B, K, _ = keywords.shape
         # fixed / scheduled temperature >= 0.07 (every shipped recipe: 0.1): the forward keeps the fp16 soft-max numerators
@@ -353,4 +355,11 @@ def fused_vq_audio_features(branch, audio_feat: torch.Tensor) -> Tuple[dict, tor
     audio_feat = branch.project_feats_to_CLIPspace(audio_feat)
     table = branch.clip.model.token_embedding.weight
     assert table.requires_grad == False  # noqa: E712  (kw_branches.py:194)
-    return branch.vector_quantizer.quantize_keywords(audio_feat, table)
+    vq = branch.vector_quantizer
+    if not getattr(vq, "hard", True):
+        # hard=False (no shipped recipe): the reference's own flow -- dense cosine scores (kw_branches.py:158-179), the dense
+        # CUDA quantiser, the lookup matmul (:195)
+        cos_score = branch.get_keyword_cosine_score(audio_feat)
+        vq_results = vq(x=cos_score)
+        return vq_results, vq_results["subword_prob"] @ table
+    return vq.quantize_keywords(audio_feat, table)

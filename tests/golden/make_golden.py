@@ -301,7 +301,7 @@ def golden_cif():
 
 
 # ----------------------------------------------------------------------------------------------
-def _fake_branch(kb, vq_mod, table: torch.Tensor, temp_spec: str, training: bool):
+def _fake_branch(kb, vq_mod, table: torch.Tensor, temp_spec: str, training: bool, hard: bool = True):
     """A GeneralBranch whose projection is the identity, so that vq_audio_features (kw_branches.py:181-197)
     runs V1 + V3 + V4 of the reference on the given keyword vectors."""
     branch = kb.GeneralBranch.__new__(kb.GeneralBranch)
@@ -313,7 +313,7 @@ def _fake_branch(kb, vq_mod, table: torch.Tensor, temp_spec: str, training: bool
     emb.weight.requires_grad_(False)
     branch.clip = types.SimpleNamespace(model=types.SimpleNamespace(token_embedding=emb))
     branch.linear_proj = torch.nn.Identity()
-    branch.vector_quantizer = vq_mod.SimpleVectorQuantizer(temp=temp_spec)
+    branch.vector_quantizer = vq_mod.SimpleVectorQuantizer(temp=temp_spec, hard=hard)
     branch.train(training)
     return branch
 
@@ -328,8 +328,12 @@ def golden_vq():
         ("vq_eval_fixed", 3, 4, 512, 64, "fixed=0.1", False, False),
         ("vq_train_learnable", 2, 8, 1024, 128, "learnable=0.07", True, False),
         ("vq_train_ties", 2, 3, 260, 64, "fixed=0.1", True, True),
+        # hard=False (my_vector_quantizer.py:130-136 without the straight-through term): subword_prob = softmax(x / tau)
+        ("vq_train_soft", 3, 4, 512, 64, "fixed=0.1", True, False, False),
     ]
-    for i, (name, B, K, V, D, temp_spec, training, dup) in enumerate(cases):
+    for i, case in enumerate(cases):
+        name, B, K, V, D, temp_spec, training, dup = case[:8]
+        hard = case[8] if len(case) > 8 else True
         g = _gen(200 + i)
         table = torch.randn(V, D, generator=g) * 0.02 + 0.003 * torch.randn(1, D, generator=g)
         if dup:
@@ -342,10 +346,11 @@ def golden_vq():
             kw[0, 0] = table[200] * 3.0
             kw[1, 2] = table[2] * 2.0  # best raw match is a masked column (2): must not be selected
         kw.requires_grad_(True)
-        branch = _fake_branch(kb, vq_mod, table, temp_spec, training)
+        branch = _fake_branch(kb, vq_mod, table, temp_spec, training, hard)
         cos = branch.get_keyword_cosine_score(kw.detach())
         vq_results, kw_out = branch.vq_audio_features(kw)
         arrays = dict(keywords_in=kw, table=table, training=np.array(training), temp_spec=np.array(temp_spec),
+                      hard=np.array(hard),
                       cos=cos, keywords_out=kw_out, subword_prob=vq_results["subword_prob"],
                       targets=vq_results["targets"], code_perplexity=vq_results["code_perplexity"],
                       prob_perplexity=vq_results["prob_perplexity"], ent_per_t=vq_results["ent_per_t"],

@@ -9,6 +9,7 @@ Tolerances (BASELINE.json north_star): VQ code indices bit-exact except exact ti
 logged metrics within 1e-3 relative error (max |a-b| / max |b|, or ||a-b|| / ||b|| for gradients).
 """
 import math
+import types
 
 import pytest
 import torch
@@ -433,18 +434,41 @@ def test_cif_full_size_vs_oracle(scp, mode):
 # =====================================================================================================================
 # S2 vector quantiser
 # =====================================================================================================================
-def _make_vq(scp, spec, training):
-    vq = scp.SimpleVectorQuantizer(spec).cuda()
+def _make_vq(scp, spec, training, hard=True):
+    vq = scp.SimpleVectorQuantizer(spec, hard=hard).cuda()
     vq.train(training)
     return vq
+
+
+class _BranchStub:
+    """What fused_vq_audio_features needs of a GeneralBranch: identity projection, the frozen table and the reference's
+    dense cosine scores (kw_branches.py:158-179, restated with one broadcast instead of the per-keyword loop)."""
+
+    def __init__(self, vq, table):
+        emb = torch.nn.Embedding.from_pretrained(table.clone(), freeze=True)
+        self.vector_quantizer, self.clip = vq, types.SimpleNamespace(model=types.SimpleNamespace(token_embedding=emb))
+
+    def project_feats_to_CLIPspace(self, feat):
+        return feat
+
+    def get_keyword_cosine_score(self, feat):
+        table = self.clip.model.token_embedding.weight
+        return torch.nn.functional.cosine_similarity(feat[:, :, None, :], table[None, None], dim=-1)
 
 
 @pytest.mark.parametrize("name", golden_names("vq_"))
 def test_vq_fused_golden(scp, name):
     g = load_golden(name)
-    vq = _make_vq(scp, g["temp_spec"], g["training"])
+    hard = bool(g.get("hard", True))
+    vq = _make_vq(scp, g["temp_spec"], g["training"], hard)
     kw = g["keywords_in"].cuda().requires_grad_(True)
-    res, out = vq.quantize_keywords(kw, g["table"].cuda())
+    if hard:
+        res, out = vq.quantize_keywords(kw, g["table"].cuda())
+    else:  # hard=False has no fused kernel: the drop-in body of vq_audio_features routes it through the dense quantiser
+        with pytest.raises(NotImplementedError):
+            vq.quantize_keywords(kw, g["table"].cuda())
+        res, out = scp.fused_vq_audio_features(_BranchStub(vq, g["table"].cuda()), kw)
+        assert rel_err(res["subword_prob"], g["subword_prob"]) < TOL
     # code indices: bit-exact (this includes the fixture with exactly tied duplicate table rows and a masked best match)
     assert torch.equal(res["targets"].cpu(), g["targets"])
     assert res["num_vars"] == int(g["num_vars"])
@@ -472,7 +496,8 @@ def test_vq_fused_golden(scp, name):
 def test_vq_dense_golden(scp, name):
     """The reference signature SimpleVectorQuantizer.forward(x) on the dense cosine scores."""
     g = load_golden(name)
-    vq = _make_vq(scp, g["temp_spec"], g["training"])
+    hard = bool(g.get("hard", True))
+    vq = _make_vq(scp, g["temp_spec"], g["training"], hard)
     x = g["cos"].cuda().clone().requires_grad_(g["training"])
     xin = x.clone() if g["training"] else x  # a leaf that requires grad cannot be modified in place
     res = vq(xin)
@@ -487,7 +512,7 @@ def test_vq_dense_golden(scp, name):
         (gx,) = torch.autograd.grad(kw_out, [x], grad_outputs=g["grad_keywords_out"].cuda())
         # reference gradient w.r.t. the cosine scores via the oracle's autograd
         xr = g["cos"].clone().requires_grad_(True)
-        vr = oracle.vq_forward(xr, torch.tensor([_temp(g["temp_spec"])]), training=True)
+        vr = oracle.vq_forward(xr, torch.tensor([_temp(g["temp_spec"])]), training=True, hard=hard)
         (gr,) = torch.autograd.grad(vr["subword_prob"] @ g["table"], [xr], grad_outputs=g["grad_keywords_out"])
         gr = torch.nan_to_num(gr, nan=0.0)
         assert norm_err(gx, gr) < TOL
