@@ -128,15 +128,17 @@ def test_vector_quantizer_live(refmods, seed):
     branch.text_dim = D
     branch.clip = types.SimpleNamespace(model=types.SimpleNamespace(token_embedding=emb))
     branch.linear_proj = torch.nn.Identity()
-    branch.vector_quantizer = refmods.vq.SimpleVectorQuantizer(temp=f"fixed={tau}")
+    hard = seed % 4 != 1                                             # every fourth case: hard=False (:130-131 without the STE term)
+    branch.vector_quantizer = refmods.vq.SimpleVectorQuantizer(temp=f"fixed={tau}", hard=hard)
     branch.train(training)
     cos = branch.get_keyword_cosine_score(kw.detach())
     res, out = branch.vq_audio_features(kw)
     assert rel_err(oracle.cosine_scores_loop(kw.detach(), table), cos) < 1e-6
     assert rel_err(oracle.cosine_scores(kw.detach(), table), cos) < 1e-5
     kw2 = kw.detach().clone().requires_grad_(True)
-    res2, out2 = oracle.vq_audio_features(kw2, table, torch.tensor([tau]), training=training, faithful_loop=True)
+    res2, out2 = oracle.vq_audio_features(kw2, table, torch.tensor([tau]), training=training, faithful_loop=True, hard=hard)
     assert torch.equal(res2["targets"], res["targets"])
+    assert rel_err(res2["subword_prob"], res["subword_prob"]) < 1e-5
     assert rel_err(out2, out) < 1e-5
     for key in ("code_perplexity", "prob_perplexity", "ent_per_t", "diversity_loss"):
         assert rel_err(res2[key], res[key]) < 2e-5, key
