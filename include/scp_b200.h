@@ -334,6 +334,13 @@ int scp_adam_packed(float* const* params, const int64_t* sizes, int n, const flo
 size_t scp_p2p_buffer_bytes(int world, size_t nbytes_capacity);
 int scp_p2p_allgather(const void* src, size_t nbytes, void* const* peer_bufs_device, void* local_buf, int rank, int world,
                       size_t nbytes_capacity, uint32_t* state, void* out, scp_stream_t stream);
+/* Same exchange, but `out` is SEGMENT-major: the payload is n_seg (<= 4) segments of seg_bytes[i] bytes (HOST array, each a
+ * multiple of 16, adding up to nbytes); out holds for every segment the world copies in rank order, i.e. segment i is the
+ * contiguous block [world * sum(seg_bytes[0..i)), + world * seg_bytes[i]) -- the gathered features and ids come out as
+ * ready-to-use (world * n, D) / (world * n,) arrays. */
+int scp_p2p_allgather_segments(const void* src, size_t nbytes, void* const* peer_bufs_device, void* local_buf, int rank, int world,
+                               size_t nbytes_capacity, uint32_t* state, const int64_t* seg_bytes, int n_seg, void* out,
+                               scp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -96,6 +96,8 @@ SIGNATURES = {
     "scp_p2p_buffer_bytes": (c_size_t, [c_int, c_size_t]),
     "scp_p2p_allgather": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p, c_void_p,
                                   c_void_p]),
+    "scp_p2p_allgather_segments": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p,
+                                           POINTER(c_int64), c_int, c_void_p, c_void_p]),
     "scp_nce_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "scp_nce_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_float, c_float, c_int, c_int,
                             c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

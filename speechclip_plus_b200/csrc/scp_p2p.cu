@@ -88,6 +88,35 @@ p2p_collect_kernel(const uint8_t* __restrict__ local_buf, size_t nbytes, int wor
   }
 }
 
+// Segment-major collect: the payload of every rank is a sequence of n_seg segments (e.g. [feature 0 | feature 1 | ids]);
+// out holds, segment after segment, the world copies of that segment in rank order -- every segment is then ONE contiguous
+// (world * n, ...) tensor for the caller, no strided copies afterwards.
+struct P2pSegs {
+  int n;
+  unsigned long long off[4];   // byte offset of segment i inside a rank's payload (off[n] = nbytes)
+  unsigned long long end[4];
+};
+__global__ void __launch_bounds__(256)
+p2p_collect_seg_kernel(const uint8_t* __restrict__ local_buf, size_t nbytes, int world, size_t slot_stride,
+                       const uint32_t* __restrict__ state, uint8_t* __restrict__ out, P2pSegs segs) {
+  const uint32_t epoch = state[0];
+  const uint8_t* base = local_buf + (size_t)(epoch & 1u) * world * slot_stride;
+  const size_t n16 = nbytes >> 4;
+  for (int r = blockIdx.y; r < world; r += gridDim.y) {
+    const uint4* s16 = reinterpret_cast<const uint4*>(base + (size_t)r * slot_stride);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+      const unsigned long long b = (unsigned long long)i << 4;
+      int sg = 0;
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (k < segs.n && b >= segs.off[k]) sg = k;
+      const unsigned long long size = segs.end[sg] - segs.off[sg];
+      // segment sg starts at world * off[sg] in `out`; rank r's copy follows r * size further on
+      *reinterpret_cast<uint4*>(out + (size_t)world * segs.off[sg] + (size_t)r * size + (b - segs.off[sg])) = s16[i];
+    }
+  }
+}
+
 }  // namespace scp
 
 using namespace scp;
@@ -117,5 +146,41 @@ extern "C" int scp_p2p_allgather(const void* src, size_t nbytes, void* const* pe
   p2p_collect_kernel<<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(local_buf), nbytes, world, slot, state,
                                           static_cast<uint8_t*>(out));
   SCP_CUDA_LAUNCH_CHECK("p2p_collect");
+  return SCP_OK;
+}
+
+extern "C" int scp_p2p_allgather_segments(const void* src, size_t nbytes, void* const* peer_bufs_device, void* local_buf,
+                                          int rank, int world, size_t nbytes_capacity, uint32_t* state,
+                                          const int64_t* seg_bytes, int n_seg, void* out, scp_stream_t stream) {
+  SCP_CHECK_ARG(src && peer_bufs_device && local_buf && state && out && seg_bytes, "p2p_allgather_segments: null pointer");
+  SCP_CHECK_ARG(world >= 1 && world <= 64 && rank >= 0 && rank < world, "p2p_allgather_segments: bad rank / world");
+  SCP_CHECK_ARG(n_seg >= 1 && n_seg <= 4, "p2p_allgather_segments: 1..4 segments, got %d", n_seg);
+  SCP_CHECK_ARG(nbytes > 0 && nbytes % 16 == 0 && nbytes <= nbytes_capacity,
+                "p2p_allgather_segments: payload %zu B (multiple of 16, <= %zu)", nbytes, nbytes_capacity);
+  SCP_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "p2p_allgather_segments: src / out must be 16-byte aligned");
+  P2pSegs segs{};
+  segs.n = n_seg;
+  unsigned long long off = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    SCP_CHECK_ARG(seg_bytes[i] > 0 && seg_bytes[i] % 16 == 0, "p2p_allgather_segments: segment %d has %lld B (multiple of 16)", i,
+                  (long long)seg_bytes[i]);
+    segs.off[i] = off;
+    off += (unsigned long long)seg_bytes[i];
+    segs.end[i] = off;
+  }
+  SCP_CHECK_ARG(off == nbytes, "p2p_allgather_segments: segments add up to %llu B, payload is %zu B", off, nbytes);
+  const size_t slot = (nbytes_capacity + 255) & ~size_t(255);
+  const size_t flag_offset = 2 * (size_t)world * slot + 256;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>(32, (nbytes / 16 + 255) / 256));
+  p2p_allgather_kernel<<<blocks, 256, 0, s>>>(static_cast<const uint8_t*>(src), nbytes,
+                                              reinterpret_cast<uint8_t* const*>(peer_bufs_device), rank, world, slot,
+                                              flag_offset, state);
+  SCP_CUDA_LAUNCH_CHECK("p2p_allgather");
+  dim3 grid((unsigned)std::max<size_t>(1, std::min<size_t>(16, (nbytes / 16 + 255) / 256)), (unsigned)std::min(world, 8));
+  p2p_collect_seg_kernel<<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(local_buf), nbytes, world, slot, state,
+                                              static_cast<uint8_t*>(out), segs);
+  SCP_CUDA_LAUNCH_CHECK("p2p_collect_seg");
   return SCP_OK;
 }

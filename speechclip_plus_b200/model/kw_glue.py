@@ -59,6 +59,29 @@ def all_gather_packed(packed: torch.Tensor, group=None) -> torch.Tensor:
     return out.reshape(world, -1)
 
 
+def gather_packed_segments(packed: torch.Tensor, n_feats: int, n: int, D: int, group=None):
+    """The peer-memory exchange with a segment-major result (every feature block and the ids come out as one contiguous
+    gathered array): ``(flat uint8 (world * nbytes,), world)``, or ``None`` when that path is unavailable (host tensors,
+    no peer access, segment sizes that are not multiples of 16) and :func:`all_gather_packed` has to do it."""
+    world = group_world_size(group)
+    seg = [n * D * 4] * n_feats + [n * 8]
+    if world == 1 or not packed.is_cuda or any(b % 16 for b in seg):
+        return None
+    from . import peer_gather
+    ctx = peer_gather.get(packed.numel() * packed.element_size(), packed.device, group, tag="feats")
+    if ctx is None:
+        return None
+    return ctx.all_gather_segments(packed, seg), world
+
+
+def unpack_segments(flat: torch.Tensor, world: int, n_feats: int, n: int, D: int) -> Tuple[List[torch.Tensor], torch.Tensor]:
+    """Views into the segment-major result of :func:`gather_packed_segments` (no copies)."""
+    fbytes = world * n * D * 4
+    feats = [flat[f * fbytes:(f + 1) * fbytes].view(torch.float32).reshape(world * n, D) for f in range(n_feats)]
+    ids = flat[n_feats * fbytes:n_feats * fbytes + world * n * 8].view(torch.int64)
+    return feats, ids
+
+
 def unpack_gathered(gathered: torch.Tensor, n_feats: int, n: int, D: int) -> Tuple[List[torch.Tensor], torch.Tensor]:
     """(world, nbytes) uint8 -> ([ (world*n, D) float32 ] * n_feats, (world*n,) int64), rank-major row order."""
     world = gathered.shape[0]
@@ -110,9 +133,15 @@ class _NormPackGatherFn(torch.autograd.Function):
             st = lib.scp_l2norm_pack(_lib.ptr_array(srcs), len(srcs), n, D, _lib.dtype_code(common),
                                      _lib.ptr(ids64), _lib.ptr(packed), _lib.ptr(inv), _lib.stream_ptr(dev))
         _lib.check(st, "scp_l2norm_pack")
-        gathered = all_gather_packed(packed, group)
-        g_feats, g_ids = unpack_gathered(gathered, len(srcs), n, D)
-        rank = dist.get_rank(group) if gathered.shape[0] > 1 else 0
+        seg = gather_packed_segments(packed, len(srcs), n, D, group)
+        if seg is not None:  # one push + one segment-major collect: the gathered arrays are views, nothing to copy
+            g_feats, g_ids = unpack_segments(seg[0], seg[1], len(srcs), n, D)
+            world = seg[1]
+        else:
+            gathered = all_gather_packed(packed, group)
+            g_feats, g_ids = unpack_gathered(gathered, len(srcs), n, D)
+            world = gathered.shape[0]
+        rank = dist.get_rank(group) if world > 1 else 0
         ctx.rows = shard_rows(n, rank)
         ctx.n_feats = len(srcs)
         ctx.in_dtypes = [f.dtype for f in feats]
@@ -155,7 +184,12 @@ def gather_loss_feats(loss_feats: Dict[str, torch.Tensor], group=None) -> Tuple[
     g_ids, g_feats = outs[0], outs[1:]
     out = dict(loss_feats)
     out["id"] = g_ids
+    n_rows = feats[0].shape[0]
+    rows = shard_rows(n_rows, dist.get_rank(group) if g_ids.shape[0] > n_rows else 0)
     for k, g in zip(keys, g_feats):
+        # the backward of this gather reads ONLY this rank's rows of the gradient: consumers that know their local rows
+        # (MaskedContrastiveLoss with local_rows) may leave the other rows of the gradient unwritten
+        g._scp_local_rows = rows
         out[k] = g
     n = feats[0].shape[0]
     world = g_ids.shape[0] // n

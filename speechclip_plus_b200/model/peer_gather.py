@@ -71,6 +71,24 @@ class PeerGather:
         return out
 
 
+    def all_gather_segments(self, src: torch.Tensor, seg_bytes) -> torch.Tensor:
+        """Like :meth:`all_gather`, but the result is SEGMENT-major: for every segment of the payload (``seg_bytes``:
+        sizes in bytes, multiples of 16, adding up to the payload) the world copies follow each other in rank order, so
+        each segment of the flat ``(world * nbytes,)`` result is one contiguous gathered array (no copies to unpack)."""
+        import ctypes
+        lib = _lib.load()
+        flat = src.reshape(-1).view(torch.uint8)
+        nbytes = flat.numel()
+        segs = (ctypes.c_int64 * len(seg_bytes))(*[int(b) for b in seg_bytes])
+        out = torch.empty(self.world * nbytes, dtype=torch.uint8, device=flat.device)
+        with torch.cuda.device(flat.device):
+            st = lib.scp_p2p_allgather_segments(_lib.ptr(flat), nbytes, _lib.ptr(self.peer_ptrs), _lib.ptr(self.buf),
+                                                self.rank, self.world, self.capacity, _lib.ptr(self.state), segs,
+                                                len(seg_bytes), _lib.ptr(out), _lib.stream_ptr(flat.device))
+        _lib.check(st, "scp_p2p_allgather_segments")
+        return out
+
+
 def get(capacity_bytes: int, device: torch.device, group=None, tag: str = "") -> Optional[PeerGather]:
     """Cached context (created collectively on first use: every rank must reach this call).  None: use NCCL."""
     if not enabled() or not (dist.is_available() and dist.is_initialized()):

@@ -75,6 +75,9 @@ class _MaskedNceFn(torch.autograd.Function):
         ctx.save_for_backward(a, b, ids, ls, lse_row, lse_col, ws if need_bwd else None)
         ctx.cfg = (float(fixed_scale), float(margin), int(dcl), int(a2b), int(b2a), int(row_begin), int(row_end))
         ctx.in_dtypes = (feat_a.dtype, feat_b.dtype)
+        # inputs gathered by gather_loss_feats: only rows [row_begin, row_end) of their gradient are ever read
+        rows = (int(row_begin), int(row_end))
+        ctx.rows_only = tuple(getattr(t, "_scp_local_rows", None) == rows for t in (feat_a, feat_b))
         return loss.reshape(())
 
     @staticmethod
@@ -88,8 +91,17 @@ class _MaskedNceFn(torch.autograd.Function):
         g = g_loss.detach().reshape(1).float().contiguous()
         need_b = ctx.needs_input_grad[1]
         need_t = ls is not None and ctx.needs_input_grad[2]
-        dA = torch.empty((n_local, D), dtype=torch.float32, device=dev)
-        dB = torch.empty((n_local, D), dtype=torch.float32, device=dev) if need_b else None
+        # The kernel writes this rank's rows straight into the full-size gradient (rows of other ranks: zero, or left
+        # unwritten when the producer of the input is known to read the local rows only) -- no zero-fill + copy afterwards.
+        def grad_buffer(rows_only: bool, dtype) -> Tuple[torch.Tensor, torch.Tensor]:
+            if n_local == N or dtype != torch.float32:
+                local = torch.empty((n_local, D), dtype=torch.float32, device=dev)
+                return local, None
+            whole = (torch.empty if rows_only else torch.zeros)((N, D), dtype=torch.float32, device=dev)
+            return whole[row_begin:row_end], whole
+
+        dA, dA_full = grad_buffer(ctx.rows_only[0], ctx.in_dtypes[0])
+        dB, dB_full = grad_buffer(ctx.rows_only[1], ctx.in_dtypes[1]) if need_b else (None, None)
         dT = torch.empty(1, dtype=torch.float32, device=dev) if need_t else None
         ws_bytes = lib.scp_nce_workspace_bytes(N, D)
         state_valid = ws is not None
@@ -102,17 +114,19 @@ class _MaskedNceFn(torch.autograd.Function):
                                  ws_bytes, _lib.stream_ptr(dev))
         _lib.check(st, "scp_nce_bwd")
 
-        def full(local: Optional[torch.Tensor], dtype) -> Optional[torch.Tensor]:
+        def full(local: Optional[torch.Tensor], whole: Optional[torch.Tensor], dtype) -> Optional[torch.Tensor]:
             if local is None:
                 return None
+            if whole is not None:
+                return whole
             if n_local == N:
                 return local.to(dtype)
             out = torch.zeros((N, D), dtype=dtype, device=dev)  # rows owned by other ranks get no gradient here
             out[row_begin:row_end] = local
             return out
 
-        gA = full(dA, ctx.in_dtypes[0]) if ctx.needs_input_grad[0] else None
-        gB = full(dB, ctx.in_dtypes[1])
+        gA = full(dA, dA_full, ctx.in_dtypes[0]) if ctx.needs_input_grad[0] else None
+        gB = full(dB, dB_full, ctx.in_dtypes[1])
         gT = dT.reshape(()) if dT is not None else None
         return gA, gB, gT, None, None, None, None, None, None, None, None, None, None
 
