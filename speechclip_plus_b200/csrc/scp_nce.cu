@@ -201,21 +201,25 @@ nce_loss_kernel(const float* __restrict__ partials, int Np, int n_groups, const 
 // ---- sharded forward (one process per GPU): each rank evaluates the denominators of ITS rows / columns only ----------
 // stats (3, n_local): [0] = log sum_j mask e^{S_ij} (row i local), [1] = log sum_i mask e^{S_ij} (column j local),
 // [2] = <A_i, B_i>.  The ranks all-gather this vector (12 bytes per sample) instead of recomputing the N x N problem.
-__global__ void nce_local_stats_kernel(const float* __restrict__ partials, int Lp, int n_groups,
-                                       const float* __restrict__ pos, int row_begin, int n_local,
-                                       float* __restrict__ stats) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= n_local) return;
-#pragma unroll
-  for (int dir = 0; dir < 2; ++dir) {
-    const float2* pp = reinterpret_cast<const float2*>(partials + ((int64_t)(dir * Lp + l) * n_groups) * 2);
-    float mx = kNegBigN;
-    for (int g = 0; g < n_groups; ++g) mx = fmaxf(mx, pp[g].x);
-    float sm = 0.f;
-    for (int g = 0; g < n_groups; ++g) sm += pp[g].y * expf(pp[g].x - mx);
+// warp <-> (direction, local row): the lanes stride over the row's partial slots (a thread per row walked up to ~150 dependent
+// loads serially: 11 us at N = 2048 for 256 local rows)
+__global__ void __launch_bounds__(256)
+nce_local_stats_kernel(const float* __restrict__ partials, int Lp, int n_groups, const float* __restrict__ pos,
+                       int row_begin, int n_local, float* __restrict__ stats) {
+  const int w = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (w >= 2 * n_local) return;  // whole warp
+  const int dir = w / n_local, l = w - dir * n_local;
+  const float2* pp = reinterpret_cast<const float2*>(partials + ((int64_t)(dir * Lp + l) * n_groups) * 2);
+  float mx = kNegBigN;
+  for (int g = lane; g < n_groups; g += 32) mx = fmaxf(mx, pp[g].x);
+  mx = warp_max(mx);
+  float sm = 0.f;
+  for (int g = lane; g < n_groups; g += 32) sm += pp[g].y * expf(pp[g].x - mx);
+  sm = warp_sum(sm);
+  if (lane == 0) {
     stats[dir * n_local + l] = mx + logf(sm);
+    if (dir == 0) stats[2 * n_local + l] = pos[row_begin + l];
   }
-  stats[2 * n_local + l] = pos[row_begin + l];
 }
 
 // one block: the loss (losses.py:234-243) from the gathered (world, 3, n) statistics; also writes the contiguous
@@ -564,8 +568,8 @@ extern "C" int scp_nce_fwd_local(const float* A, const float* Bm, const int64_t*
   float* partials = ws.out;
   NceFwdEpi::Params ep{c, partials, (int)Np, sweep_groups, (int)Lp, (int)row_begin, (int)n_local};
   if ((rc = tc::launch_stream_gemm<kNceBN, 1, 6, NceFwdEpi>(maps, sc, ep, s, "nce_fwd_local_sweep"))) return rc;
-  nce_local_stats_kernel<<<(unsigned)ceil_div(n_local, 128), 128, 0, s>>>(partials, (int)Lp, 2 * sweep_groups, ws.pos,
-                                                                         (int)row_begin, (int)n_local, stats_local);
+  nce_local_stats_kernel<<<(unsigned)ceil_div(2 * n_local, 8), 256, 0, s>>>(partials, (int)Lp, 2 * sweep_groups, ws.pos,
+                                                                           (int)row_begin, (int)n_local, stats_local);
   SCP_CUDA_LAUNCH_CHECK("nce_local_stats");
   return SCP_OK;
 }
