@@ -143,6 +143,17 @@ def test_pack_layout_roundtrip_on_host():
     assert torch.equal(out_ids, ids)
     assert kw_glue.shard_rows(5, 3) == (15, 20)
     assert kw_glue.ddp_grad_scale(8) == 8.0
+    # segment-major result of the peer all-gather (scp_p2p_allgather_segments): for every segment of the payload the world
+    # copies follow each other in rank order -- restated here on the host -- and unpack_segments returns plain VIEWS
+    fbytes = n * D * 4
+    segs = [gathered[:, f * fbytes:(f + 1) * fbytes].reshape(-1) for f in range(n_feats)]
+    segs.append(gathered[:, n_feats * fbytes:].reshape(-1))
+    flat = torch.cat(segs)
+    seg_feats, seg_ids = kw_glue.unpack_segments(flat, world, n_feats, n, D)
+    for a, b in zip(seg_feats, feats):
+        assert torch.equal(a, b) and a.data_ptr() >= flat.data_ptr() and a.is_contiguous()
+    assert torch.equal(seg_ids, ids)
+    assert kw_glue.gather_packed_segments(gathered[0], n_feats, n, D, kw_glue.LOCAL) is None   # world 1 / host tensors
 
 
 def test_compute_loss_key_contract():
