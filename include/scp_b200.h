@@ -154,8 +154,10 @@ int scp_vq_fwd(const float* kw, int64_t M, int64_t K, int64_t V, int64_t D,
  * i.e. softmax_tau(cos[m,:]) up to the row's normaliser (kw_branches.py:158-179 + my_vector_quantizer.py:130-136); avg_probs
  * and the exact arg-max are derived from the same buffer (e^cos = P''^tau e^{1 - 10 tau}).  Outputs are identical to
  * scp_vq_fwd within the stated tolerances.  The buffer must stay untouched until scp_vq_bwd_saved has consumed it.  Meant for
- * tau >= 0.07: below that the numerators far from the row maximum fall into fp16 subnormals (the Python wrapper selects the
- * recompute path then). */
+ * tau >= 0.1 (every shipped recipe): the cosines span 2/tau nats of exponent and fp16 offers ~20 with the factor 2 of head
+ * room Q'' needs; below 0.1 the numerators of strongly negative cosines (cos < 1 - 26.6 tau) underflow, which the gradient
+ * tolerates (they carry no probability mass at temperature tau) but avg_probs, derived from them at temperature 1, does not
+ * (the Python wrapper selects scp_vq_fwd / scp_vq_bwd then). */
 size_t scp_vq_saved_probs_bytes(int64_t M, int64_t V);
 size_t scp_vq_fwd_save_workspace_bytes(int64_t M, int64_t V, int64_t D);   /* saved_probs != NULL: no (M,V) scratch inside */
 int scp_vq_fwd_save(const float* kw, int64_t M, int64_t K, int64_t V, int64_t D,

@@ -331,11 +331,13 @@ class SimpleVectorQuantizer(nn.Module):
                                       "uses it); call forward() on the dense cosine scores -- fused_vq_audio_features does")
         cache = self._table_cache.get(table)
         B, K, _ = keywords.shape
-        # fixed / scheduled temperature >= 0.07 (every shipped recipe: 0.1): the forward keeps the fp16 soft-max numerators
-        # and the backward skips the k . E^T product and the exponentials (scp_vq_fwd_save / scp_vq_bwd_saved); a learnable
-        # temperature needs the logits for d/dtau and a smaller one the full dynamic range: recompute path
+        # fixed / scheduled temperature >= 0.1 (every shipped recipe: 0.1): the forward keeps the fp16 soft-max numerators
+        # and the backward skips the k . E^T product and the exponentials (scp_vq_fwd_save / scp_vq_bwd_saved).  A learnable
+        # temperature needs the logits for d/dtau; below 0.1 the numerators exp((c - 1)/tau + 10) of strongly negative
+        # cosines (c < 1 - 26.6 tau) underflow fp16 and avg_probs, which is derived from them, would lose those columns
+        # (tests/test_vq_saved_math.py): recompute path.
         save_probs = (self.training and self.temp_type != "learnable" and torch.is_grad_enabled()
-                      and keywords.requires_grad and self._temp_as_float() >= 0.07)
+                      and keywords.requires_grad and self._temp_as_float() >= 0.1 - 1e-6)
         out, idx, metrics, row_stats, code_hist, avg_probs = _FusedVQFn.apply(
             keywords, self.curr_temp, cache, tuple(prob_msk), self.training, compute_prob_perplexity, save_probs)
         result = {"num_vars": cache.V}

@@ -710,6 +710,7 @@ def test_vq_saved_numerators_vs_recompute(scp, cfg):
     kw = (torch.randn(B, K, D, generator=gen).cuda() * table.std(0) + table.mean(0))
     pick = torch.randint(0, V, (B,), generator=gen).cuda()
     kw[:, 0] = table[pick] * 1.5 + 0.002 * torch.randn(B, D, generator=gen).cuda()   # rows with a cosine close to 1
+    kw[:, 1] = -table[pick.flip(0)] * 0.7     # ... and close to -1: numerators at the bottom of the fp16 range (e^-10 at tau = 0.1)
     gout = torch.randn(B, K, D, generator=gen).cuda()
     vq = _make_vq(scp, f"fixed={tau}", True)
     cache = vq._table_cache.get(table)
