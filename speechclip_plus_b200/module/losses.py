@@ -97,7 +97,9 @@ class _MaskedNceFn(torch.autograd.Function):
             if n_local == N or dtype != torch.float32:
                 local = torch.empty((n_local, D), dtype=torch.float32, device=dev)
                 return local, None
-            whole = (torch.empty if rows_only else torch.zeros)((N, D), dtype=torch.float32, device=dev)
+            # (anomaly detection inspects whole gradient tensors: give it zeros, not uninitialised memory)
+            skip_fill = rows_only and not torch.is_anomaly_enabled()
+            whole = (torch.empty if skip_fill else torch.zeros)((N, D), dtype=torch.float32, device=dev)
             return whole[row_begin:row_end], whole
 
         dA, dA_full = grad_buffer(ctx.rows_only[0], ctx.in_dtypes[0])
