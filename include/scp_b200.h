@@ -183,8 +183,8 @@ int scp_vq_bwd(const float* g_keywords, const float* kw, int64_t M, int64_t V, i
 /* Same gradient from the numerators saved by scp_vq_fwd_save (saved_probs nullable -> scp_vq_bwd): only g . E^T is formed
  * on the tensor cores (no k . E^T product, no exponentials: 6 instead of 8 M V D executed FLOP over forward + backward ... 4
  * instead of 8 in this call) and the output GEMM reads P'' in place.  Falls back to the recompute path when g_tau is
- * requested (a learnable temperature needs the logits), for single-tile problems and for D > 512. */
-/* 1 when scp_vq_bwd_saved would use the saved numerators for this shape (at least two 128-row tiles, D <= 512): callers
+ * requested (a learnable temperature needs the logits) and for single-tile problems. */
+/* 1 when scp_vq_bwd_saved would use the saved numerators for this shape (at least two 128-row tiles): callers
  * that cannot profit should call scp_vq_fwd (its avg_probs pass is cheaper than the one of scp_vq_fwd_save). */
 int scp_vq_bwd_saved_available(int64_t M, int64_t V, int64_t D);
 size_t scp_vq_bwd_saved_workspace_bytes(int64_t M, int64_t V, int64_t D, int want_tau);   /* want_tau: g_tau != NULL */

@@ -21,7 +21,7 @@
 //                       writes fp16 Q'' and the row sums of Q'', P''
 //   gemm_out (tcgen05)  U = Q'' * Ehat, W = P'' * Ehat  (K = V, split-K; P'' read in place from the forward's buffer)
 //   vq_bwd_finalize     g_khat = (U - s W)/(tau sum P''), projection through the normalisation
-// Backward, recompute (scp_vq_bwd; learnable temperature, single-tile problems, D > 512):
+// Backward, recompute (scp_vq_bwd; learnable temperature, tau < 0.1, single-tile problems):
 //   sweep 3 (tcgen05)   two accumulators sharing Ehat tiles: S1 = khat Ehat^T, S2 = ghat Ehat^T;
 //                       P = softmax_tau row, Q = P * (T - s0); writes fp16 P~, Q~ and the row sums
 //   gemm_out, vq_bwd_finalize as above (+ optional d/dtau)
@@ -1408,7 +1408,11 @@ static int vq_pipe_ring() {
 // the saved-numerator path of scp_vq_bwd_saved is taken iff ... (one predicate for the launch and the workspace size)
 static bool vq_saved_path_ok(int64_t M, int64_t D, bool want_tau) {
   const int64_t Mp = round_up(M, tc::kTileM);
-  return !want_tau && !vq_bwd_pipe_mode(D) && vq_use_pair((int)(Mp / tc::kTileM)) && vq_saved_enabled() &&
+  return !want_tau && !vq_bwd_pipe_mode(D) && vq_use_pair((int)(Mp / tc::kTileM)) && vq_saved_enabled();
+}
+// sweep T keeps the ghat tile resident when it fits next to a 5-stage ring (D <= 512) and streams it otherwise
+static bool vq_sweep_t_resident(int64_t D) {
+  return vq_resident_enabled() &&
          tc::resident_smem_bytes<kVqBN, 1, 5, SweepTEpi, tc::MC_PAIR>((int)(D / tc::kChunkK)) <= tc::kMaxDynSmem;
 }
 static VqBwdWs vq_bwd_ws(void* base, int64_t M, int64_t V, int64_t D, bool saved = false) {
@@ -1842,7 +1846,9 @@ extern "C" int scp_vq_bwd_saved(const float* g_keywords, const float* kw, int64_
     ep.D = (int)D;
     static const int st_dbg = [] { const char* e = getenv("SCP_VQ_ST_DBG"); return e ? atoi(e) : 0; }();
     ep.dbg = st_dbg;
-    if ((rc = tc::launch_stream_gemm<kVqBN, 1, 5, SweepTEpi, 2, tc::MC_PAIR, 1>(maps, sc, ep, s, "vq_sweep_t"))) return rc;
+    rc = vq_sweep_t_resident(D) ? tc::launch_stream_gemm<kVqBN, 1, 5, SweepTEpi, 2, tc::MC_PAIR, 1>(maps, sc, ep, s, "vq_sweep_t")
+                                : tc::launch_stream_gemm<kVqBN, 1, 5, SweepTEpi, 2, tc::MC_PAIR>(maps, sc, ep, s, "vq_sweep_t");
+    if (rc) return rc;
     p_src = static_cast<const __half*>(saved_probs);
     fin_groups = 2 * sc.n_groups;
   }

@@ -307,7 +307,7 @@ static void check_vq_saved(cudaStream_t st) {
   for (int d = 0; d < D; ++d) kw[9 * D + d] = 2.0f * table[17 * D + d];   /* a row whose cosine with column 17 is 1 */
   const int64_t Vp = scp_vq_padded_vocab(V), Mp = (M + 127) / 128 * 128;
   EXPECT(scp_vq_bwd_saved_available(M, V, D) == 1 && scp_vq_bwd_saved_available(12, V, D) == 0 &&
-             scp_vq_bwd_saved_available(M, V, 768) == 0, "scp_vq_bwd_saved_available");
+             scp_vq_bwd_saved_available(M, V, 768) == 1, "scp_vq_bwd_saved_available");
   EXPECT(scp_vq_saved_probs_bytes(M, V) == (size_t)Mp * Vp * 2, "scp_vq_saved_probs_bytes");
   EXPECT(scp_vq_fwd_save_workspace_bytes(M, V, D) + (size_t)Mp * Vp * 2 <= scp_vq_fwd_workspace_bytes(M, V, D) + 4096,
          "the saved forward needs no (M,V) scratch inside its workspace");

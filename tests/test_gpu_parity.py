@@ -695,14 +695,14 @@ def test_vq_full_size_vs_fp64_oracle(scp, cfg):
 
 
 @pytest.mark.parametrize("cfg", [(32, 8, 8112, 512, 0.1), (24, 12, 19787, 256, 0.5), (256, 8, 49408, 512, 0.1), (20, 8, 8112, 768, 0.1)],
-                         ids=["flickr_vocab", "generic_tau_D256", "bench_shape", "D768_falls_back"])
+                         ids=["flickr_vocab", "generic_tau_D256", "bench_shape", "D768_streamed_ghat"])
 def test_vq_saved_numerators_vs_recompute(scp, cfg):
     """The two forms of the straight-through backward (kw_branches.py:181-197 + my_vector_quantizer.py:130-136) must agree:
     `save_probs=True` (scp_vq_fwd_save / scp_vq_bwd_saved: the forward keeps P'' = exp((c-1)/tau + 10) as fp16, the column
     sums and the arg-max filter read it, the backward forms only g . E^T) against `save_probs=False` (the backward recomputes
     k . E^T and the soft-max).  Same indices, metrics within 1e-4 of each other, keyword gradients within 5e-4 of each other
-    and within the 1e-3 tolerance of the fp64 oracle.  D = 768 has no resident tile: the saved forward must still be
-    correct and the backward silently takes the recompute path."""
+    and within the 1e-3 tolerance of the fp64 oracle.  D = 768 has no resident tile: sweep 1 and sweep T stream the
+    keyword / gradient tile through the ring instead."""
     from speechclip_plus_b200.module.vector_quantizers import _FusedVQFn
     B, K, V, D, tau = cfg
     gen = torch.Generator().manual_seed(B * 7 + V)
