@@ -26,6 +26,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "-diag-suppress", "177",
 ]
+if os.environ.get("SCP_BUILD_ABLATION") == "1":  # timing-ablation switches (results invalid), see csrc/scp_common.cuh
+    NVCC_FLAGS += ["-DSCP_ABLATION"]
 
 
 def _nvcc() -> str:

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/scp_b200.h"
 
@@ -36,6 +37,20 @@ int join_from_side(cudaStream_t main);
   } while (0)
 
 constexpr int kNumSMs = 148;  // B200
+
+// Timing-ablation switches (SCP_DEBUG_ABLATE, SCP_VQ_S1_DBG, SCP_VQ_ST_DBG, SCP_PIPE_DEBUG) skip parts of a kernel and make
+// its results INVALID; they are how the "MMAs alone / epilogue alone" figures in DESIGN.md were taken.  A regular build
+// ignores them: only a library built with -DSCP_ABLATION (SCP_BUILD_ABLATION=1 python -m speechclip_plus_b200.build)
+// reads the environment.
+static inline int ablation_env(const char* name) {
+#ifdef SCP_ABLATION
+  const char* e = getenv(name);
+  return e ? atoi(e) : 0;
+#else
+  (void)name;
+  return 0;
+#endif
+}
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 static inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }

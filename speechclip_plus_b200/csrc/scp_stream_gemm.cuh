@@ -496,7 +496,7 @@ int launch_stream_gemm(const GemmMaps& maps, const Sched& sched, const typename 
   if (grid <= 0) return SCP_OK;
   Sched sched_dbg = sched;
   {
-    static const int ablate = [] { const char* e = getenv("SCP_DEBUG_ABLATE"); return e ? atoi(e) : 0; }();
+    static const int ablate = scp::ablation_env("SCP_DEBUG_ABLATE");
     sched_dbg.debug = ablate;
   }
   if (MC == MC_X && sched.n_groups % CL != 0) return fail(SCP_ERR_INVALID, "%s: n_groups %% cluster != 0", name);

@@ -1490,7 +1490,7 @@ static int launch_sweep1(const GemmMaps& maps, const Sched& sc, const VqFwdWs& w
   ep.tau = tau;
   ep.e16 = e16;
   ep.ldE = Vp;
-  static const int s1_dbg = [] { const char* e = getenv("SCP_VQ_S1_DBG"); return e ? atoi(e) : 0; }();
+  static const int s1_dbg = ablation_env("SCP_VQ_S1_DBG");
   ep.dbg = s1_dbg;
   ep.n_chunks = ws.n_chunks;
   ep.n_groups = ws.n_groups;
@@ -1772,7 +1772,7 @@ extern "C" int scp_vq_bwd_saved(const float* g_keywords, const float* kw, int64_
     pp.M = M; pp.Mp = Mp;
     pp.fused = ws.pipe_mode == 1;
     pp.ring = ws.ring; pp.sa = ws.sa; pp.sc = ws.sc; pp.uw_slots = ws.uw_slots;
-    static const int pipe_dbg = [] { const char* e = getenv("SCP_PIPE_DEBUG"); return e ? atoi(e) : 0; }();
+    static const int pipe_dbg = ablation_env("SCP_PIPE_DEBUG");
     pp.debug = pipe_dbg;
     pp.scratch = ws.pq;
     pp.ready = ws.flags; pp.done = ws.flags + (size_t)ws.NP * ws.ring;
@@ -1844,7 +1844,7 @@ extern "C" int scp_vq_bwd_saved(const float* g_keywords, const float* kw, int64_
     ep.partials = ws.partials;
     ep.n_groups = sc.n_groups;
     ep.D = (int)D;
-    static const int st_dbg = [] { const char* e = getenv("SCP_VQ_ST_DBG"); return e ? atoi(e) : 0; }();
+    static const int st_dbg = ablation_env("SCP_VQ_ST_DBG");
     ep.dbg = st_dbg;
     rc = vq_sweep_t_resident(D) ? tc::launch_stream_gemm<kVqBN, 1, 5, SweepTEpi, 2, tc::MC_PAIR, 1>(maps, sc, ep, s, "vq_sweep_t")
                                 : tc::launch_stream_gemm<kVqBN, 1, 5, SweepTEpi, 2, tc::MC_PAIR>(maps, sc, ep, s, "vq_sweep_t");

@@ -1,4 +1,7 @@
-"""Time the VQ forward/backward groups under engine ablations (SCP_DEBUG_ABLATE is read once per process)."""
+"""Time the VQ forward/backward groups under engine ablations (SCP_DEBUG_ABLATE is read once per process).
+
+Needs a library built with the ablation switches compiled in: SCP_BUILD_ABLATION=1 python -m speechclip_plus_b200.build
+(a regular build ignores the variable; rebuild without it afterwards)."""
 import os, subprocess, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CODE = r'''
