@@ -212,11 +212,12 @@ __device__ __forceinline__ void load_grad_vec(const TG* p, float* g) {
 
 // ------------------------------------------------------------------------------------------------------------
 // backward, plain: d_l = sum g*x_l ; optional g_l = w_l * g
-// LCAP = compile-time bound on the number of layers (16 or 32): the per-thread accumulators are sized by it, and with
-// 16 (HuBERT-base: 13 layers) the kernel fits three resident blocks per SM instead of two -- half again as many loads in
-// flight, which is what an HBM-bound read-only kernel lives on.
-template <typename TIn, typename TG, int LCAP>
-__global__ void __launch_bounds__(kWsumThreads, LCAP <= 16 ? 3 : 2)
+// LCAP = compile-time bound on the number of layers (16, 25 or 32): the per-thread accumulators are sized by it; G = layers
+// loaded per group (G 16-byte loads in flight per thread).  LCAP + 4 G registers must leave the kernel at <= 85 registers:
+// three resident blocks per SM instead of two -- half again as many loads in flight, which is what an HBM-bound read-only
+// kernel lives on (16 / 8 for HuBERT-base, 25 / 5 for HuBERT-large, 32 / 4 up to SCP_MAX_LAYERS).
+template <typename TIn, typename TG, int LCAP, int G = 8, int MINB = 3>
+__global__ void __launch_bounds__(kWsumThreads, MINB)
 wsum_bwd_plain_kernel(LayerPtrs lp, int L, int64_t n_vec, int vec_per_row, int64_t T, int64_t stride_b,
                       int64_t stride_t, const float* __restrict__ weights, const float* __restrict__ utt_scale,
                       int64_t B, const TG* __restrict__ g_y, float* __restrict__ partials, LayerOutPtrs gl,
@@ -238,15 +239,15 @@ wsum_bwd_plain_kernel(LayerPtrs lp, int L, int64_t n_vec, int vec_per_row, int64
     float g[NE];
     load_grad_vec<TG, NE>(g_y + goff, g);
 #pragma unroll
-    for (int l0 = 0; l0 < LCAP; l0 += 8) {
+    for (int l0 = 0; l0 < LCAP; l0 += G) {
       if (l0 < L) {
-        uint4 raw[8];
+        uint4 raw[G];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (l0 + j < L) raw[j] = ld_stream16(reinterpret_cast<const TIn*>(lp.p[l0 + j]) + off);
+        for (int j = 0; j < G; ++j)
+          if (l0 + j < LCAP && l0 + j < L) raw[j] = ld_stream16(reinterpret_cast<const TIn*>(lp.p[l0 + j]) + off);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (l0 + j < L) {
+        for (int j = 0; j < G; ++j)
+          if (l0 + j < LCAP && l0 + j < L) {
             float f[NE];
             Vec16<TIn>::unpack(raw[j], f);
             float s = 0.f;
@@ -563,10 +564,16 @@ static int launch_bwd(const LayerPtrs& lp, int L, int64_t B, int64_t T, int64_t 
           lp, L, n_vec, vec_per_row, T, sb, st, weights, norm_mode == SCP_NORM_UTT_MEAN ? utt_scale : nullptr, B,
           reinterpret_cast<const TG*>(g_y), partials, gl, write_gl);
     } else {
-      blocks = (int)std::min<int64_t>(ceil_div(n_vec, kWsumThreads), kWsumBwdBlocks);
-      wsum_bwd_plain_kernel<TIn, TG, 32><<<blocks, kWsumThreads, 0, stream>>>(
-          lp, L, n_vec, vec_per_row, T, sb, st, weights, norm_mode == SCP_NORM_UTT_MEAN ? utt_scale : nullptr, B,
-          reinterpret_cast<const TG*>(g_y), partials, gl, write_gl);
+      // 17..32 layers: shorter load groups keep the kernel at 80 registers = three resident blocks per SM as well
+      // (groups of eight need 113: two blocks).  HuBERT-large (25 layers, B*T = 512*249, D = 1024): 2.22 -> 2.01 ms.
+      blocks = (int)std::min<int64_t>(ceil_div(n_vec, kWsumThreads), kNumSMs * 3);
+#define SCP_WB(LC, GG)                                                                                            \
+  wsum_bwd_plain_kernel<TIn, TG, LC, GG, 3><<<blocks, kWsumThreads, 0, stream>>>(                                  \
+      lp, L, n_vec, vec_per_row, T, sb, st, weights, norm_mode == SCP_NORM_UTT_MEAN ? utt_scale : nullptr, B,     \
+      reinterpret_cast<const TG*>(g_y), partials, gl, write_gl)
+      if (L <= 25) SCP_WB(25, 5);
+      else SCP_WB(32, 4);
+#undef SCP_WB
     }
     SCP_CUDA_LAUNCH_CHECK("wsum_bwd_plain");
   } else {

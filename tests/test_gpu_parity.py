@@ -111,7 +111,7 @@ def test_upstream_tail_vs_oracle(scp, shape, ntype, dtype):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("norm", [False, True])
-@pytest.mark.parametrize("shape", [(13, 8, 249, 768), (25, 3, 61, 1024), (5, 2, 7, 64)])
+@pytest.mark.parametrize("shape", [(13, 8, 249, 768), (25, 3, 61, 1024), (5, 2, 7, 64), (17, 2, 33, 256), (29, 2, 33, 512)])
 def test_wsum_vs_oracle(scp, shape, norm, dtype):
     L, B, T, D = shape
     gen = torch.Generator().manual_seed(L * 1000 + T)
